@@ -1,0 +1,164 @@
+"""Freeze outputs of the UNMODIFIED reference as golden fixtures.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/generate_golden.py            # small fixtures, seconds
+    python tests/golden/generate_golden.py --pubmed   # + full C1 config (~2 min, 6 workers)
+
+The reference has no tests or golden vectors of its own, so these
+files ARE the parity pins: every value below is produced by
+/root/reference/utils.py itself, imported verbatim through oracle/ref_shim.py.
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from graphpope_b200 import synth  # noqa: E402
+from oracle.ref_shim import RefData, load_reference_utils  # noqa: E402
+
+
+def micro_graphs():
+    """name -> (num_nodes, edge list, anchors)."""
+    return {
+        # SURVEY §8c known answers: 0->1->2->3, isolated 4
+        "directed_chain": (5, [(0, 1), (1, 2), (2, 3)], [3, 0]),
+        "path_sym": (6, [(i, i + 1) for i in range(5)] + [(i + 1, i) for i in range(5)], [0, 5, 2]),
+        "star_sym": (7, [(0, i) for i in range(1, 7)] + [(i, 0) for i in range(1, 7)], [0, 3]),
+        "two_components": (8, [(0, 1), (1, 0), (1, 2), (2, 1), (4, 5), (5, 4), (5, 6), (6, 5), (6, 7), (7, 6)],
+                           [0, 7, 3]),
+        "self_loop": (4, [(0, 0), (0, 1), (1, 2), (2, 2), (3, 3)], [2, 3, 0]),
+        "duplicate_edge": (4, [(0, 1), (0, 1), (1, 2), (1, 2), (2, 3), (0, 1)], [3, 1]),
+        "isolated_and_dup_anchor": (5, [(0, 1), (1, 0), (2, 3)], [1, 1, 4, 3, 1]),
+        "in_star_directed": (5, [(1, 0), (2, 0), (3, 0), (4, 0)], [0, 1]),
+        "out_star_directed": (5, [(0, 1), (0, 2), (0, 3), (0, 4)], [0, 1]),
+        "cycle_directed": (5, [(0, 1), (1, 2), (2, 3), (3, 4), (4, 0)], [0, 2]),
+    }
+
+
+def ref_rows(utils, n, edges, anchors):
+    ei = torch.tensor(np.asarray(edges, dtype=np.int64).reshape(-1, 2).T.copy())
+    data = RefData(ei, n)
+    G = utils.to_networkx(data)
+    rows = utils.shortest_path_length(G, anchors, list(range(n)))
+    return np.asarray([rows[i] for i in range(n)], dtype=np.float64)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--pubmed", action="store_true")
+    args = ap.parse_args()
+    utils = load_reference_utils()
+    out = {}
+
+    # 1. micro graphs through utils.shortest_path_length (utils.py:64-81)
+    for name, (n, edges, anchors) in micro_graphs().items():
+        out[f"micro/{name}/n"] = np.int64(n)
+        out[f"micro/{name}/edges"] = np.asarray(edges, dtype=np.int64).reshape(-1, 2).T
+        out[f"micro/{name}/anchors"] = np.asarray(anchors, dtype=np.int64)
+        out[f"micro/{name}/rows_f64"] = ref_rows(utils, n, edges, anchors)
+
+    # 2. full geodesic pipeline, asymmetric multigraph, seed-42 stochastic anchors
+    n, k = 300, 8
+    ei = synth.random_digraph(n, 900, seed=7)
+    x = np.random.default_rng(11).standard_normal((n, 5)).astype(np.float32)
+    data = RefData(torch.tensor(ei), n, torch.tensor(x))
+    np.random.seed(42)
+    feats = utils.attach_distance_embedding(data, "toy", k, "stochastic", None, 2)
+    out["toy/n"] = np.int64(n)
+    out["toy/edge_index"] = ei
+    out["toy/x"] = x
+    out["toy/anchors"] = np.asarray(data.anchor_nodes, dtype=np.int64)
+    out["toy/features"] = feats.numpy()
+    assert feats.dtype == torch.float32 and tuple(feats.shape) == (n, 5 + k)
+
+    # 2b. same graph, symmetric variant (pull == push direction) with K=70 (two lane words)
+    ei_sym = np.concatenate([ei, ei[::-1]], axis=1)
+    data = RefData(torch.tensor(ei_sym), n, torch.tensor(x))
+    np.random.seed(43)
+    data.anchor_nodes = utils.sample_anchor_nodes(data, 70, "stochastic")
+    emb = utils.get_geodesic_distance_vector(data, 2)
+    out["toysym/edge_index"] = ei_sym
+    out["toysym/anchors"] = np.asarray(data.anchor_nodes, dtype=np.int64)
+    out["toysym/embedding"] = emb.numpy().astype(np.float32)
+
+    # 3. samplers on a 2000-node graph (ties at the cut are the norm)
+    n3 = 2000
+    ei3 = synth.chung_lu_symmetric(n3, 12000, 2.2, seed=21)
+    ei3 = np.concatenate([ei3, synth.random_digraph(n3, 500, seed=22)], axis=1)  # asymmetric part
+    data3 = RefData(torch.tensor(ei3), n3)
+    out["samplers/n"] = np.int64(n3)
+    out["samplers/edge_index"] = ei3
+    for k3 in (1, 16, 64, 256):
+        out[f"samplers/degree_centrality/{k3}"] = np.asarray(
+            utils.sample_anchor_nodes(data3, k3, "degree_centrality"), dtype=np.int64)
+        out[f"samplers/pagerank/{k3}"] = np.asarray(
+            utils.sample_anchor_nodes(data3, k3, "pagerank"), dtype=np.int64)
+    import networkx as nx
+    G3 = utils.to_networkx(data3)
+    pr = nx.pagerank(G3)
+    out["samplers/pagerank_scores"] = np.asarray([pr[i] for i in range(n3)], dtype=np.float64)
+    out["samplers/degree"] = np.asarray([G3.degree(i) for i in range(n3)], dtype=np.int64)
+    np.random.seed(42)
+    out["samplers/stochastic_89250_256"] = np.asarray(
+        utils.sample_anchor_nodes(RefData(None, 89250), 256, "stochastic"), dtype=np.int64)
+    np.random.seed(42)
+    out["samplers/stochastic_300_8"] = np.asarray(
+        utils.sample_anchor_nodes(RefData(None, 300), 8, "stochastic"), dtype=np.int64)
+
+    # 4. node2vec branch (utils.py:149-180) with torch.load patched to serve the table
+    n4, d4, k4 = 400, 128, 12
+    table = synth.node2vec_table(n4, d4, seed=3)
+    x4 = np.random.default_rng(12).standard_normal((n4, 3)).astype(np.float32)
+    real_load = torch.load
+    torch.load = lambda *a, **kw: torch.tensor(table)
+    try:
+        for fn in ("distance", "similarity", "euclidean"):
+            data4 = RefData(None, n4, torch.tensor(x4))
+            np.random.seed(5)
+            f4 = utils.attach_node2vec(data4, "toy", k4, "stochastic", fn, 2)
+            out[f"node2vec/{fn}"] = f4.numpy()
+            assert f4.dtype == torch.float32, f4.dtype
+    finally:
+        torch.load = real_load
+    np.random.seed(5)
+    out["node2vec/anchors"] = np.asarray(np.random.choice(np.arange(n4), k4), dtype=np.int64)
+    out["node2vec/table_seed"] = np.int64(3)
+    out["node2vec/x"] = x4
+
+    np.savez_compressed(os.path.join(HERE, "reference_small.npz"), **out)
+    print("wrote reference_small.npz with", len(out), "arrays")
+
+    if args.pubmed:
+        # 5. C1: Pubmed-shape, K=256, reference verbatim with num_workers=6
+        import time
+        shape = synth.PUBMED_SHAPE
+        ei5 = synth.make_graph(shape)
+        data5 = RefData(torch.tensor(ei5), shape.num_nodes)
+        np.random.seed(42)
+        data5.anchor_nodes = utils.sample_anchor_nodes(data5, 256, "stochastic")
+        t0 = time.time()
+        emb5 = utils.get_geodesic_distance_vector(data5, 6).numpy().astype(np.float32)
+        dt = time.time() - t0
+        rows = np.arange(0, shape.num_nodes, 97)
+        np.savez_compressed(
+            os.path.join(HERE, "reference_pubmed_shape.npz"),
+            anchors=np.asarray(data5.anchor_nodes, dtype=np.int64),
+            sha256=np.frombuffer(hashlib.sha256(np.ascontiguousarray(emb5).tobytes()).digest(), dtype=np.uint8),
+            sample_rows=rows, sample=emb5[rows],
+            column_sums=emb5.astype(np.float64).sum(axis=0),
+            seconds=np.float64(dt), num_workers=np.int64(6))
+        print("wrote reference_pubmed_shape.npz; reference took %.1f s" % dt)
+
+
+if __name__ == "__main__":
+    main()

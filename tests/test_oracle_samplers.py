@@ -1,0 +1,42 @@
+"""Pin the sampler restatements to anchor lists produced by the reference."""
+import numpy as np
+
+from graphpope_b200 import synth
+from oracle import samplers as s
+
+
+def test_stochastic_matches_reference_stream(golden_small):
+    np.random.seed(42)
+    assert np.array_equal(s.stochastic(89250, 256), golden_small["samplers/stochastic_89250_256"])
+    assert np.array_equal(synth.stochastic_anchors(89250, 256, 42)[:8],
+                          [15795, 860, 76820, 54886, 6265, 82386, 37194, 87498])
+    # np.random.choice(arange(N), K) consumes the same stream as randint(0, N, K)
+    np.random.seed(42)
+    assert np.array_equal(np.random.randint(0, 89250, 256), golden_small["samplers/stochastic_89250_256"])
+
+
+def test_degree_centrality_matches_reference(golden_small):
+    ei = golden_small["samplers/edge_index"]
+    n = int(golden_small["samplers/n"])
+    assert np.array_equal(s.degree_scores(ei, n), golden_small["samplers/degree"])
+    for k in (1, 16, 64, 256):
+        assert s.degree_centrality_anchors(ei, n, k) == golden_small[f"samplers/degree_centrality/{k}"].tolist()
+
+
+def test_pagerank_matches_reference(golden_small):
+    ei = golden_small["samplers/edge_index"]
+    n = int(golden_small["samplers/n"])
+    x, iters = s.pagerank_scores(ei, n)
+    assert 1 <= iters <= 100
+    want = golden_small["samplers/pagerank_scores"]
+    assert np.abs(x - want).sum() < 1e-12
+    assert np.array_equal(x, want)  # same operation order -> bit-equal float64
+    for k in (1, 16, 64, 256):
+        assert s.pagerank_anchors(ei, n, k) == golden_small[f"samplers/pagerank/{k}"].tolist()
+
+
+def test_top_k_quirks():
+    score = np.array([3, 1, 3, 2, 3])
+    assert s.stable_top_k(score, 2) == [2, 4]          # ties -> larger ids, ascending score order
+    assert s.stable_top_k(score, 0) == [1, 3, 0, 2, 4]  # list[-0:] is the whole list
+    assert s.stable_top_k(score, 9) == [1, 3, 0, 2, 4]
