@@ -1,0 +1,205 @@
+// gp_api.cu — library-level entry points of the C ABI: errors, device info and the one-call
+// host-buffer path that stands in for get_geodesic_distance_vector + concat_into_features
+// (reference utils.py:116-135).
+#include "gp_msbfs.cuh"
+
+#include <algorithm>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace {
+thread_local char g_err[512] = "";
+int g_sm_count = 0;
+}  // namespace
+
+void gp_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int gp_sm_count()
+{
+    if (g_sm_count == 0) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            g_sm_count = sms;
+        else
+            return 148;
+    }
+    return g_sm_count;
+}
+
+extern "C" int gp_abi_version(void) { return GP_ABI_VERSION; }
+
+extern "C" const char *gp_last_error(void) { return g_err; }
+
+extern "C" const char *gp_status_string(int status)
+{
+    switch (status) {
+        case GP_OK: return "ok";
+        case GP_ERR_INVALID: return "invalid argument";
+        case GP_ERR_CUDA: return "CUDA runtime error";
+        case GP_ERR_OOM: return "out of memory";
+        case GP_ERR_INDEX_RANGE: return "index outside [0, num_nodes)";
+        case GP_ERR_LEVEL_OVERFLOW: return "hop distance does not fit uint16";
+        case GP_ERR_UNSUPPORTED: return "unsupported size or option";
+        case GP_ERR_NOT_CONVERGED: return "power iteration failed to converge";
+        case GP_ERR_NO_DEVICE: return "no usable CUDA device";
+        default: return "unknown status";
+    }
+}
+
+extern "C" int gp_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, char *name,
+                              int64_t name_cap)
+{
+    int dev = 0, count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        gp_set_error("no CUDA device is visible to this process");
+        return GP_ERR_NO_DEVICE;
+    }
+    GP_CUDA_CHECK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    GP_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (name && name_cap > 0) {
+        strncpy(name, prop.name, (size_t)name_cap - 1);
+        name[name_cap - 1] = 0;
+    }
+    return GP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// One-call host path.  A small cache keeps the handles, device staging and the stream alive
+// between calls of the same shape so repeated calls pay no allocation.
+namespace {
+
+struct HostCtx {
+    int64_t n = -1, e_cap = -1, k_cap = -1;
+    uint32_t flags = 0;
+    gp_csr *csr = nullptr;
+    gp_msbfs *bfs = nullptr;
+    int64_t *d_edges = nullptr;
+    int64_t *d_anchors = nullptr;
+    float *d_feat = nullptr;
+    uint16_t *d_hops = nullptr;
+    cudaStream_t stream = nullptr;
+
+    void release()
+    {
+        gp_msbfs_free(bfs);
+        gp_csr_free(csr);
+        cudaFree(d_edges);
+        cudaFree(d_anchors);
+        cudaFree(d_feat);
+        cudaFree(d_hops);
+        bfs = nullptr;
+        csr = nullptr;
+        d_edges = nullptr;
+        d_anchors = nullptr;
+        d_feat = nullptr;
+        d_hops = nullptr;
+        n = e_cap = k_cap = -1;
+    }
+};
+
+HostCtx g_ctx;
+std::mutex g_ctx_mutex;
+
+int ensure_ctx(int64_t n, int64_t e, int64_t k, uint32_t flags)
+{
+    HostCtx &c = g_ctx;
+    if (c.stream == nullptr) GP_CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    if (c.n == n && c.flags == flags && e <= c.e_cap && k <= c.k_cap) return GP_OK;
+    c.release();
+    GP_TRY(gp_csr_create(n, e, flags, &c.csr));
+    GP_TRY(gp_msbfs_create(c.csr, k, &c.bfs));
+    GP_CUDA_CHECK(cudaMalloc(&c.d_edges, sizeof(int64_t) * (size_t)std::max<int64_t>(2 * e, 2)));
+    GP_CUDA_CHECK(cudaMalloc(&c.d_anchors, sizeof(int64_t) * (size_t)std::max<int64_t>(k, 1)));
+    GP_CUDA_CHECK(cudaMalloc(&c.d_feat, sizeof(float) * (size_t)std::max<int64_t>(n * k, 1)));
+    GP_CUDA_CHECK(cudaMalloc(&c.d_hops, sizeof(uint16_t) * (size_t)std::max<int64_t>(n * k, 1)));
+    c.n = n;
+    c.e_cap = e;
+    c.k_cap = k;
+    c.flags = flags;
+    return GP_OK;
+}
+
+void copy_rows_parallel(const float *src, int64_t ld_src, float *dst, int64_t ld_dst, int64_t rows,
+                        int64_t cols)
+{
+    if (rows <= 0 || cols <= 0) return;
+    const int64_t total = rows * cols;
+    int nt = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    if (total < (1 << 20)) nt = 1;
+    auto work = [=](int64_t r0, int64_t r1) {
+        for (int64_t r = r0; r < r1; ++r)
+            memcpy(dst + r * ld_dst, src + r * ld_src, (size_t)cols * sizeof(float));
+    };
+    if (nt == 1) {
+        work(0, rows);
+        return;
+    }
+    std::vector<std::thread> th;
+    const int64_t chunk = gp_ceil_div(rows, nt);
+    for (int t = 0; t < nt; ++t) {
+        const int64_t r0 = t * chunk, r1 = std::min(rows, r0 + chunk);
+        if (r0 < r1) th.emplace_back(work, r0, r1);
+    }
+    for (auto &t : th) t.join();
+}
+
+}  // namespace
+
+extern "C" int gp_geodesic_embed_host(const int64_t *h_edge_index, int64_t num_edges, int64_t num_nodes,
+                                      uint32_t csr_flags, const int64_t *h_anchors, int64_t num_anchors,
+                                      const float *h_x, int64_t num_features, float *h_out, int64_t ld_out,
+                                      int64_t col_offset, uint16_t *h_hops, gp_msbfs_stats_t *stats)
+{
+    GP_REQUIRE(num_edges >= 0 && num_nodes >= 0 && num_anchors >= 0 && num_features >= 0, GP_ERR_INVALID,
+               "gp_geodesic_embed_host: negative size");
+    GP_REQUIRE(num_edges == 0 || h_edge_index != nullptr, GP_ERR_INVALID, "edge_index is NULL");
+    GP_REQUIRE(num_anchors == 0 || h_anchors != nullptr, GP_ERR_INVALID, "anchors is NULL");
+    GP_REQUIRE(h_out != nullptr || num_nodes == 0 || (num_anchors == 0 && h_x == nullptr), GP_ERR_INVALID,
+               "out is NULL");
+    GP_REQUIRE(col_offset >= 0 && ld_out >= col_offset + num_anchors && (h_x == nullptr || col_offset >= num_features),
+               GP_ERR_INVALID, "gp_geodesic_embed_host: inconsistent ld_out / col_offset");
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    GP_TRY(ensure_ctx(num_nodes, num_edges, num_anchors, csr_flags));
+    HostCtx &c = g_ctx;
+    cudaStream_t s = c.stream;
+    if (num_edges > 0)
+        GP_CUDA_CHECK(cudaMemcpyAsync(c.d_edges, h_edge_index, sizeof(int64_t) * 2 * (size_t)num_edges,
+                                      cudaMemcpyHostToDevice, s));
+    if (num_anchors > 0)
+        GP_CUDA_CHECK(cudaMemcpyAsync(c.d_anchors, h_anchors, sizeof(int64_t) * (size_t)num_anchors,
+                                      cudaMemcpyHostToDevice, s));
+    GP_TRY(gp_csr_build(c.csr, c.d_edges, num_edges, s));
+    GP_TRY(gp_msbfs_run(c.bfs, c.d_anchors, num_anchors, s));
+    if (num_nodes > 0 && num_anchors > 0) {
+        GP_TRY(gp_msbfs_features(c.bfs, nullptr, 0, 0, c.d_feat, num_anchors, 0, s));
+        if (h_hops) GP_TRY(gp_msbfs_hops_u16(c.bfs, c.d_hops, num_anchors, 0, s));
+    }
+    // The feature block lands in columns [col_offset, col_offset + K); enqueue its copy first so
+    // that (with pinned h_out) it overlaps the host-side concat below.
+    if (num_nodes > 0 && num_anchors > 0) {
+        GP_CUDA_CHECK(cudaMemcpy2DAsync(h_out + col_offset, sizeof(float) * (size_t)ld_out, c.d_feat,
+                                        sizeof(float) * (size_t)num_anchors, sizeof(float) * (size_t)num_anchors,
+                                        (size_t)num_nodes, cudaMemcpyDeviceToHost, s));
+        if (h_hops)
+            GP_CUDA_CHECK(cudaMemcpyAsync(h_hops, c.d_hops, sizeof(uint16_t) * (size_t)(num_nodes * num_anchors),
+                                          cudaMemcpyDeviceToHost, s));
+    }
+    // concat_into_features (utils.py:129-135): x goes into columns [0, F) on the host.
+    if (h_x != nullptr) copy_rows_parallel(h_x, num_features, h_out, ld_out, num_nodes, num_features);
+    gp_msbfs_stats_t local;
+    GP_TRY(gp_msbfs_stats(c.bfs, stats ? stats : &local, s));  // synchronises and reports device errors
+    return GP_OK;
+}

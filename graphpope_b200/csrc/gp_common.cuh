@@ -1,0 +1,110 @@
+// gp_common.cuh — shared host/device helpers for the graphpope_b200 kernels (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/graphpope_b200.h"
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// ---------------------------------------------------------------- host-side errors
+void gp_set_error(const char *fmt, ...);
+
+#define GP_CUDA_CHECK(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            gp_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),         \
+                         __FILE__, __LINE__);                                            \
+            return (_e == cudaErrorMemoryAllocation) ? GP_ERR_OOM : GP_ERR_CUDA;         \
+        }                                                                                \
+    } while (0)
+
+#define GP_REQUIRE(cond, status, ...)                                                    \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            gp_set_error(__VA_ARGS__);                                                   \
+            return (status);                                                             \
+        }                                                                                \
+    } while (0)
+
+#define GP_TRY(expr)                                                                     \
+    do {                                                                                 \
+        int _s = (expr);                                                                 \
+        if (_s != GP_OK) return _s;                                                      \
+    } while (0)
+
+static inline int64_t gp_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Device-latched error bits (status words live in handle-owned device memory).
+enum : int { GP_DEV_ERR_EDGE_RANGE = 1, GP_DEV_ERR_ANCHOR_RANGE = 2, GP_DEV_ERR_LEVEL_OVERFLOW = 4 };
+
+int gp_sm_count();  // cached multiProcessorCount of the current device
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+
+constexpr u32 FULL_MASK = 0xFFFFFFFFu;
+
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31u; }
+
+__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m)
+{
+    u32 lo = (u32)v, hi = (u32)(v >> 32);
+    lo = __shfl_xor_sync(FULL_MASK, lo, m);
+    hi = __shfl_xor_sync(FULL_MASK, hi, m);
+    return ((u64)hi << 32) | lo;
+}
+
+__device__ __forceinline__ u64 warp_or_u64(u64 v)
+{
+    u32 lo = __reduce_or_sync(FULL_MASK, (u32)v);
+    u32 hi = __reduce_or_sync(FULL_MASK, (u32)(v >> 32));
+    return ((u64)hi << 32) | lo;
+}
+
+__device__ __forceinline__ u32 ld_acquire_u32(const u32 *p)
+{
+    u32 v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ u32 ld_relaxed_u32(const u32 *p)
+{
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_relaxed_u32(u32 *p, u32 v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void red_release_add_u32(u32 *p, u32 v)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Grid-wide barrier for a cooperatively launched (co-resident) grid.  `counter`
+// is a zero-initialised device word that only ever grows; `target` is the
+// caller's running arrival target (per thread, all threads keep the same value).
+__device__ __forceinline__ void grid_barrier(u32 *counter, u32 &target, u32 nblocks)
+{
+    target += nblocks;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        red_release_add_u32(counter, 1u);
+        while (ld_acquire_u32(counter) < target) {
+        }
+    }
+    __syncthreads();
+}
+
+#endif  // __CUDACC__

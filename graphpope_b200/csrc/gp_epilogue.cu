@@ -1,0 +1,258 @@
+// gp_epilogue.cu — fused normalise / unreachable-fill / concat epilogue and the uint16 decode.
+//
+// Reproduces the reference value convention (utils.py:72-76): value = 1/len(path) = 1/(d+1),
+// anchor itself = 1.0, no path = 0; float32 output (utils.py:125) — computed here as IEEE
+// fp32 1.0f/(float)(d+1), which is bit-identical to the reference's float64 divide followed
+// by the float32 rounding of torch.as_tensor for every d+1 in [1, 65536].  Also performs
+// concat_into_features (utils.py:129-135) by streaming x into columns [0, F) of the same
+// output rows, so each [N, F+K] row is written once, contiguously.
+//
+// Input is the bit-sliced result of gp_msbfs.cu (plane 0 = reached mask, plane 1+p = bit p
+// of the hop distance); HBM-bound: reads (1+P)*N*K/8 bytes of planes (+4NF of x), writes
+// 4*N*(F+K) bytes.
+#include "gp_msbfs.cuh"
+
+namespace {
+
+__device__ __forceinline__ float inv_hops(u32 d)
+{
+    return __fdiv_rn(1.0f, __uint2float_rn(d + 1u));
+}
+
+__device__ __forceinline__ int dist_planes(const GpDecodeParams &p)
+{
+    if (p.num_dist_planes >= 0) return p.num_dist_planes;
+    const int ml = p.status[GP_BFS_ST_MAX_LEVEL];
+    return ml > 0 ? 32 - __clz(ml) : 0;
+}
+
+// Word that holds column j (global anchor index) of node u, and the bit inside it.
+__device__ __forceinline__ const u64 *lane_word(const GpDecodeParams &p, long long u, long long j, int &bit)
+{
+    const long long r = j / p.anchors_per_rank, jl = j - r * p.anchors_per_rank;
+    const long long b = jl / (64 * p.wb);
+    const int w = (int)((jl >> 6) % p.wb);
+    bit = (int)(jl & 63);
+    return p.planes0 + r * p.rank_stride + ((size_t)b * p.n + (size_t)u) * p.wb + w;
+}
+
+__device__ __forceinline__ float decode_one(const GpDecodeParams &p, int np, long long u, long long j)
+{
+    int bit;
+    const u64 *w = lane_word(p, u, j, bit);
+    if (!((w[0] >> bit) & 1ull)) return 0.0f;
+    u32 d = 0;
+    for (int q = 0; q < np; ++q) d |= (u32)((w[(size_t)(q + 1) * p.plane_stride] >> bit) & 1ull) << q;
+    return inv_hops(d);
+}
+
+// One warp per output row.
+__global__ void __launch_bounds__(256) decode_features_kernel(GpDecodeParams p, long long k_total, int vec_x,
+                                                              int vec_f)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int np = dist_planes(p);
+    for (long long u = warp; u < p.n; u += nwarps) {
+        float *orow = p.out + (size_t)u * p.ld_out;
+        if (p.x != nullptr) {
+            const float *xrow = p.x + (size_t)u * p.ld_x;
+            if (vec_x) {
+                const float4 *x4 = reinterpret_cast<const float4 *>(xrow);
+                float4 *o4 = reinterpret_cast<float4 *>(orow);
+                const int q = (int)(p.num_features >> 2);
+                for (int i = lane; i < q; i += 32) o4[i] = __ldg(x4 + i);
+                for (long long i = ((long long)q << 2) + lane; i < p.num_features; i += 32) orow[i] = __ldg(xrow + i);
+            } else {
+                for (long long i = lane; i < p.num_features; i += 32) orow[i] = __ldg(xrow + i);
+            }
+        }
+        float *frow = orow + p.col_offset;
+        if (vec_f) {
+            // groups of 4 columns never straddle a lane word or a rank (anchors_per_rank % 4 == 0)
+            const long long groups = k_total >> 2;
+            for (long long g = lane; g < groups; g += 32) {
+                const long long j0 = g << 2;
+                int bit;
+                const u64 *w = lane_word(p, u, j0, bit);
+                const u32 reach = (u32)(w[0] >> bit) & 0xFu;
+                u32 d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+                if (reach) {
+                    for (int q = 0; q < np; ++q) {
+                        const u32 nib = (u32)(w[(size_t)(q + 1) * p.plane_stride] >> bit) & 0xFu;
+                        d0 |= (nib & 1u) << q;
+                        d1 |= ((nib >> 1) & 1u) << q;
+                        d2 |= ((nib >> 2) & 1u) << q;
+                        d3 |= ((nib >> 3) & 1u) << q;
+                    }
+                }
+                float4 v;
+                v.x = (reach & 1u) ? inv_hops(d0) : 0.0f;
+                v.y = (reach & 2u) ? inv_hops(d1) : 0.0f;
+                v.z = (reach & 4u) ? inv_hops(d2) : 0.0f;
+                v.w = (reach & 8u) ? inv_hops(d3) : 0.0f;
+                reinterpret_cast<float4 *>(frow)[g] = v;
+            }
+            for (long long j = (groups << 2) + lane; j < k_total; j += 32) frow[j] = decode_one(p, np, u, j);
+        } else {
+            for (long long j = lane; j < k_total; j += 32) frow[j] = decode_one(p, np, u, j);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) decode_u16_kernel(GpDecodeParams p, long long k_total, uint16_t *dist,
+                                                         long long ld, long long col_offset)
+{
+    const int np = dist_planes(p);
+    const long long total = p.n * k_total;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long u = i / k_total, j = i - u * k_total;
+        int bit;
+        const u64 *w = lane_word(p, u, j, bit);
+        u32 d = GP_UNREACHABLE_U16;
+        if ((w[0] >> bit) & 1ull) {
+            d = 0;
+            for (int q = 0; q < np; ++q) d |= (u32)((w[(size_t)(q + 1) * p.plane_stride] >> bit) & 1ull) << q;
+        }
+        dist[(size_t)u * ld + col_offset + j] = (uint16_t)d;
+    }
+}
+
+__global__ void __launch_bounds__(256) normalize_u16_kernel(const uint16_t *__restrict__ dist, long long n,
+                                                            long long k, long long ld_dist,
+                                                            float *__restrict__ out, long long ld_out,
+                                                            long long col_offset)
+{
+    const long long total = n * k;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long u = i / k, j = i - u * k;
+        const u32 d = dist[(size_t)u * ld_dist + j];
+        out[(size_t)u * ld_out + col_offset + j] = d == GP_UNREACHABLE_U16 ? 0.0f : inv_hops(d);
+    }
+}
+
+int grid_for(long long work_items, int per_block)
+{
+    long long b = gp_ceil_div(work_items > 0 ? work_items : 1, per_block);
+    const long long cap = (long long)gp_sm_count() * 8;
+    return (int)(b < cap ? b : cap);
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+int gp_launch_decode_features(const GpDecodeParams &p, cudaStream_t stream)
+{
+    const long long k_total = p.anchors_per_rank * p.num_ranks;
+    if (p.n == 0 || (k_total == 0 && (p.x == nullptr || p.num_features == 0))) return GP_OK;
+    const int vec_x = p.x != nullptr && aligned16(p.x) && aligned16(p.out) && (p.ld_x % 4 == 0) &&
+                      (p.ld_out % 4 == 0);
+    const int vec_f = aligned16(p.out) && (p.ld_out % 4 == 0) && (p.col_offset % 4 == 0) &&
+                      (p.anchors_per_rank % 4 == 0 || p.num_ranks == 1);
+    decode_features_kernel<<<grid_for(p.n, 8), 256, 0, stream>>>(p, k_total, vec_x, vec_f);
+    GP_CUDA_CHECK(cudaGetLastError());
+    return GP_OK;
+}
+
+static GpDecodeParams local_params(gp_msbfs *h)
+{
+    GpDecodeParams p;
+    memset(&p, 0, sizeof(p));
+    p.planes0 = h->seen;
+    p.rank_stride = 0;
+    p.plane_stride = (long long)h->wb * h->batches * h->num_nodes;
+    p.num_ranks = 1;
+    p.num_dist_planes = -1;
+    p.status = h->status;
+    p.n = h->num_nodes;
+    p.anchors_per_rank = h->num_anchors;
+    p.wb = h->wb;
+    return p;
+}
+
+extern "C" int gp_msbfs_features(gp_msbfs_t *h, const float *d_x, int64_t num_features, int64_t ld_x,
+                                 float *d_out, int64_t ld_out, int64_t col_offset, gp_stream_t stream_)
+{
+    GP_REQUIRE(h != nullptr && d_out != nullptr, GP_ERR_INVALID, "gp_msbfs_features: NULL argument");
+    GP_REQUIRE(h->ran, GP_ERR_INVALID, "gp_msbfs_features: gp_msbfs_run has not been called");
+    GP_REQUIRE(num_features >= 0 && col_offset >= 0 && ld_out >= col_offset + h->num_anchors &&
+                   (d_x == nullptr || (ld_x >= num_features && ld_out >= num_features)),
+               GP_ERR_INVALID, "gp_msbfs_features: inconsistent leading dimensions");
+    GpDecodeParams p = local_params(h);
+    p.x = d_x;
+    p.num_features = d_x ? num_features : 0;
+    p.ld_x = ld_x;
+    p.out = d_out;
+    p.ld_out = ld_out;
+    p.col_offset = col_offset;
+    return gp_launch_decode_features(p, (cudaStream_t)stream_);
+}
+
+extern "C" int gp_msbfs_hops_u16(gp_msbfs_t *h, uint16_t *d_dist, int64_t ld, int64_t col_offset,
+                                 gp_stream_t stream_)
+{
+    GP_REQUIRE(h != nullptr && d_dist != nullptr, GP_ERR_INVALID, "gp_msbfs_hops_u16: NULL argument");
+    GP_REQUIRE(h->ran, GP_ERR_INVALID, "gp_msbfs_hops_u16: gp_msbfs_run has not been called");
+    GP_REQUIRE(col_offset >= 0 && ld >= col_offset + h->num_anchors, GP_ERR_INVALID,
+               "gp_msbfs_hops_u16: leading dimension too small");
+    if (h->num_nodes == 0 || h->num_anchors == 0) return GP_OK;
+    GpDecodeParams p = local_params(h);
+    decode_u16_kernel<<<grid_for(p.n * h->num_anchors, 256), 256, 0, (cudaStream_t)stream_>>>(
+        p, h->num_anchors, d_dist, ld, col_offset);
+    GP_CUDA_CHECK(cudaGetLastError());
+    return GP_OK;
+}
+
+extern "C" int gp_decode_gathered(const uint64_t *d_gathered, int64_t rank_stride_words, int32_t num_ranks,
+                                  int64_t num_nodes, int64_t anchors_per_rank, int32_t num_planes,
+                                  int32_t batches, int32_t words_per_batch, int64_t plane_stride_words,
+                                  const float *d_x, int64_t num_features, int64_t ld_x, float *d_out,
+                                  int64_t ld_out, int64_t col_offset, gp_stream_t stream_)
+{
+    GP_REQUIRE(d_gathered != nullptr && d_out != nullptr, GP_ERR_INVALID, "gp_decode_gathered: NULL argument");
+    GP_REQUIRE(num_ranks >= 1 && num_nodes >= 0 && anchors_per_rank >= 0 && num_planes >= 1 &&
+                   num_planes <= 1 + GP_BFS_PLANES && batches >= 1 &&
+                   (words_per_batch == 1 || words_per_batch == 2 || words_per_batch == 4),
+               GP_ERR_INVALID, "gp_decode_gathered: bad shape arguments");
+    GP_REQUIRE(anchors_per_rank <= (int64_t)batches * words_per_batch * 64, GP_ERR_INVALID,
+               "gp_decode_gathered: anchors_per_rank exceeds the lane capacity of a shard");
+    GP_REQUIRE(ld_out >= col_offset + anchors_per_rank * num_ranks, GP_ERR_INVALID,
+               "gp_decode_gathered: ld_out too small");
+    GpDecodeParams p;
+    memset(&p, 0, sizeof(p));
+    p.planes0 = (const u64 *)d_gathered;
+    p.rank_stride = rank_stride_words;
+    p.plane_stride = plane_stride_words;
+    p.num_ranks = num_ranks;
+    p.num_dist_planes = num_planes - 1;
+    p.status = nullptr;
+    p.n = num_nodes;
+    p.anchors_per_rank = anchors_per_rank;
+    p.wb = words_per_batch;
+    p.x = d_x;
+    p.num_features = d_x ? num_features : 0;
+    p.ld_x = ld_x;
+    p.out = d_out;
+    p.ld_out = ld_out;
+    p.col_offset = col_offset;
+    return gp_launch_decode_features(p, (cudaStream_t)stream_);
+}
+
+extern "C" int gp_normalize_into(const uint16_t *d_dist, int64_t num_nodes, int64_t num_anchors,
+                                 int64_t ld_dist, float *d_out, int64_t ld_out, int64_t col_offset,
+                                 gp_stream_t stream_)
+{
+    GP_REQUIRE(d_dist != nullptr && d_out != nullptr, GP_ERR_INVALID, "gp_normalize_into: NULL argument");
+    GP_REQUIRE(num_nodes >= 0 && num_anchors >= 0 && ld_dist >= num_anchors && col_offset >= 0 &&
+                   ld_out >= col_offset + num_anchors,
+               GP_ERR_INVALID, "gp_normalize_into: inconsistent sizes");
+    if (num_nodes == 0 || num_anchors == 0) return GP_OK;
+    normalize_u16_kernel<<<grid_for(num_nodes * num_anchors, 256), 256, 0, (cudaStream_t)stream_>>>(
+        d_dist, num_nodes, num_anchors, ld_dist, d_out, ld_out, col_offset);
+    GP_CUDA_CHECK(cudaGetLastError());
+    return GP_OK;
+}

@@ -1,0 +1,246 @@
+"""Drop-in mirror of the reference's ``utils.py`` embedding helpers, backed by the B200 library.
+
+Same names, argument meaning, side effects and error behaviour as
+JeroendenBoef/GraphPOPE ``utils.py`` (citations are file:line into the reference):
+
+    sample_anchor_nodes                      utils.py:18-62
+    shortest_path_length                     utils.py:64-81
+    merge_dicts                              utils.py:83-90
+    all_pairs_shortest_path_length_parallel  utils.py:92-114
+    get_geodesic_distance_vector             utils.py:116-126
+    concat_into_features                     utils.py:129-135
+    attach_distance_embedding                utils.py:137-147
+    attach_node2vec                          utils.py:149-180
+    Graphpope                                utils.py:182-210
+
+``main.py`` keeps ``from utils import Graphpope`` and its flags (``--embedding_space``,
+``--sampling_method``, ``--num_anchor_nodes``, ``--distance_function``,
+``--num_workers``, main.py:34-39) unchanged; ``num_workers`` is accepted and ignored —
+the CPU process pool it sized (utils.py:98) is replaced by one multi-source BFS on the GPU.
+
+What runs where
+  * geodesic distances, 1/(d+1) normalisation, concat: device (libgraphpope_b200.so).
+  * ``stochastic`` anchors: host numpy global RNG, exactly utils.py:22-24 (same seed, same anchors).
+  * ``degree_centrality`` / ``pagerank`` anchors: device (CSR row-pointer differences, float64 SpMV power
+    iteration, stable top-k).
+  * betweenness / eigenvector / closeness / clustering anchors and KMeans centres: the reference's own
+    networkx / scikit-learn calls on the host (stated scope of the port).
+There is no CPU fallback for the device parts: without the CUDA library or a GPU these functions raise.
+"""
+from __future__ import annotations
+
+import os
+import os.path as osp
+
+import numpy as np
+import torch
+
+from . import device as _dev
+from . import _lib
+
+# Opt-in symmetrisation (north_star wording); the default keeps the reference's DiGraph semantics
+# (utils.py:121).  It is the identity on Flickr / PubMed / ogbn-products, whose edge_index is symmetric.
+SYMMETRIZE = os.environ.get("GRAPHPOPE_SYMMETRIZE", "0") == "1"
+VERBOSE = os.environ.get("GRAPHPOPE_QUIET", "0") != "1"
+
+_HOST_CENTRALITIES = ("betweenness_centrality", "eigenvector_centrality", "closeness_centrality",
+                      "clustering_coefficient")
+
+last_stats: dict = {}  # stats of the most recent MS-BFS (levels, edges examined, ...)
+
+
+def _say(msg):
+    if VERBOSE:
+        print(msg)
+
+
+def _edge_index_of(data) -> torch.Tensor:
+    ei = data.edge_index
+    if not torch.is_tensor(ei):
+        ei = torch.as_tensor(np.asarray(ei))
+    return ei.to(torch.int64)
+
+
+def _to_networkx(data):
+    """PyG ``to_networkx(data)`` defaults as called at utils.py:27,33,...: DiGraph, nodes 0..N-1."""
+    import networkx as nx
+
+    G = nx.DiGraph()
+    G.add_nodes_from(range(int(data.num_nodes)))
+    ei = _edge_index_of(data).cpu()
+    G.add_edges_from(zip(ei[0].tolist(), ei[1].tolist()))
+    return G
+
+
+def _device_csr(data) -> _dev.DeviceCsr:
+    ei = _edge_index_of(data).cuda(non_blocking=True)
+    csr = _dev.DeviceCsr(int(data.num_nodes), ei.size(1), symmetrize=False)
+    return csr.build(ei)
+
+
+def sample_anchor_nodes(data, num_anchor_nodes, sampling_method):
+    """utils.py:18-62.  ndarray for ``stochastic``, ``list[int]`` (ascending score) otherwise."""
+    if sampling_method == 'stochastic':
+        # host numpy global RNG, with replacement — identical stream to utils.py:23-24
+        return np.random.choice(np.arange(data.num_nodes), num_anchor_nodes)
+
+    if sampling_method == 'degree_centrality':
+        csr = _device_csr(data)
+        csr.info()  # surfaces a bad edge_index as an exception
+        return _dev.topk_stable(csr.degree(), num_anchor_nodes).cpu().tolist()
+
+    if sampling_method == 'pagerank':
+        csr = _device_csr(data)
+        score, _ = csr.pagerank()  # networkx pagerank_scipy defaults
+        return _dev.topk_stable(score, num_anchor_nodes).cpu().tolist()
+
+    if sampling_method in _HOST_CENTRALITIES:
+        # Not re-implemented (north_star): the reference's own networkx call, same top-k rule.
+        import networkx as nx
+
+        G = _to_networkx(data)
+        score = {
+            'betweenness_centrality': nx.betweenness_centrality,
+            'eigenvector_centrality': nx.eigenvector_centrality_numpy,
+            'closeness_centrality': nx.closeness_centrality,
+            'clustering_coefficient': nx.clustering,
+        }[sampling_method](G)
+        ranked = sorted(score.items(), key=lambda item: item[1])  # stable, ascending
+        return [k for k, _ in ranked][-num_anchor_nodes:]
+
+    # the reference falls through every ``if`` and fails at ``return`` (utils.py:62)
+    raise UnboundLocalError("cannot access local variable 'sampled_anchor_nodes' where it is not "
+                            "associated with a value")
+
+
+def _graph_to_edge_index(G):
+    n = G.number_of_nodes()
+    if n and (min(G.nodes) != 0 or max(G.nodes) != n - 1):
+        raise ValueError("graph nodes must be labelled 0..N-1 (as to_networkx produces)")
+    edges = np.asarray(list(G.edges()), dtype=np.int64).reshape(-1, 2)
+    if not G.is_directed():
+        edges = np.concatenate([edges, edges[:, ::-1]], axis=0)
+    return torch.from_numpy(np.ascontiguousarray(edges.T)), n
+
+
+def shortest_path_length(G, anchor_nodes, partition_length):
+    """utils.py:64-81: ``{node: [1/len(path) per anchor]}`` with ``0`` where there is no path.
+
+    ``G`` is the networkx graph ``to_networkx`` built; distances come from one device MS-BFS.
+    Values are Python floats ``1/(d+1)`` and the int ``0``, exactly as the reference appends them.
+    """
+    ei, n = _graph_to_edge_index(G)
+    anchors = [int(a) for a in anchor_nodes]
+    _, hops, stats = _dev.geodesic_embed_host(ei, n, anchors, None, False, want_hops=True)
+    last_stats.update(stats)
+    h = hops.numpy()
+    out = {}
+    for node in partition_length:
+        row = h[node]
+        out[node] = [0 if d == _lib.GP_UNREACHABLE_U16 else 1 / (int(d) + 1) for d in row]
+    return out
+
+
+def merge_dicts(dicts):
+    """utils.py:83-90: later dicts win, insertion order of first appearance is kept."""
+    merged = {}
+    for part in dicts:
+        merged.update(part)
+    return merged
+
+
+def all_pairs_shortest_path_length_parallel(G, anchor_nodes, num_workers):
+    """utils.py:92-114.  ``num_workers`` sized a CPU pool there; one GPU sweep replaces it."""
+    return shortest_path_length(G, anchor_nodes, list(G.nodes))
+
+
+def get_geodesic_distance_vector(data, num_workers):
+    """utils.py:116-126: float32 ``[N, K]`` of ``1/(hops(node -> anchor)+1)``, 0 when unreachable.
+
+    Reads ``data.anchor_nodes``.  Always float32 (the reference yields int64 in the degenerate case
+    where every entry is 0).
+    """
+    out, _, stats = _dev.geodesic_embed_host(_edge_index_of(data), int(data.num_nodes), data.anchor_nodes,
+                                             None, SYMMETRIZE)
+    last_stats.update(stats)
+    return out
+
+
+def concat_into_features(embedding_matrix, data):
+    """utils.py:129-135: ``torch.cat((data.x, embedding), 1)``."""
+    emb = torch.as_tensor(embedding_matrix)
+    return torch.cat((data.x, emb.to(data.x.device)), 1)
+
+
+def attach_distance_embedding(data, dataset, num_anchor_nodes, sampling_method, distance_function, num_workers):
+    """utils.py:137-147.  Sets ``data.anchor_nodes``; returns a new CPU float32 ``[N, F + K]``.
+
+    Distance block and concat are one fused C-ABI call (the epilogue writes the ``[N, F+K]`` rows once).
+    """
+    _say('sampling anchor nodes...')
+    data.anchor_nodes = sample_anchor_nodes(data=data, num_anchor_nodes=num_anchor_nodes,
+                                            sampling_method=sampling_method)
+    _say('deriving shortest paths to anchor nodes...')
+    x = data.x
+    if x.dtype != torch.float32:
+        # torch.cat type-promotes; keep that behaviour by taking the slow generic route
+        return concat_into_features(get_geodesic_distance_vector(data, num_workers), data)
+    out, _, stats = _dev.geodesic_embed_host(_edge_index_of(data), int(data.num_nodes), data.anchor_nodes,
+                                             x, SYMMETRIZE)
+    last_stats.update(stats)
+    _say('feature matrix is blessed by the POPE!')
+    return out
+
+
+def node2vec_path(dataset):
+    """Where utils.py:155 looks: ``<module dir>/data/<dataset>_node2vec.pt`` (override: GRAPHPOPE_DATA_DIR)."""
+    base = os.environ.get("GRAPHPOPE_DATA_DIR") or osp.join(osp.dirname(osp.realpath(__file__)), 'data')
+    return osp.join(base, f'{dataset}_node2vec.pt')
+
+
+def attach_node2vec(data, dataset, num_anchor_nodes, sampling_method, distance_function, num_workers):
+    """utils.py:149-180: pairwise distances to anchor embeddings, per-column min-max, concat."""
+    _say('sampling anchor nodes...')
+    table = torch.load(node2vec_path(dataset), map_location="cpu").detach()
+    mode = _lib.CDIST_MODES[distance_function]  # KeyError on an unknown key, as utils.py:164
+    if sampling_method == 'stochastic':
+        anchor_nodes = sample_anchor_nodes(data, num_anchor_nodes, sampling_method='stochastic')
+        anchor_emb = table[torch.as_tensor(np.asarray(anchor_nodes, dtype=np.int64))]
+    else:
+        # anything but 'stochastic' means KMeans centres (utils.py:168-170); stays on scikit-learn
+        from sklearn.cluster import KMeans
+
+        kmeans = KMeans(n_clusters=num_anchor_nodes).fit(table.numpy())
+        anchor_emb = torch.as_tensor(kmeans.cluster_centers_)
+        _say('K means cluster anchor nodes derived!')
+    block = _dev.cdist_minmax(table, anchor_emb, mode, apply_minmax=True)
+    out = concat_into_features(block.cpu(), data)
+    _say('feature matrix is blessed by the POPE')
+    return out
+
+
+def clear_cache():
+    """Drop the process-global memo (extension; the reference has no way to reset it)."""
+    globals().pop("cached_pope_embedding", None)
+
+
+def Graphpope(data, dataset: str, embedding_space: str, sampling_method: str, num_anchor_nodes: int,
+              distance_function=None, num_workers=4):
+    """utils.py:182-210.  Dispatch on ``embedding_space`` in {'geodesic', 'node2vec'}.
+
+    Keeps the reference's process-global memo: the first call computes, every later call returns
+    the cached tensor whatever its arguments (utils.py:195-208).
+    """
+    global cached_pope_embedding
+    pope_map = {
+        'geodesic': attach_distance_embedding,
+        'node2vec': attach_node2vec,
+    }
+    try:
+        enhanced_features = cached_pope_embedding
+    except NameError:
+        pope = pope_map[embedding_space]  # KeyError on an unknown space, as utils.py:206
+        enhanced_features = pope(data, dataset, num_anchor_nodes, sampling_method, distance_function,
+                                 num_workers=num_workers)
+        cached_pope_embedding = enhanced_features
+    return enhanced_features

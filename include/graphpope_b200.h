@@ -1,0 +1,190 @@
+/*
+ * graphpope_b200.h — C ABI of the B200-native GraphPOPE embedding-generation path.
+ *
+ * The reference (JeroendenBoef/GraphPOPE) is pure Python and has no FFI; this
+ * header IS the drop-in boundary a maintainer binds from utils.py (ctypes stub in
+ * INTEGRATION.md).  Each entry point cites the reference code it replaces
+ * (file:line into the reference repository).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - Every function returns an int status (GP_OK == 0) and never throws;
+ *     gp_last_error() returns a thread-local message for the last failure.
+ *   - "d_" pointers are device pointers on the current CUDA device, "h_"
+ *     pointers are host pointers.  The caller owns every buffer it passes in;
+ *     the library owns only the opaque handles it creates.
+ *   - gp_stream_t is a cudaStream_t (0 = the legacy default stream).  Calls
+ *     documented "async" only enqueue work on that stream; results are valid
+ *     after the stream is synchronised.  Calls documented "syncs" synchronise it.
+ *   - Data-dependent failures detected on the device (edge index out of range,
+ *     anchor out of range, hop distance not representable in uint16) are
+ *     latched in the handle and reported by the next syncing call.
+ */
+#ifndef GRAPHPOPE_B200_H
+#define GRAPHPOPE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GP_ABI_VERSION 1
+
+typedef void *gp_stream_t;
+
+enum gp_status {
+    GP_OK = 0,
+    GP_ERR_INVALID = 1,        /* bad argument (NULL, negative size, misuse)      */
+    GP_ERR_CUDA = 2,           /* a CUDA runtime call failed                     */
+    GP_ERR_OOM = 3,            /* device or host allocation failed               */
+    GP_ERR_INDEX_RANGE = 4,    /* edge_index / anchor entry outside [0, N)       */
+    GP_ERR_LEVEL_OVERFLOW = 5, /* a hop distance >= 65535 (uint16 sentinel)      */
+    GP_ERR_UNSUPPORTED = 6,    /* size beyond what this build supports           */
+    GP_ERR_NOT_CONVERGED = 7,  /* PageRank hit max_iter (networkx raises too)    */
+    GP_ERR_NO_DEVICE = 8       /* no CUDA device / wrong architecture            */
+};
+
+#define GP_UNREACHABLE_U16 0xFFFFu
+
+/* gp_csr_create flags */
+#define GP_CSR_SYMMETRIZE 0x1u /* add the reverse of every edge (identity on the
+                                  symmetric datasets; default off = reference
+                                  DiGraph semantics, utils.py:121)                */
+
+/* cdist modes: keys of dist_map, utils.py:158-162 */
+enum gp_cdist_mode {
+    GP_CDIST_COSINE_DISTANCE = 0,   /* 'distance'   -> sklearn cosine_distances   */
+    GP_CDIST_COSINE_SIMILARITY = 1, /* 'similarity' -> sklearn cosine_similarity  */
+    GP_CDIST_EUCLIDEAN = 2          /* 'euclidean'  -> sklearn euclidean_distances */
+};
+
+typedef struct gp_csr gp_csr_t;     /* de-duplicated digraph in CSR form          */
+typedef struct gp_msbfs gp_msbfs_t; /* multi-source BFS workspace + results       */
+
+typedef struct gp_csr_info {
+    int64_t num_nodes;
+    int64_t num_input_edges;  /* E columns given to gp_csr_build                 */
+    int64_t num_edges;        /* directed edges after de-duplication (E')        */
+    int64_t max_out_degree;
+    int32_t is_symmetric;     /* 1 if every edge has its reverse                 */
+    int32_t reserved;
+} gp_csr_info_t;
+
+typedef struct gp_msbfs_stats {
+    int64_t num_anchors;
+    int64_t lane_words;        /* uint64 lane words per node (64 anchors each)   */
+    int32_t max_level;         /* largest finite hop distance                    */
+    int32_t levels_run;        /* level sweeps executed                          */
+    int32_t pull_levels;
+    int32_t push_levels;
+    int64_t edges_examined;    /* neighbour lane-word gathers + pushes issued    */
+    int64_t grid_blocks;       /* persistent grid size                           */
+} gp_msbfs_stats_t;
+
+/* ------------------------------------------------------------------ library */
+int gp_abi_version(void);
+const char *gp_last_error(void);
+const char *gp_status_string(int status);
+/* Device properties the host layer reports (SM count, name).  Syncs nothing. */
+int gp_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, char *name, int64_t name_cap);
+
+/* ------------------------------------------------------------------ CSR build
+ * Replaces torch_geometric.utils.to_networkx(data) as called at utils.py:121
+ * (and :27,33,39,45,51,57): nodes 0..N-1, parallel edges collapse, self-loops
+ * kept, no symmetrisation unless GP_CSR_SYMMETRIZE.  Built on the device with a
+ * radix sort of packed (src,dst) keys + unique + row-pointer search.            */
+int gp_csr_create(int64_t num_nodes, int64_t edge_capacity, uint32_t flags, gp_csr_t **out);
+/* async.  d_edge_index: int64 [2, num_edges] row-major (row 0 = src, row 1 = dst). */
+int gp_csr_build(gp_csr_t *csr, const int64_t *d_edge_index, int64_t num_edges, gp_stream_t stream);
+/* syncs.  Reports latched GP_ERR_INDEX_RANGE. */
+int gp_csr_info(gp_csr_t *csr, gp_csr_info_t *info, gp_stream_t stream);
+/* syncs.  Copies the CSR into caller device buffers: which = 0 out-edges (row u
+ * lists v with u->v), 1 in-edges (row v lists u with u->v).  d_rowptr int32[N+1],
+ * d_col int32[>= num_edges].  Rows are ascending and unique.                    */
+int gp_csr_export(gp_csr_t *csr, int which, int32_t *d_rowptr, int32_t *d_col, gp_stream_t stream);
+int gp_csr_free(gp_csr_t *csr);
+
+/* ------------------------------------------------------------------ MS-BFS
+ * Replaces shortest_path_length + all_pairs_shortest_path_length_parallel
+ * (utils.py:64-81, 92-114): hops(node -> anchor_j) for every node and anchor,
+ * as one multi-source BFS from the anchors over reversed edges, 64 anchors per
+ * uint64 lane word, in one persistent kernel.                                   */
+int gp_msbfs_create(const gp_csr_t *csr, int64_t max_anchors, gp_msbfs_t **out);
+/* async.  d_anchors: int64[num_anchors] (duplicates allowed, utils.py:24). */
+int gp_msbfs_run(gp_msbfs_t *bfs, const int64_t *d_anchors, int64_t num_anchors, gp_stream_t stream);
+/* async.  Integer hop matrix: d_dist[node*ld + col_offset + j] = hops or 0xFFFF. */
+int gp_msbfs_hops_u16(gp_msbfs_t *bfs, uint16_t *d_dist, int64_t ld, int64_t col_offset, gp_stream_t stream);
+/* async.  Fused normalise / unreachable-fill / concat epilogue; replaces the
+ * value convention of utils.py:73,76, the tensor conversion of utils.py:125 and
+ * concat_into_features (utils.py:129-135):
+ *   d_out[node*ld_out + j]                 = d_x[node*ld_x + j]      j in [0, F)   (skipped if d_x == NULL)
+ *   d_out[node*ld_out + col_offset + j]    = 1/(hops+1), 0 if unreachable, j in [0, K)
+ * IEEE fp32 division (bit-equal to the reference's float64 -> float32 rounding). */
+int gp_msbfs_features(gp_msbfs_t *bfs, const float *d_x, int64_t num_features, int64_t ld_x,
+                      float *d_out, int64_t ld_out, int64_t col_offset, gp_stream_t stream);
+/* syncs.  Reports latched GP_ERR_INDEX_RANGE / GP_ERR_LEVEL_OVERFLOW. */
+int gp_msbfs_stats(gp_msbfs_t *bfs, gp_msbfs_stats_t *stats, gp_stream_t stream);
+int gp_msbfs_free(gp_msbfs_t *bfs);
+
+/* Bit-sliced result planes of the last run, for the multi-GPU gather
+ * (anchor-sharded ranks exchange these instead of uint16/fp32 columns):
+ * plane 0 = "reached" mask, planes 1..num_planes-1 = distance bits 0.. ;
+ * each plane is uint64 [batches][N][words_per_batch].  syncs (needs max_level). */
+int gp_msbfs_planes(gp_msbfs_t *bfs, const uint64_t **d_planes, int64_t *plane_stride_words,
+                    int32_t *num_planes, int32_t *batches, int32_t *words_per_batch, gp_stream_t stream);
+/* async.  Decode planes gathered from `num_ranks` anchor shards (each shard laid
+ * out as gp_msbfs_planes reports, shard r at d_gathered + r*rank_stride_words)
+ * into columns [col_offset + r*anchors_per_rank + j] of d_out, optionally
+ * copying x as gp_msbfs_features does.                                          */
+int gp_decode_gathered(const uint64_t *d_gathered, int64_t rank_stride_words, int32_t num_ranks,
+                       int64_t num_nodes, int64_t anchors_per_rank, int32_t num_planes,
+                       int32_t batches, int32_t words_per_batch, int64_t plane_stride_words,
+                       const float *d_x, int64_t num_features, int64_t ld_x,
+                       float *d_out, int64_t ld_out, int64_t col_offset, gp_stream_t stream);
+
+/* async.  Stand-alone epilogue from a uint16 hop matrix (utils.py:73,76,125). */
+int gp_normalize_into(const uint16_t *d_dist, int64_t num_nodes, int64_t num_anchors, int64_t ld_dist,
+                      float *d_out, int64_t ld_out, int64_t col_offset, gp_stream_t stream);
+
+/* ------------------------------------------------------------------ one-call host entry
+ * get_geodesic_distance_vector + concat_into_features with HOST buffers
+ * (utils.py:116-135): copies edge_index/anchors to the device, builds the CSR,
+ * runs the MS-BFS and the epilogue, and copies the feature block back into
+ * h_out[:, col_offset:col_offset+K] (row pitch ld_out floats).  If h_x != NULL
+ * its F columns are copied into h_out[:, 0:F] on the host while the GPU works.
+ * h_hops (optional, may be NULL) receives the uint16 hop matrix [N, K].  syncs. */
+int gp_geodesic_embed_host(const int64_t *h_edge_index, int64_t num_edges, int64_t num_nodes,
+                           uint32_t csr_flags, const int64_t *h_anchors, int64_t num_anchors,
+                           const float *h_x, int64_t num_features,
+                           float *h_out, int64_t ld_out, int64_t col_offset,
+                           uint16_t *h_hops, gp_msbfs_stats_t *stats);
+
+/* ------------------------------------------------------------------ samplers
+ * degree_centrality (utils.py:38-42): in+out degree over de-duplicated edges
+ * (a self-loop counts 2).  async.  d_degree int32[N].                           */
+int gp_degree(const gp_csr_t *csr, int32_t *d_degree, gp_stream_t stream);
+/* pagerank (utils.py:26-30 -> networkx _pagerank_scipy defaults): float64 power
+ * iteration, uniform start/personalisation, dangling mass spread uniformly,
+ * stop when the L1 change < N*tol.  syncs.  d_x float64[N].                     */
+int gp_pagerank(const gp_csr_t *csr, double alpha, double tol, int32_t max_iter,
+                double *d_x, int32_t *iterations, gp_stream_t stream);
+/* Stable top-k of utils.py:29-30 / 41-42: ascending stable sort by score, keep
+ * the last k (ties keep ascending node id; output in ascending-score order).
+ * async.  d_out int64[min(k, N)] (k == 0 returns all N: list[-0:] quirk).       */
+int gp_topk_stable_i32(const int32_t *d_score, int64_t num_nodes, int64_t k, int64_t *d_out, gp_stream_t stream);
+int gp_topk_stable_f64(const double *d_score, int64_t num_nodes, int64_t k, int64_t *d_out, gp_stream_t stream);
+
+/* ------------------------------------------------------------------ node2vec block
+ * The pairwise step + MinMaxScaler of attach_node2vec (utils.py:174-176):
+ * out[:, col_offset + j] = minmax_j( f(emb_i, anchor_j) ), f per gp_cdist_mode,
+ * tensor-core GEMM with split-precision operands and fp32 accumulation.
+ * d_emb float32 [N, D], d_anchor_emb float32 [K, D].  async.                    */
+int gp_cdist_minmax(const float *d_emb, const float *d_anchor_emb, int64_t num_nodes, int64_t num_anchors,
+                    int64_t dim, int32_t mode, int32_t apply_minmax,
+                    float *d_out, int64_t ld_out, int64_t col_offset, gp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHPOPE_B200_H */

@@ -1,0 +1,60 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/*.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "graphpope_b200.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"^\s*(?:const\s+)?(?:int|char)\s*\*?\s*(gp_[a-z0-9_]+)\s*\(", src, flags=re.M)
+    return sorted(set(names))
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_functions()
+    for must in ("gp_csr_build", "gp_msbfs_run", "gp_msbfs_features", "gp_normalize_into",
+                 "gp_geodesic_embed_host", "gp_degree", "gp_pagerank", "gp_topk_stable_f64",
+                 "gp_cdist_minmax", "gp_decode_gathered", "gp_last_error"):
+        assert must in names
+    assert len(names) >= 24
+
+
+def test_library_exports_every_declared_symbol():
+    from graphpope_b200 import _lib
+
+    assert os.path.exists(_lib.LIB_PATH), "build the library first: __graft_entry__.build()"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared_functions():
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert set(declared_functions()) == set(_lib.SIGNATURES), "ctypes table out of sync with the header"
+
+
+def test_no_compute_without_gpu_but_clean_errors():
+    import torch
+
+    from graphpope_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.gp_abi_version() == 1
+    assert lib.gp_status_string(5) == b"hop distance does not fit uint16"
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            _lib.require_cuda()
+        assert lib.gp_device_info(None, None, None, None, 0) == _lib.GP_ERR_NO_DEVICE
+        assert b"no CUDA device" in lib.gp_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "graphpope_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "/root/reference" not in text, f

@@ -1,0 +1,259 @@
+"""Parity of the CUDA geodesic path against the CPU oracle and the frozen reference outputs.
+
+Everything here calls through the C ABI (graphpope_b200.device / graphpope_b200.utils ->
+libgraphpope_b200.so).  Bar: bit-exact uint16 hops and bit-exact float32 features.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import micro_names
+from graphpope_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from graphpope_b200 import device
+    return device
+
+
+def _oracle_hops(ei, n, anchors, symmetrize=False):
+    from oracle import cbfs
+    return cbfs.bfs_hops(cbfs.InCsr(ei, n, symmetrize), anchors)
+
+
+def _gpu_hops_and_features(dev, ei, n, anchors, x=None, symmetrize=False):
+    eng = dev.GeodesicEngine(n, ei.shape[1], len(anchors), symmetrize)
+    ei_d = torch.as_tensor(ei, dtype=torch.int64).cuda()
+    a_d = torch.as_tensor(np.asarray(anchors, dtype=np.int64)).cuda()
+    x_d = None if x is None else torch.as_tensor(x).cuda()
+    feats = eng.run(ei_d, a_d, x_d)
+    hops = eng.bfs.hops_u16()
+    stats = eng.bfs.stats()
+    torch.cuda.synchronize()
+    return hops.cpu().numpy(), feats.cpu().numpy(), stats
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+# ------------------------------------------------------------------ CSR builder
+@pytest.mark.parametrize("n,e,seed", [(1, 3, 0), (7, 0, 1), (50, 400, 2), (3000, 20000, 3), (70000, 300000, 4)])
+@pytest.mark.parametrize("symmetrize", [False, True])
+def test_csr_matches_oracle(dev, n, e, seed, symmetrize):
+    from oracle import geodesic as g
+    ei = synth.random_digraph(n, e, seed=seed)
+    csr = dev.DeviceCsr(n, ei.shape[1], symmetrize).build(torch.as_tensor(ei).cuda())
+    info = csr.info()
+    for which, fn in (("out", g.out_csr), ("in", g.in_csr)):
+        rp_want, col_want = fn(ei, n, symmetrize)
+        rp, col = csr.export(which)
+        assert np.array_equal(rp.cpu().numpy(), rp_want), which
+        assert np.array_equal(col.cpu().numpy(), col_want), which
+    s, d = g.dedup_edges(ei, n, symmetrize)
+    assert info["num_edges"] == s.size
+    assert info["num_input_edges"] == ei.shape[1]
+    assert info["max_out_degree"] == (np.bincount(s, minlength=n).max() if s.size else 0)
+    sym = set(zip(s.tolist(), d.tolist())) == set(zip(d.tolist(), s.tolist()))
+    assert bool(info["is_symmetric"]) == sym
+
+
+def test_csr_rejects_out_of_range_index(dev):
+    ei = torch.tensor([[0, 1, 9], [1, 2, 0]], dtype=torch.int64).cuda()
+    csr = dev.DeviceCsr(5, 3).build(ei)
+    with pytest.raises(IndexError):
+        csr.info()
+    ei = torch.tensor([[0, -1], [1, 2]], dtype=torch.int64).cuda()
+    with pytest.raises(IndexError):
+        dev.DeviceCsr(5, 2).build(ei).info()
+
+
+# ------------------------------------------------------------------ golden fixtures (reference outputs)
+def test_micro_graphs_match_reference(dev, golden_small):
+    for name in micro_names(golden_small):
+        n = int(golden_small[f"micro/{name}/n"])
+        ei = golden_small[f"micro/{name}/edges"]
+        anchors = golden_small[f"micro/{name}/anchors"]
+        want = golden_small[f"micro/{name}/rows_f64"].astype(np.float32)
+        hops, feats, _ = _gpu_hops_and_features(dev, ei, n, anchors)
+        assert np.array_equal(_bits(feats), _bits(want)), name
+        assert np.array_equal(hops, _oracle_hops(ei, n, anchors)), name
+
+
+def test_toy_pipeline_matches_reference(dev, golden_small):
+    n = int(golden_small["toy/n"])
+    ei, x = golden_small["toy/edge_index"], golden_small["toy/x"]
+    anchors = golden_small["toy/anchors"]
+    want = golden_small["toy/features"]
+    _, feats, _ = _gpu_hops_and_features(dev, ei, n, anchors, x)  # F=5, K=8: unaligned scalar epilogue
+    assert feats.shape == want.shape
+    assert np.array_equal(_bits(feats), _bits(want))
+    # duplicate anchor 102 -> identical columns
+    assert np.array_equal(feats[:, 5 + 0], feats[:, 5 + 6])
+
+
+def test_toysym_matches_reference(dev, golden_small):
+    ei, anchors = golden_small["toysym/edge_index"], golden_small["toysym/anchors"]
+    want = golden_small["toysym/embedding"]
+    for sym in (False, True):
+        _, feats, _ = _gpu_hops_and_features(dev, ei, 300, anchors, symmetrize=sym)
+        assert np.array_equal(_bits(feats), _bits(want))
+
+
+def test_pubmed_shape_matches_reference_verbatim(dev, golden_pubmed):
+    """BASELINE.json configs[0]: the reference's own run (num_workers=6) frozen as a hash."""
+    shape = synth.PUBMED_SHAPE
+    ei = synth.make_graph(shape)
+    anchors = synth.stochastic_anchors(shape.num_nodes, 256, 42)
+    assert np.array_equal(anchors, golden_pubmed["anchors"])
+    hops, feats, stats = _gpu_hops_and_features(dev, ei, shape.num_nodes, anchors)
+    rows = golden_pubmed["sample_rows"]
+    assert np.array_equal(_bits(feats[rows]), _bits(golden_pubmed["sample"]))
+    assert hashlib.sha256(np.ascontiguousarray(feats).tobytes()).digest() == golden_pubmed["sha256"].tobytes()
+    assert np.array_equal(hops, _oracle_hops(ei, shape.num_nodes, anchors))
+    assert stats["max_level"] == int(hops[hops != 0xFFFF].max())
+
+
+# ------------------------------------------------------------------ oracle parity, many shapes
+@pytest.mark.parametrize("k", [1, 2, 63, 64, 65, 128, 129, 256, 257, 700])
+def test_anchor_counts_and_lane_padding(dev, k):
+    n = 2500
+    ei = synth.random_digraph(n, 9000, seed=k)
+    anchors = np.random.default_rng(k).integers(0, n, k)
+    hops, feats, stats = _gpu_hops_and_features(dev, ei, n, anchors)
+    want = _oracle_hops(ei, n, anchors)
+    assert hops.shape == (n, k) and np.array_equal(hops, want)
+    from oracle import cbfs
+    assert np.array_equal(_bits(feats), _bits(cbfs.normalise(want)))
+    assert stats["num_anchors"] == k
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_asymmetric_multigraphs(dev, seed):
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(2, 4000))
+    ei = synth.random_digraph(n, int(rng.integers(0, 6 * n)), seed=seed)
+    anchors = rng.integers(0, n, int(rng.integers(1, 300)))
+    hops, _, _ = _gpu_hops_and_features(dev, ei, n, anchors)
+    assert np.array_equal(hops, _oracle_hops(ei, n, anchors))
+
+
+def test_hub_rows_take_the_cta_and_warp_paths(dev):
+    # star with 5000 leaves + a 300-leaf hub + chain: exercises large / medium / small row classes
+    n = 6000
+    e = [(0, i) for i in range(1, 5001)] + [(i, 0) for i in range(1, 5001)]
+    e += [(5001, i) for i in range(5002, 5302)] + [(i, 5001) for i in range(5002, 5302)]
+    e += [(i, i + 1) for i in range(5302, 5999)] + [(5001, 0), (5500, 5001)]
+    ei = np.asarray(e, dtype=np.int64).T
+    anchors = np.array([0, 17, 5001, 5999, 5302, 5100, 17], dtype=np.int64)
+    hops, _, stats = _gpu_hops_and_features(dev, ei, n, anchors)
+    assert np.array_equal(hops, _oracle_hops(ei, n, anchors))
+
+
+def test_deep_path_uses_many_distance_planes(dev):
+    n = 5000
+    ei = np.stack([np.arange(n - 1), np.arange(1, n)]).astype(np.int64)
+    anchors = np.array([n - 1, 0, 2500], dtype=np.int64)
+    hops, feats, stats = _gpu_hops_and_features(dev, ei, n, anchors)
+    want = _oracle_hops(ei, n, anchors)
+    assert np.array_equal(hops, want)
+    assert stats["max_level"] == n - 1
+    from oracle import cbfs
+    assert np.array_equal(_bits(feats), _bits(cbfs.normalise(want)))
+
+
+def test_uint16_overflow_is_reported(dev):
+    n = 65600
+    ei = np.stack([np.arange(n - 1), np.arange(1, n)]).astype(np.int64)
+    eng = dev.GeodesicEngine(n, ei.shape[1], 1)
+    eng.csr.build(torch.as_tensor(ei).cuda())
+    eng.bfs.run(torch.tensor([n - 1], dtype=torch.int64).cuda())
+    with pytest.raises(OverflowError):
+        eng.bfs.stats()
+    # 65534 hops is the largest representable distance
+    eng.bfs.run(torch.tensor([65534], dtype=torch.int64).cuda())
+    assert eng.bfs.stats()["max_level"] == 65534
+    hops = eng.bfs.hops_u16().cpu().numpy()
+    assert hops[0, 0] == 65534 and hops[65535, 0] == 0xFFFF
+
+
+def test_bad_anchor_is_reported(dev):
+    ei = synth.random_digraph(100, 300, seed=1)
+    eng = dev.GeodesicEngine(100, ei.shape[1], 4)
+    eng.csr.build(torch.as_tensor(ei).cuda())
+    eng.bfs.run(torch.tensor([1, 100, 3], dtype=torch.int64).cuda())
+    with pytest.raises(IndexError):
+        eng.bfs.stats()
+
+
+def test_empty_inputs(dev):
+    ei = np.zeros((2, 0), dtype=np.int64)
+    hops, feats, _ = _gpu_hops_and_features(dev, ei, 4, np.array([1, 1]))
+    assert feats.tolist() == [[0, 0], [1, 1], [0, 0], [0, 0]]
+    out, hops, _ = dev.geodesic_embed_host(ei, 3, [], None)
+    assert tuple(out.shape) == (3, 0)
+    x = np.arange(6, dtype=np.float32).reshape(3, 2)
+    out, _, _ = dev.geodesic_embed_host(ei, 3, [], x)
+    assert np.array_equal(out.numpy(), x)
+    out, _, _ = dev.geodesic_embed_host(ei, 0, [], None)
+    assert tuple(out.shape) == (0, 0)
+
+
+# ------------------------------------------------------------------ full-size properties (Flickr shape)
+@pytest.fixture(scope="module")
+def flickr():
+    shape = synth.FLICKR_SHAPE
+    ei = synth.make_graph(shape)
+    anchors = synth.stochastic_anchors(shape.num_nodes, 256, 42)
+    return shape, ei, anchors
+
+
+def test_flickr_shape_k256_bit_exact(dev, flickr):
+    """BASELINE.json configs[1] (the headline workload) against the C oracle."""
+    shape, ei, anchors = flickr
+    x = np.random.default_rng(0).standard_normal((shape.num_nodes, shape.num_features)).astype(np.float32)
+    hops, feats, stats = _gpu_hops_and_features(dev, ei, shape.num_nodes, anchors, x)
+    want = _oracle_hops(ei, shape.num_nodes, anchors)
+    assert np.array_equal(hops, want)
+    from oracle import cbfs
+    assert np.array_equal(_bits(feats[:, shape.num_features:]), _bits(cbfs.normalise(want)))
+    assert np.array_equal(feats[:, : shape.num_features], x)
+    assert stats["lane_words"] == 4
+
+
+def test_flickr_shape_properties(dev, flickr):
+    shape, ei, anchors = flickr
+    n = shape.num_nodes
+    hops, feats, _ = _gpu_hops_and_features(dev, ei, n, anchors)
+    hops2, feats2, _ = _gpu_hops_and_features(dev, ei, n, anchors)
+    assert np.array_equal(hops, hops2) and np.array_equal(_bits(feats), _bits(feats2))  # deterministic
+    cols = np.arange(anchors.size)
+    assert np.all(hops[anchors, cols] == 0) and np.all(feats[anchors, cols] == 1.0)
+    # symmetric graph: hops(a_i -> a_j) == hops(a_j -> a_i)
+    sub = hops[anchors][:, :]
+    assert np.array_equal(sub, sub.T)
+    # triangle inequality through anchor 0 on reachable triples (sampled rows)
+    r = np.arange(0, n, 37)
+    d0 = hops[r, 0].astype(np.int64)
+    a0 = hops[anchors[0]].astype(np.int64)  # hops(anchor0 -> anchor_j)
+    ok = (hops[r] != 0xFFFF) & (d0[:, None] != 0xFFFF) & (a0[None, :] != 0xFFFF)
+    assert np.all((hops[r].astype(np.int64) <= d0[:, None] + a0[None, :]) | ~ok)
+    # permuting the anchors permutes the columns
+    perm = np.random.default_rng(1).permutation(anchors.size)
+    hops_p, _, _ = _gpu_hops_and_features(dev, ei, n, anchors[perm])
+    assert np.array_equal(hops_p, hops[:, perm])
+
+
+def test_normalize_into_matches_convention(dev):
+    d = np.array([[0, 1, 2, 0xFFFF], [65534, 7, 0xFFFF, 3]], dtype=np.uint16)
+    out = torch.full((2, 6), -1.0, device="cuda")
+    dev.normalize_into(torch.as_tensor(d.view(np.int16)).cuda().view(torch.uint16), out, col_offset=2)
+    from oracle import cbfs
+    got = out.cpu().numpy()
+    assert np.array_equal(_bits(got[:, 2:]), _bits(cbfs.normalise(d)))
+    assert np.all(got[:, :2] == -1.0)
