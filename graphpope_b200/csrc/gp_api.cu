@@ -4,6 +4,7 @@
 #include "gp_msbfs.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -11,7 +12,12 @@
 namespace {
 thread_local char g_err[512] = "";
 int g_sm_count = 0;
+std::atomic<long long> g_launches{0};
 }  // namespace
+
+void gp_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+extern "C" int64_t gp_launch_count(void) { return (int64_t)g_launches.load(); }
 
 void gp_set_error(const char *fmt, ...)
 {
@@ -91,6 +97,8 @@ struct HostCtx {
     float *d_feat = nullptr;
     uint16_t *d_hops = nullptr;
     cudaStream_t stream = nullptr;
+    void *h_stage = nullptr;  // pinned staging for pageable outputs
+    size_t h_stage_bytes = 0;
 
     void release()
     {
@@ -187,18 +195,42 @@ extern "C" int gp_geodesic_embed_host(const int64_t *h_edge_index, int64_t num_e
         GP_TRY(gp_msbfs_features(c.bfs, nullptr, 0, 0, c.d_feat, num_anchors, 0, s));
         if (h_hops) GP_TRY(gp_msbfs_hops_u16(c.bfs, c.d_hops, num_anchors, 0, s));
     }
-    // The feature block lands in columns [col_offset, col_offset + K); enqueue its copy first so
-    // that (with pinned h_out) it overlaps the host-side concat below.
-    if (num_nodes > 0 && num_anchors > 0) {
-        GP_CUDA_CHECK(cudaMemcpy2DAsync(h_out + col_offset, sizeof(float) * (size_t)ld_out, c.d_feat,
-                                        sizeof(float) * (size_t)num_anchors, sizeof(float) * (size_t)num_anchors,
-                                        (size_t)num_nodes, cudaMemcpyDeviceToHost, s));
+    // The feature block lands in columns [col_offset, col_offset + K).  A pinned h_out takes a
+    // strided DMA directly; a pageable one goes through a pinned staging block (one contiguous DMA,
+    // then a threaded row scatter) because a pageable 2-D copy degenerates into N tiny transfers.
+    const bool have_block = num_nodes > 0 && num_anchors > 0;
+    bool staged = false;
+    if (have_block) {
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, h_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (pinned) {
+            GP_CUDA_CHECK(cudaMemcpy2DAsync(h_out + col_offset, sizeof(float) * (size_t)ld_out, c.d_feat,
+                                            sizeof(float) * (size_t)num_anchors, sizeof(float) * (size_t)num_anchors,
+                                            (size_t)num_nodes, cudaMemcpyDeviceToHost, s));
+        } else {
+            const size_t need = sizeof(float) * (size_t)(num_nodes * num_anchors);
+            if (c.h_stage_bytes < need) {
+                if (c.h_stage) cudaFreeHost(c.h_stage);
+                c.h_stage = nullptr;
+                c.h_stage_bytes = 0;
+                GP_CUDA_CHECK(cudaMallocHost(&c.h_stage, need));
+                c.h_stage_bytes = need;
+            }
+            GP_CUDA_CHECK(cudaMemcpyAsync(c.h_stage, c.d_feat, need, cudaMemcpyDeviceToHost, s));
+            staged = true;
+        }
         if (h_hops)
             GP_CUDA_CHECK(cudaMemcpyAsync(h_hops, c.d_hops, sizeof(uint16_t) * (size_t)(num_nodes * num_anchors),
                                           cudaMemcpyDeviceToHost, s));
     }
-    // concat_into_features (utils.py:129-135): x goes into columns [0, F) on the host.
+    // concat_into_features (utils.py:129-135): x goes into columns [0, F) on the host, while the
+    // GPU works.
     if (h_x != nullptr) copy_rows_parallel(h_x, num_features, h_out, ld_out, num_nodes, num_features);
+    if (staged) {
+        GP_CUDA_CHECK(cudaStreamSynchronize(s));
+        copy_rows_parallel((const float *)c.h_stage, num_anchors, h_out + col_offset, ld_out, num_nodes, num_anchors);
+    }
     gp_msbfs_stats_t local;
     GP_TRY(gp_msbfs_stats(c.bfs, stats ? stats : &local, s));  // synchronises and reports device errors
     return GP_OK;

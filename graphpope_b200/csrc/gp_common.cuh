@@ -46,6 +46,15 @@ enum : int { GP_DEV_ERR_EDGE_RANGE = 1, GP_DEV_ERR_ANCHOR_RANGE = 2, GP_DEV_ERR_
 
 int gp_sm_count();  // cached multiProcessorCount of the current device
 
+// Every kernel launch of the library goes through GP_LAUNCH so callers (bench.py) can report how
+// many of OUR kernels ran inside a timed region (gp_launch_count in the ABI).
+void gp_count_launch();
+#define GP_LAUNCH(kernel, grid, block, smem, stream, ...)                         \
+    do {                                                                          \
+        gp_count_launch();                                                        \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);               \
+    } while (0)
+
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
 

@@ -210,20 +210,19 @@ extern "C" int gp_csr_build(gp_csr_t *c, const int64_t *d_edge_index, int64_t nu
     c->in_built = false;
     GP_CUDA_CHECK(cudaMemsetAsync(c->meta, 0, GP_META_WORDS * sizeof(int), stream));
     if (num_edges > 0)
-        pack_keys_kernel<<<launch_blocks(num_edges, 256), 256, 0, stream>>>(
-            (const long long *)d_edge_index, num_edges, n, nb, sym, c->keys, c->meta);
+        GP_LAUNCH(pack_keys_kernel, launch_blocks(num_edges, 256), 256, 0, stream, (const long long *)d_edge_index, num_edges, n, nb, sym, c->keys, c->meta);
     u64 *sorted = c->keys;
     GP_TRY(gp_radix_sort(&c->sort_ws, c->keys, nullptr, nullptr, nkeys, 0, 2 * nb, stream, &sorted, nullptr));
     GP_TRY(gp_unique_sorted(sorted, c->ukeys, nullptr, nkeys, (u32 *)&c->meta[GP_META_NUM_EDGES],
                             c->uniq_status, stream));
     const int64_t work = nkeys > n + 1 ? nkeys : n + 1;
-    unpack_csr_kernel<<<launch_blocks(work, 256), 256, 0, stream>>>(c->ukeys, c->meta, n, nb, nkeys,
+    GP_LAUNCH(unpack_csr_kernel, launch_blocks(work, 256), 256, 0, stream, c->ukeys, c->meta, n, nb, nkeys,
                                                                     c->rowptr_out, c->col_out);
     if (n > 0) {
-        degree_keys_kernel<<<launch_blocks(n, 256), 256, 0, stream>>>(c->rowptr_out, n, c->okeys, c->meta);
+        GP_LAUNCH(degree_keys_kernel, launch_blocks(n, 256), 256, 0, stream, c->rowptr_out, n, c->okeys, c->meta);
         u64 *osorted = c->okeys;
         GP_TRY(gp_radix_sort(&c->sort_ws, c->okeys, nullptr, nullptr, n, 32, 48, stream, &osorted, nullptr));
-        order_kernel<<<launch_blocks(n, 256), 256, 0, stream>>>(osorted, n, c->deg_small_max, c->deg_large_min,
+        GP_LAUNCH(order_kernel, launch_blocks(n, 256), 256, 0, stream, osorted, n, c->deg_small_max, c->deg_large_min,
                                                                 c->order, c->meta);
     }
     GP_CUDA_CHECK(cudaGetLastError());
@@ -239,17 +238,17 @@ int gp_csr_ensure_in(gp_csr *c, cudaStream_t stream)
     const int64_t n = c->num_nodes;
     const int64_t cap = c->num_input_edges * ((c->flags & GP_CSR_SYMMETRIZE) ? 2 : 1);
     // c->keys (raw packed input) is dead after the unique step: reuse it for the transposed keys.
-    transpose_keys_kernel<<<launch_blocks(cap, 256), 256, 0, stream>>>(c->ukeys, c->meta, nb, cap, c->keys);
+    GP_LAUNCH(transpose_keys_kernel, launch_blocks(cap, 256), 256, 0, stream, c->ukeys, c->meta, nb, cap, c->keys);
     u64 *tsorted = c->keys;
     // distinct keys are (src,dst)-sorted, so a stable sort on the dst half alone yields (dst,src) order
     GP_TRY(gp_radix_sort(&c->sort_ws, c->keys, nullptr, (const u32 *)&c->meta[GP_META_NUM_EDGES], cap, nb,
                          2 * nb, stream, &tsorted, nullptr));
-    set_meta_kernel<<<1, 1, 0, stream>>>(c->meta, GP_META_IS_SYMMETRIC, 1);
-    symmetric_check_kernel<<<launch_blocks(cap, 256), 256, 0, stream>>>(c->ukeys, tsorted, cap, c->meta);
+    GP_LAUNCH(set_meta_kernel, 1, 1, 0, stream, c->meta, GP_META_IS_SYMMETRIC, 1);
+    GP_LAUNCH(symmetric_check_kernel, launch_blocks(cap, 256), 256, 0, stream, c->ukeys, tsorted, cap, c->meta);
     const int64_t work = cap > n + 1 ? cap : n + 1;
-    unpack_csr_kernel<<<launch_blocks(work, 256), 256, 0, stream>>>(tsorted, c->meta, n, nb, cap, c->rowptr_in,
+    GP_LAUNCH(unpack_csr_kernel, launch_blocks(work, 256), 256, 0, stream, tsorted, c->meta, n, nb, cap, c->rowptr_in,
                                                                     c->col_in);
-    set_meta_kernel<<<1, 1, 0, stream>>>(c->meta, GP_META_IN_BUILT, 1);
+    GP_LAUNCH(set_meta_kernel, 1, 1, 0, stream, c->meta, GP_META_IN_BUILT, 1);
     GP_CUDA_CHECK(cudaGetLastError());
     c->in_built = true;
     return GP_OK;

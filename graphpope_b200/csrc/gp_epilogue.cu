@@ -153,7 +153,7 @@ int gp_launch_decode_features(const GpDecodeParams &p, cudaStream_t stream)
                       (p.ld_out % 4 == 0);
     const int vec_f = aligned16(p.out) && (p.ld_out % 4 == 0) && (p.col_offset % 4 == 0) &&
                       (p.anchors_per_rank % 4 == 0 || p.num_ranks == 1);
-    decode_features_kernel<<<grid_for(p.n, 8), 256, 0, stream>>>(p, k_total, vec_x, vec_f);
+    GP_LAUNCH(decode_features_kernel, grid_for(p.n, 8), 256, 0, stream, p, k_total, vec_x, vec_f);
     GP_CUDA_CHECK(cudaGetLastError());
     return GP_OK;
 }
@@ -201,8 +201,7 @@ extern "C" int gp_msbfs_hops_u16(gp_msbfs_t *h, uint16_t *d_dist, int64_t ld, in
                "gp_msbfs_hops_u16: leading dimension too small");
     if (h->num_nodes == 0 || h->num_anchors == 0) return GP_OK;
     GpDecodeParams p = local_params(h);
-    decode_u16_kernel<<<grid_for(p.n * h->num_anchors, 256), 256, 0, (cudaStream_t)stream_>>>(
-        p, h->num_anchors, d_dist, ld, col_offset);
+    GP_LAUNCH(decode_u16_kernel, grid_for(p.n * h->num_anchors, 256), 256, 0, (cudaStream_t)stream_, p, h->num_anchors, d_dist, ld, col_offset);
     GP_CUDA_CHECK(cudaGetLastError());
     return GP_OK;
 }
@@ -251,8 +250,7 @@ extern "C" int gp_normalize_into(const uint16_t *d_dist, int64_t num_nodes, int6
                    ld_out >= col_offset + num_anchors,
                GP_ERR_INVALID, "gp_normalize_into: inconsistent sizes");
     if (num_nodes == 0 || num_anchors == 0) return GP_OK;
-    normalize_u16_kernel<<<grid_for(num_nodes * num_anchors, 256), 256, 0, (cudaStream_t)stream_>>>(
-        d_dist, num_nodes, num_anchors, ld_dist, d_out, ld_out, col_offset);
+    GP_LAUNCH(normalize_u16_kernel, grid_for(num_nodes * num_anchors, 256), 256, 0, (cudaStream_t)stream_, d_dist, num_nodes, num_anchors, ld_dist, d_out, ld_out, col_offset);
     GP_CUDA_CHECK(cudaGetLastError());
     return GP_OK;
 }

@@ -342,8 +342,11 @@ int launch_bfs(gp_msbfs *h, const BfsParams &p, cudaStream_t stream)
     }
     BfsParams pp = p;
     void *args[] = {&pp};
+    gp_count_launch();
+    GP_CUDA_CHECK(cudaEventRecord(h->ev_start, stream));
     GP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)msbfs_kernel<WB>, dim3(h->grid_blocks),
                                               dim3(GP_BFS_THREADS), args, 0, stream));
+    GP_CUDA_CHECK(cudaEventRecord(h->ev_stop, stream));
     return GP_OK;
 }
 
@@ -390,6 +393,10 @@ extern "C" int gp_msbfs_create(const gp_csr_t *csr, int64_t max_anchors, gp_msbf
     alloc((void **)&h->sync_words, 64 * sizeof(u32));
     alloc((void **)&h->status, GP_BFS_ST_WORDS * sizeof(int));
     alloc((void **)&h->counters, 4 * sizeof(u64));
+    if (rc == GP_OK && (cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess)) {
+        gp_set_error("gp_msbfs_create: cudaEventCreate failed");
+        rc = GP_ERR_CUDA;
+    }
     if (rc != GP_OK) {
         gp_msbfs_free(h);
         return rc;
@@ -408,6 +415,8 @@ extern "C" int gp_msbfs_free(gp_msbfs_t *h)
     cudaFree(h->sync_words);
     cudaFree(h->status);
     cudaFree(h->counters);
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->ev_stop) cudaEventDestroy(h->ev_stop);
     delete h;
     return GP_OK;
 }
@@ -500,6 +509,17 @@ extern "C" int gp_msbfs_stats(gp_msbfs_t *h, gp_msbfs_stats_t *stats, gp_stream_
                "anchor index outside [0, %lld)", (long long)h->num_nodes);
     GP_REQUIRE(!(st[GP_BFS_ST_ERROR] & GP_DEV_ERR_LEVEL_OVERFLOW), GP_ERR_LEVEL_OVERFLOW,
                "a hop distance reached 65535 and does not fit the uint16 distance matrix");
+    return GP_OK;
+}
+
+extern "C" int gp_msbfs_kernel_ms(gp_msbfs_t *h, float *ms)
+{
+    GP_REQUIRE(h != nullptr && ms != nullptr, GP_ERR_INVALID, "gp_msbfs_kernel_ms: NULL argument");
+    GP_REQUIRE(h->ran, GP_ERR_INVALID, "gp_msbfs_kernel_ms: gp_msbfs_run has not been called");
+    *ms = 0.0f;
+    if (h->num_nodes == 0 || h->num_anchors == 0) return GP_OK;
+    GP_CUDA_CHECK(cudaEventSynchronize(h->ev_stop));
+    GP_CUDA_CHECK(cudaEventElapsedTime(ms, h->ev_start, h->ev_stop));
     return GP_OK;
 }
 

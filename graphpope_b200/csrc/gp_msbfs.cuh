@@ -37,6 +37,7 @@ struct gp_msbfs {
     int *status = nullptr;      // [GP_BFS_ST_WORDS]
     u64 *counters = nullptr;    // [4] gathers issued, pushes issued, ...
     int grid_blocks = 0;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;  // bracket the persistent kernel alone
 };
 
 // Fused decode + concat epilogue over `num_ranks` plane sets (1 = local result).

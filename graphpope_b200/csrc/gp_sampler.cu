@@ -181,7 +181,7 @@ extern "C" int gp_degree(const gp_csr_t *csr_, int32_t *d_degree, gp_stream_t st
     GP_REQUIRE(csr->built, GP_ERR_INVALID, "gp_degree: the CSR has not been built");
     GP_TRY(gp_csr_ensure_in(csr, stream));
     if (csr->num_nodes == 0) return GP_OK;
-    degree_kernel<<<blocks_for(csr->num_nodes), 256, 0, stream>>>(csr->rowptr_out, csr->rowptr_in,
+    GP_LAUNCH(degree_kernel, blocks_for(csr->num_nodes), 256, 0, stream, csr->rowptr_out, csr->rowptr_in,
                                                                   csr->num_nodes, d_degree);
     GP_CUDA_CHECK(cudaGetLastError());
     return GP_OK;
@@ -211,16 +211,16 @@ extern "C" int gp_pagerank(const gp_csr_t *csr_, double alpha, double tol, int32
     int *dang = (int *)b_dang.p;
     double *dsum = (double *)b_small.p, *err = dsum + 1;
     int *n_dang = (int *)(dsum + 2);
-    pr_init_kernel<<<nblocks, 256, 0, stream>>>(csr->rowptr_out, n, xa, inv_out);
-    dangling_list_kernel<<<1, 32, 0, stream>>>(csr->rowptr_out, n, dang, n_dang);
+    GP_LAUNCH(pr_init_kernel, nblocks, 256, 0, stream, csr->rowptr_out, n, xa, inv_out);
+    GP_LAUNCH(dangling_list_kernel, 1, 32, 0, stream, csr->rowptr_out, n, dang, n_dang);
     const double one_minus_alpha = 1 - alpha;
     bool converged = false;
     int it = 0;
     for (it = 1; it <= max_iter; ++it) {
-        pr_contrib_kernel<<<nblocks + 1, 256, 0, stream>>>(xa, inv_out, n, contrib, dang, n_dang, dsum);
-        pr_pull_kernel<<<nblocks, 256, 0, stream>>>(csr->rowptr_in, csr->col_in, contrib, xa, n, alpha,
+        GP_LAUNCH(pr_contrib_kernel, nblocks + 1, 256, 0, stream, xa, inv_out, n, contrib, dang, n_dang, dsum);
+        GP_LAUNCH(pr_pull_kernel, nblocks, 256, 0, stream, csr->rowptr_in, csr->col_in, contrib, xa, n, alpha,
                                                     one_minus_alpha, dsum, xb, (double *)b_partial.p);
-        pr_err_kernel<<<1, 256, 0, stream>>>((const double *)b_partial.p, nblocks, err);
+        GP_LAUNCH(pr_err_kernel, 1, 256, 0, stream, (const double *)b_partial.p, nblocks, err);
         double h_err = 0.0;
         GP_CUDA_CHECK(cudaMemcpyAsync(&h_err, err, sizeof(double), cudaMemcpyDeviceToHost, stream));
         GP_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -264,14 +264,14 @@ static int topk_common(const int *d_score_i32, const double *d_score_f64, int64_
     u64 *keys = (u64 *)b_keys.p, *skeys = nullptr;
     u32 *vals = (u32 *)b_vals.p, *svals = nullptr;
     if (f64) {
-        topk_keys_f64_kernel<<<blocks_for(n), 256, 0, stream>>>(d_score_f64, n, keys, vals);
+        GP_LAUNCH(topk_keys_f64_kernel, blocks_for(n), 256, 0, stream, d_score_f64, n, keys, vals);
         rc = gp_radix_sort(&ws, keys, vals, nullptr, n, 0, 64, stream, &skeys, &svals);
     } else {
-        topk_keys_i32_kernel<<<blocks_for(n), 256, 0, stream>>>(d_score_i32, n, keys);
+        GP_LAUNCH(topk_keys_i32_kernel, blocks_for(n), 256, 0, stream, d_score_i32, n, keys);
         rc = gp_radix_sort(&ws, keys, nullptr, nullptr, n, 32, 64, stream, &skeys, nullptr);
     }
     if (rc == GP_OK) {
-        topk_emit_kernel<<<blocks_for(take), 256, 0, stream>>>(skeys, f64 ? svals : nullptr, n, take, (long long *)d_out);
+        GP_LAUNCH(topk_emit_kernel, blocks_for(take), 256, 0, stream, skeys, f64 ? svals : nullptr, n, take, (long long *)d_out);
         if (cudaGetLastError() != cudaSuccess) rc = GP_ERR_CUDA;
     }
     cudaStreamSynchronize(stream);  // temporaries are freed below

@@ -302,17 +302,15 @@ int gp_radix_sort(GpSortWorkspace *ws, u64 *keys, u32 *vals, const u32 *d_n, int
                                        (size_t)plan.npass * tiles * 256);
     GP_CUDA_CHECK(cudaMemsetAsync(ws->scratch, 0, used, stream));
     int hist_blocks = (int)(tiles < (int64_t)gp_sm_count() * 4 ? tiles : (int64_t)gp_sm_count() * 4);
-    radix_hist_kernel<<<hist_blocks, GP_SORT_THREADS, 0, stream>>>(keys, d_n, (u32)n_max, plan, hist);
+    GP_LAUNCH(radix_hist_kernel, hist_blocks, GP_SORT_THREADS, 0, stream, keys, d_n, (u32)n_max, plan, hist);
     u64 *ksrc = keys, *kdst = ws->keys_alt;
     u32 *vsrc = vals, *vdst = ws->vals_alt;
     for (int p = 0; p < plan.npass; ++p) {
         if (vals)
-            onesweep_kernel<true><<<(unsigned)tiles, GP_SORT_THREADS, 0, stream>>>(
-                ksrc, kdst, vsrc, vdst, d_n, (u32)n_max, hist + p * 256, status + (size_t)p * tiles * 256,
+            GP_LAUNCH(onesweep_kernel<true>, (unsigned)tiles, GP_SORT_THREADS, 0, stream, ksrc, kdst, vsrc, vdst, d_n, (u32)n_max, hist + p * 256, status + (size_t)p * tiles * 256,
                 counters + p, plan.shift[p], plan.width[p]);
         else
-            onesweep_kernel<false><<<(unsigned)tiles, GP_SORT_THREADS, 0, stream>>>(
-                ksrc, kdst, nullptr, nullptr, d_n, (u32)n_max, hist + p * 256,
+            GP_LAUNCH(onesweep_kernel<false>, (unsigned)tiles, GP_SORT_THREADS, 0, stream, ksrc, kdst, nullptr, nullptr, d_n, (u32)n_max, hist + p * 256,
                 status + (size_t)p * tiles * 256, counters + p, plan.shift[p], plan.width[p]);
         u64 *tk = ksrc; ksrc = kdst; kdst = tk;
         u32 *tv = vsrc; vsrc = vdst; vdst = tv;
@@ -328,7 +326,7 @@ int gp_unique_sorted(const u64 *in, u64 *out, const u32 *d_n, int64_t n_max, u32
 {
     const int64_t tiles = gp_ceil_div(n_max > 0 ? n_max : 1, GP_SORT_TILE);
     GP_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(u32) * (size_t)(tiles + 1), stream));
-    unique_kernel<<<(unsigned)tiles, GP_SORT_THREADS, 0, stream>>>(in, out, d_n, (u32)(n_max > 0 ? n_max : 0),
+    GP_LAUNCH(unique_kernel, (unsigned)tiles, GP_SORT_THREADS, 0, stream, in, out, d_n, (u32)(n_max > 0 ? n_max : 0),
                                                                    d_m, status);
     GP_CUDA_CHECK(cudaGetLastError());
     return GP_OK;

@@ -24,6 +24,11 @@ def _ptr(t: torch.Tensor | None) -> c_void_p:
     return c_void_p(0 if t is None else t.data_ptr())
 
 
+def launch_count() -> int:
+    """Kernels launched by libgraphpope_b200.so in this process so far."""
+    return int(_lib.load().gp_launch_count())
+
+
 def device_info() -> dict:
     lib = _lib.require_cuda()
     sm, major, minor = c_int32(), c_int32(), c_int32()
@@ -161,6 +166,12 @@ class MsBfs:
         st = MsbfsStats()
         check(self._lib.gp_msbfs_stats(self._h, byref(st), _stream()))
         return st.as_dict()
+
+    def kernel_ms(self) -> float:
+        """Device time of the last persistent MS-BFS kernel alone (events on its launch stream)."""
+        ms = ctypes.c_float()
+        check(self._lib.gp_msbfs_kernel_ms(self._h, byref(ms)))
+        return float(ms.value)
 
     def planes(self):
         """(uint64 view [num_planes, words], meta dict) of the bit-sliced result, for the gather."""

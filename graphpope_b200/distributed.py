@@ -1,0 +1,92 @@
+"""Anchor-sharded multi-GPU geodesic embedding (one process per GPU, torch.distributed / NCCL).
+
+The reference shards its CPU pool by *node slice* (utils.py:99-100) because its unit of work is
+a (node, anchor) pair; every DDP rank then recomputes the identical embedding (main.py:88-98).
+Here the BFS is sharded by *anchor*: the CSR is replicated, rank r owns anchors
+``[r*K/G, (r+1)*K/G)`` as its own bit lanes, and there is no exchange during traversal.  The one
+real exchange step is assembling the replicated ``[N, F+K]`` output: ranks all-gather their
+bit-sliced result planes (≈ (1 + log2(max hops)) bits per (node, anchor) instead of 16 or 32) and
+each rank's epilogue kernel decodes all shards, performing the ``[G][N][K/G] -> [N, F + g*K/G + j]``
+column permutation while it writes fp32.
+
+The host-side logic below (shard bounds, plane-count agreement, gather layout) is backend
+agnostic so the world_size-2 ``gloo`` tests can drive it with CPU tensors.
+"""
+from __future__ import annotations
+
+from ctypes import c_void_p
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(num_anchors: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous, equal anchor shards; K must divide evenly so every shard has the same lane layout."""
+    if num_anchors % world_size:
+        raise ValueError(f"num_anchor_nodes={num_anchors} must be divisible by the world size {world_size}")
+    per = num_anchors // world_size
+    return rank * per, (rank + 1) * per
+
+
+def agree_num_planes(local_num_planes: int, group=None, device="cpu") -> int:
+    """All ranks must decode the same number of planes: the max over ranks (one tiny all-reduce)."""
+    t = torch.tensor([int(local_num_planes)], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item())
+
+
+def gather_planes(local_planes: torch.Tensor, group=None) -> torch.Tensor:
+    """all-gather equal-shaped int64 plane blocks ``[P, words]`` into ``[G, P, words]``."""
+    world = dist.get_world_size(group)
+    out = torch.empty((world,) + tuple(local_planes.shape), dtype=local_planes.dtype, device=local_planes.device)
+    dist.all_gather_into_tensor(out, local_planes.contiguous(), group=group)
+    return out
+
+
+def _wrap_device_words(ptr: int, nwords: int) -> torch.Tensor:
+    """Zero-copy int64 view of library-owned device memory (the bit planes of the last run)."""
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (nwords,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(h, device="cuda")
+
+
+def sharded_geodesic_features(engine, edge_index: torch.Tensor, anchors: torch.Tensor,
+                              x: torch.Tensor | None = None, out: torch.Tensor | None = None,
+                              group=None) -> torch.Tensor:
+    """Every rank returns the full float32 ``[N, F + K]`` block; rank r ran only its K/G anchors.
+
+    ``engine`` is a :class:`graphpope_b200.device.GeodesicEngine` sized for K/G anchors;
+    ``anchors`` holds all K anchors (identical on every rank: same seed, same sampler).
+    """
+    from . import _lib
+    from ._lib import check
+    from .device import _ptr, _stream
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = engine.csr.num_nodes
+    k = anchors.numel()
+    f = 0 if x is None else x.size(1)
+    if out is None:
+        out = torch.empty((n, f + k), dtype=torch.float32, device="cuda")
+    if world == 1:
+        return engine.run(edge_index, anchors, x, out)
+    lo, hi = shard_bounds(k, world, rank)
+    engine.csr.build(edge_index)
+    engine.bfs.run(anchors[lo:hi].contiguous())
+    meta = engine.bfs.planes()  # syncs: needs max_level
+    stride = meta["plane_stride_words"]
+    num_planes = agree_num_planes(meta["num_planes"], group, device="cuda")
+    local = _wrap_device_words(meta["ptr"], (1 + 16) * stride)[: num_planes * stride].view(num_planes, stride)
+    if num_planes > meta["num_planes"]:
+        local[meta["num_planes"]:].zero_()  # planes this shard never reached hold stale bits
+    gathered = gather_planes(local, group)  # [G, P, words] int64
+    lib = _lib.load()
+    check(lib.gp_decode_gathered(_ptr(gathered), num_planes * stride, world, n, hi - lo, num_planes,
+                                 meta["batches"], meta["words_per_batch"], stride, _ptr(x), f,
+                                 x.stride(0) if x is not None and n > 1 else f, _ptr(out),
+                                 out.stride(0) if n > 1 else f + k, f, _stream()))
+    return out

@@ -88,6 +88,8 @@ const char *gp_last_error(void);
 const char *gp_status_string(int status);
 /* Device properties the host layer reports (SM count, name).  Syncs nothing. */
 int gp_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, char *name, int64_t name_cap);
+/* Number of kernels this library has launched in this process so far (bench.py's gpu_launches). */
+int64_t gp_launch_count(void);
 
 /* ------------------------------------------------------------------ CSR build
  * Replaces torch_geometric.utils.to_networkx(data) as called at utils.py:121
@@ -125,6 +127,9 @@ int gp_msbfs_features(gp_msbfs_t *bfs, const float *d_x, int64_t num_features, i
                       float *d_out, int64_t ld_out, int64_t col_offset, gp_stream_t stream);
 /* syncs.  Reports latched GP_ERR_INDEX_RANGE / GP_ERR_LEVEL_OVERFLOW. */
 int gp_msbfs_stats(gp_msbfs_t *bfs, gp_msbfs_stats_t *stats, gp_stream_t stream);
+/* syncs on the kernel's own events.  Device time of the last MS-BFS kernel launch alone (CUDA
+ * events recorded on the launch stream right around the persistent kernel), in milliseconds. */
+int gp_msbfs_kernel_ms(gp_msbfs_t *bfs, float *ms);
 int gp_msbfs_free(gp_msbfs_t *bfs);
 
 /* Bit-sliced result planes of the last run, for the multi-GPU gather
