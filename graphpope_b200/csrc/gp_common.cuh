@@ -110,8 +110,11 @@ __device__ __forceinline__ void grid_barrier(u32 *counter, u32 &target, u32 nblo
     __syncthreads();
     if (threadIdx.x == 0) {
         red_release_add_u32(counter, 1u);
-        while (ld_acquire_u32(counter) < target) {
+        // poll with relaxed loads (an acquire load invalidates this SM's L1 on every poll, which
+        // would evict lines other CTAs on the SM are still using), then acquire once
+        while (ld_relaxed_u32(counter) < target) {
         }
+        (void)ld_acquire_u32(counter);
     }
     __syncthreads();
 }

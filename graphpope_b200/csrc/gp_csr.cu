@@ -71,21 +71,100 @@ __global__ void degree_keys_kernel(const int *__restrict__ rowptr, long long n, 
     if (lane_id() == 0 && mx > 0) atomicMax(&meta[GP_META_MAX_DEGREE], mx);
 }
 
-__global__ void order_kernel(const u64 *__restrict__ okeys, long long n, int small_max, int large_min,
-                             int *__restrict__ order, int *meta)
+__global__ void order_kernel(const u64 *__restrict__ okeys, long long n, int *__restrict__ order, int *meta)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (long long i = gid; i < n; i += stride) order[i] = (int)(u32)okeys[i];
-    if (gid < 2) {
-        // rows with degree >= thr  <=>  key high half <= 65535 - thr
-        const int thr = gid == 0 ? large_min : small_max + 1;
-        int cnt = 0;
-        if (thr <= 65535) {
-            const u64 bound = (u64)(65535u - (u32)thr + 1u) << 32;  // first key with smaller degree
-            cnt = (int)lower_bound_u64(okeys, (u32)n, bound);
+    if (gid < GP_NUM_CLASSES) {
+        // rank boundary: number of rows with degree > thr  <=>  key high half < 65535 - thr
+        int cnt = (int)n;
+        if (gid < GP_NUM_CLASSES - 1) {
+            const int thr = GP_CHUNK_EDGES >> gid;  // 128, 64, 32, 16, 8
+            cnt = (int)lower_bound_u64(okeys, (u32)n, (u64)(65535u - (u32)thr) << 32);
         }
-        meta[gid == 0 ? GP_META_N_LARGE : GP_META_N_LARGE_MED] = cnt;
+        meta[GP_META_RANK + gid] = cnt;
+        if (gid == 0) meta[GP_META_NUM_HUB_ROWS] = cnt;
+    }
+}
+
+// Exclusive prefix over the hub rows (degree order) of their chunk counts; one block, running carry.
+__global__ void __launch_bounds__(1024)
+hub_scan_kernel(const int *__restrict__ order, const int *__restrict__ rowptr, int *meta,
+                int *__restrict__ chunk_off)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int nh = meta[GP_META_NUM_HUB_ROWS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nh; base += 1024) {
+        const int k = base + tid;
+        int v = 0;
+        if (k < nh) {
+            const int u = order[k];
+            v = (rowptr[u + 1] - rowptr[u] + GP_CHUNK_EDGES - 1) / GP_CHUNK_EDGES;
+        }
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(FULL_MASK, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        int wbase = 0, tot = 0;
+        for (int w = 0; w < 32; ++w) {
+            const int t = s_warp[w];
+            if (w < warp) wbase += t;
+            tot += t;
+        }
+        const int carry = s_carry;
+        if (k < nh) chunk_off[k] = carry + wbase + x - v;
+        __syncthreads();
+        if (tid == 0) s_carry = carry + tot;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const int chunks = s_carry;
+        chunk_off[nh] = chunks;
+        // class c: descriptors [ent_base[c], ent_base[c+1]), G(c) slots each, regions aligned
+        int ent = 0, slot = 0;
+        for (int c = 0; c < GP_NUM_CLASSES; ++c) {
+            const int rows = c == 0 ? chunks : meta[GP_META_RANK + c] - meta[GP_META_RANK + c - 1];
+            const int g = c <= 1 ? 16 : (16 >> (c - 1));
+            meta[GP_META_ENT_BASE + c] = ent;
+            meta[GP_META_SLOT_BASE + c] = slot;
+            ent += rows;
+            slot += (rows * g + GP_SLOT_ALIGN - 1) / GP_SLOT_ALIGN * GP_SLOT_ALIGN;
+        }
+        meta[GP_META_ENT_BASE + GP_NUM_CLASSES] = ent;
+        meta[GP_META_SLOT_BASE + GP_NUM_CLASSES] = slot;
+    }
+}
+
+// One descriptor per row (degree order), hub rows expanded into GP_CHUNK_EDGES-edge chunks.
+__global__ void desc_kernel(const int *__restrict__ order, const int *__restrict__ rowptr,
+                            const int *__restrict__ meta, const int *__restrict__ chunk_off, long long n,
+                            int4 *__restrict__ desc)
+{
+    const int nh = meta[GP_META_NUM_HUB_ROWS];
+    const int chunks = chunk_off[nh];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const int u = order[k];
+        const int s = rowptr[u], d = rowptr[u + 1] - s;
+        if (k >= nh) {
+            desc[chunks + (k - nh)] = make_int4(u, s, d, -1);
+        } else {
+            const int nch = (d + GP_CHUNK_EDGES - 1) / GP_CHUNK_EDGES;
+            const int off = chunk_off[k];
+            for (int c = 0; c < nch; ++c) {
+                const int cnt = min(GP_CHUNK_EDGES, d - c * GP_CHUNK_EDGES);
+                desc[off + c] = make_int4(u, s + c * GP_CHUNK_EDGES, cnt | (nch << 8) | (c == 0 ? 1 << 30 : 0), (int)k);
+            }
+        }
     }
 }
 
@@ -142,10 +221,8 @@ extern "C" int gp_csr_create(int64_t num_nodes, int64_t edge_capacity, uint32_t 
     int nb = 1;
     while ((1ll << nb) < num_nodes) ++nb;
     c->node_bits = nb;
-    if (const char *s = getenv("GP_DEG_SMALL_MAX")) c->deg_small_max = atoi(s);
-    if (const char *s = getenv("GP_DEG_LARGE_MIN")) c->deg_large_min = atoi(s);
-    if (c->deg_small_max < 0) c->deg_small_max = 0;
-    if (c->deg_large_min <= c->deg_small_max) c->deg_large_min = c->deg_small_max + 1;
+    c->hub_capacity = kcap / (GP_CHUNK_EDGES + 1) + 1;
+    c->desc_capacity = num_nodes + kcap / GP_CHUNK_EDGES + 2;
     const size_t kc = (size_t)(kcap > 0 ? kcap : 1), nn = (size_t)num_nodes;
     int rc = GP_OK;
     auto alloc = [&](void **p, size_t bytes) {
@@ -164,6 +241,8 @@ extern "C" int gp_csr_create(int64_t num_nodes, int64_t edge_capacity, uint32_t 
     alloc((void **)&c->col_in, kc * sizeof(int));
     alloc((void **)&c->order, (nn + 1) * sizeof(int));
     alloc((void **)&c->okeys, (nn + 1) * sizeof(u64));
+    alloc((void **)&c->desc, (size_t)c->desc_capacity * sizeof(int4));
+    alloc((void **)&c->hub_chunk_off, (size_t)(c->hub_capacity + 1) * sizeof(int));
     alloc((void **)&c->meta, GP_META_WORDS * sizeof(int));
     alloc((void **)&c->uniq_status, (size_t)(gp_ceil_div((int64_t)kc, GP_SORT_TILE) + 2) * sizeof(u32));
     if (rc == GP_OK) rc = gp_sort_workspace_create(&c->sort_ws, (int64_t)(kc > nn ? kc : nn), false);
@@ -186,6 +265,8 @@ extern "C" int gp_csr_free(gp_csr_t *c)
     cudaFree(c->col_in);
     cudaFree(c->order);
     cudaFree(c->okeys);
+    cudaFree(c->desc);
+    cudaFree(c->hub_chunk_off);
     cudaFree(c->meta);
     cudaFree(c->uniq_status);
     gp_sort_workspace_free(&c->sort_ws);
@@ -222,8 +303,10 @@ extern "C" int gp_csr_build(gp_csr_t *c, const int64_t *d_edge_index, int64_t nu
         GP_LAUNCH(degree_keys_kernel, launch_blocks(n, 256), 256, 0, stream, c->rowptr_out, n, c->okeys, c->meta);
         u64 *osorted = c->okeys;
         GP_TRY(gp_radix_sort(&c->sort_ws, c->okeys, nullptr, nullptr, n, 32, 48, stream, &osorted, nullptr));
-        GP_LAUNCH(order_kernel, launch_blocks(n, 256), 256, 0, stream, osorted, n, c->deg_small_max, c->deg_large_min,
-                                                                c->order, c->meta);
+        GP_LAUNCH(order_kernel, launch_blocks(n, 256), 256, 0, stream, osorted, n, c->order, c->meta);
+        GP_LAUNCH(hub_scan_kernel, 1, 1024, 0, stream, c->order, c->rowptr_out, c->meta, c->hub_chunk_off);
+        GP_LAUNCH(desc_kernel, launch_blocks(n, 256), 256, 0, stream, c->order, c->rowptr_out, c->meta,
+                  c->hub_chunk_off, n, c->desc);
     }
     GP_CUDA_CHECK(cudaGetLastError());
     c->built = true;

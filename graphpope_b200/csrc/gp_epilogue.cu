@@ -7,9 +7,9 @@
 // concat_into_features (utils.py:129-135) by streaming x into columns [0, F) of the same
 // output rows, so each [N, F+K] row is written once, contiguously.
 //
-// Input is the bit-sliced result of gp_msbfs.cu (plane 0 = reached mask, plane 1+p = bit p
-// of the hop distance); HBM-bound: reads (1+P)*N*K/8 bytes of planes (+4NF of x), writes
-// 4*N*(F+K) bytes.
+// Input is the result block R of gp_msbfs.cu (R[0] = reached mask, R[l] = lanes first reached at
+// hop l for l <= 15, R[16+q] = bit q of deeper hop counts); HBM-bound: reads (1+L)*N*K/8 bytes of
+// masks (+4NF of x), writes 4*N*(F+K) bytes.
 #include "gp_msbfs.cuh"
 
 namespace {
@@ -19,11 +19,22 @@ __device__ __forceinline__ float inv_hops(u32 d)
     return __fdiv_rn(1.0f, __uint2float_rn(d + 1u));
 }
 
-__device__ __forceinline__ int dist_planes(const GpDecodeParams &p)
+// How much of R is valid: hop arrays R[1..levels] and, for deep graphs, `deep` bit planes.
+struct Valid {
+    int levels, deep;
+};
+
+__device__ __forceinline__ Valid valid_arrays(const GpDecodeParams &p)
 {
-    if (p.num_dist_planes >= 0) return p.num_dist_planes;
-    const int ml = p.status[GP_BFS_ST_MAX_LEVEL];
-    return ml > 0 ? 32 - __clz(ml) : 0;
+    int na = p.num_arrays;
+    if (na < 0) {
+        const int ml = p.status[GP_BFS_ST_MAX_LEVEL];
+        na = ml <= GP_BFS_LEVEL_ARRAYS ? 1 + ml : GP_BFS_RESULT_ARRAYS;
+    }
+    Valid v;
+    v.levels = min(na - 1, GP_BFS_LEVEL_ARRAYS);
+    v.deep = na > 1 + GP_BFS_LEVEL_ARRAYS ? GP_BFS_PLANES : 0;
+    return v;
 }
 
 // Word that holds column j (global anchor index) of node u, and the bit inside it.
@@ -36,14 +47,27 @@ __device__ __forceinline__ const u64 *lane_word(const GpDecodeParams &p, long lo
     return p.planes0 + r * p.rank_stride + ((size_t)b * p.n + (size_t)u) * p.wb + w;
 }
 
-__device__ __forceinline__ float decode_one(const GpDecodeParams &p, int np, long long u, long long j)
+// Hop count of one reached lane.
+__device__ __forceinline__ u32 hops_one(const GpDecodeParams &p, Valid va, const u64 *w, int bit)
+{
+    u32 d = 0;
+    for (int l = 1; l <= va.levels; ++l)
+        if ((w[(size_t)l * p.plane_stride] >> bit) & 1ull) d = (u32)l;
+    if (va.deep) {
+        u32 dd = 0;
+        const u64 *pl = w + (size_t)(1 + GP_BFS_LEVEL_ARRAYS) * p.plane_stride;
+        for (int q = 0; q < va.deep; ++q) dd |= (u32)((pl[(size_t)q * p.plane_stride] >> bit) & 1ull) << q;
+        if (dd) d = dd;  // lanes first reached at hop >= 16 carry their whole hop count in the planes
+    }
+    return d;
+}
+
+__device__ __forceinline__ float decode_one(const GpDecodeParams &p, Valid va, long long u, long long j)
 {
     int bit;
     const u64 *w = lane_word(p, u, j, bit);
     if (!((w[0] >> bit) & 1ull)) return 0.0f;
-    u32 d = 0;
-    for (int q = 0; q < np; ++q) d |= (u32)((w[(size_t)(q + 1) * p.plane_stride] >> bit) & 1ull) << q;
-    return inv_hops(d);
+    return inv_hops(hops_one(p, va, w, bit));
 }
 
 // One warp per output row.
@@ -53,7 +77,7 @@ __global__ void __launch_bounds__(256) decode_features_kernel(GpDecodeParams p, 
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const int np = dist_planes(p);
+    const Valid va = valid_arrays(p);
     for (long long u = warp; u < p.n; u += nwarps) {
         float *orow = p.out + (size_t)u * p.ld_out;
         if (p.x != nullptr) {
@@ -79,12 +103,29 @@ __global__ void __launch_bounds__(256) decode_features_kernel(GpDecodeParams p, 
                 const u32 reach = (u32)(w[0] >> bit) & 0xFu;
                 u32 d0 = 0, d1 = 0, d2 = 0, d3 = 0;
                 if (reach) {
-                    for (int q = 0; q < np; ++q) {
-                        const u32 nib = (u32)(w[(size_t)(q + 1) * p.plane_stride] >> bit) & 0xFu;
-                        d0 |= (nib & 1u) << q;
-                        d1 |= ((nib >> 1) & 1u) << q;
-                        d2 |= ((nib >> 2) & 1u) << q;
-                        d3 |= ((nib >> 3) & 1u) << q;
+                    for (int l = 1; l <= va.levels; ++l) {
+                        const u32 nib = (u32)(w[(size_t)l * p.plane_stride] >> bit) & 0xFu;
+                        if (nib) {
+                            if (nib & 1u) d0 = l;
+                            if (nib & 2u) d1 = l;
+                            if (nib & 4u) d2 = l;
+                            if (nib & 8u) d3 = l;
+                        }
+                    }
+                    if (va.deep) {
+                        const u64 *pl = w + (size_t)(1 + GP_BFS_LEVEL_ARRAYS) * p.plane_stride;
+                        u32 e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+                        for (int q = 0; q < va.deep; ++q) {
+                            const u32 nib = (u32)(pl[(size_t)q * p.plane_stride] >> bit) & 0xFu;
+                            e0 |= (nib & 1u) << q;
+                            e1 |= ((nib >> 1) & 1u) << q;
+                            e2 |= ((nib >> 2) & 1u) << q;
+                            e3 |= ((nib >> 3) & 1u) << q;
+                        }
+                        if (e0) d0 = e0;
+                        if (e1) d1 = e1;
+                        if (e2) d2 = e2;
+                        if (e3) d3 = e3;
                     }
                 }
                 float4 v;
@@ -94,9 +135,9 @@ __global__ void __launch_bounds__(256) decode_features_kernel(GpDecodeParams p, 
                 v.w = (reach & 8u) ? inv_hops(d3) : 0.0f;
                 reinterpret_cast<float4 *>(frow)[g] = v;
             }
-            for (long long j = (groups << 2) + lane; j < k_total; j += 32) frow[j] = decode_one(p, np, u, j);
+            for (long long j = (groups << 2) + lane; j < k_total; j += 32) frow[j] = decode_one(p, va, u, j);
         } else {
-            for (long long j = lane; j < k_total; j += 32) frow[j] = decode_one(p, np, u, j);
+            for (long long j = lane; j < k_total; j += 32) frow[j] = decode_one(p, va, u, j);
         }
     }
 }
@@ -104,7 +145,7 @@ __global__ void __launch_bounds__(256) decode_features_kernel(GpDecodeParams p, 
 __global__ void __launch_bounds__(256) decode_u16_kernel(GpDecodeParams p, long long k_total, uint16_t *dist,
                                                          long long ld, long long col_offset)
 {
-    const int np = dist_planes(p);
+    const Valid va = valid_arrays(p);
     const long long total = p.n * k_total;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -112,10 +153,7 @@ __global__ void __launch_bounds__(256) decode_u16_kernel(GpDecodeParams p, long 
         int bit;
         const u64 *w = lane_word(p, u, j, bit);
         u32 d = GP_UNREACHABLE_U16;
-        if ((w[0] >> bit) & 1ull) {
-            d = 0;
-            for (int q = 0; q < np; ++q) d |= (u32)((w[(size_t)(q + 1) * p.plane_stride] >> bit) & 1ull) << q;
-        }
+        if ((w[0] >> bit) & 1ull) d = hops_one(p, va, w, bit);
         dist[(size_t)u * ld + col_offset + j] = (uint16_t)d;
     }
 }
@@ -166,7 +204,7 @@ static GpDecodeParams local_params(gp_msbfs *h)
     p.rank_stride = 0;
     p.plane_stride = (long long)h->wb * h->batches * h->num_nodes;
     p.num_ranks = 1;
-    p.num_dist_planes = -1;
+    p.num_arrays = -1;
     p.status = h->status;
     p.n = h->num_nodes;
     p.anchors_per_rank = h->num_anchors;
@@ -214,7 +252,7 @@ extern "C" int gp_decode_gathered(const uint64_t *d_gathered, int64_t rank_strid
 {
     GP_REQUIRE(d_gathered != nullptr && d_out != nullptr, GP_ERR_INVALID, "gp_decode_gathered: NULL argument");
     GP_REQUIRE(num_ranks >= 1 && num_nodes >= 0 && anchors_per_rank >= 0 && num_planes >= 1 &&
-                   num_planes <= 1 + GP_BFS_PLANES && batches >= 1 &&
+                   num_planes <= GP_BFS_RESULT_ARRAYS && batches >= 1 &&
                    (words_per_batch == 1 || words_per_batch == 2 || words_per_batch == 4),
                GP_ERR_INVALID, "gp_decode_gathered: bad shape arguments");
     GP_REQUIRE(anchors_per_rank <= (int64_t)batches * words_per_batch * 64, GP_ERR_INVALID,
@@ -227,7 +265,7 @@ extern "C" int gp_decode_gathered(const uint64_t *d_gathered, int64_t rank_strid
     p.rank_stride = rank_stride_words;
     p.plane_stride = plane_stride_words;
     p.num_ranks = num_ranks;
-    p.num_dist_planes = num_planes - 1;
+    p.num_arrays = num_planes;
     p.status = nullptr;
     p.n = num_nodes;
     p.anchors_per_rank = anchors_per_rank;

@@ -4,20 +4,26 @@
 #include "gp_common.cuh"
 #include "gp_sort.cuh"
 
-// Row classes of the degree-ordered work list (see gp_msbfs.cu).
-constexpr int GP_DEG_SMALL_MAX_DEFAULT = 16;   // <= : one thread group per row
-constexpr int GP_DEG_LARGE_MIN_DEFAULT = 512;  // >= : one CTA per row; between: one warp per row
+// Work list of the MS-BFS (see gp_msbfs.cu).  A "pair slot" gathers at most GP_SLOT_EDGES
+// neighbour rows; a row of degree d is served by G = 1,2,4,8,16 slots (G * GP_SLOT_EDGES >= d),
+// rows above 16 * GP_SLOT_EDGES edges are cut into chunks of that size (class 0).
+constexpr int GP_SLOT_EDGES = 8;
+constexpr int GP_CHUNK_EDGES = 16 * GP_SLOT_EDGES;  // 128
+constexpr int GP_NUM_CLASSES = 6;   // 0: chunks of hub rows (G=16), 1: G=16, 2: G=8, 3: G=4, 4: G=2, 5: G=1
+constexpr int GP_SLOT_ALIGN = 32;   // class regions start on a multiple of this many slots
 
 // Device-resident metadata words of a CSR (int32 each).
 enum : int {
     GP_META_NUM_EDGES = 0,    // E' after de-duplication
     GP_META_ERROR = 1,        // GP_DEV_ERR_* bits
-    GP_META_N_LARGE = 2,      // rows with degree >= large_min          (order[0 .. n_large))
-    GP_META_N_LARGE_MED = 3,  // rows with degree >  small_max          (order[0 .. n_large_med))
     GP_META_MAX_DEGREE = 4,
     GP_META_IS_SYMMETRIC = 5,
     GP_META_IN_BUILT = 6,
-    GP_META_WORDS = 16
+    GP_META_NUM_HUB_ROWS = 7,   // rows with degree > GP_CHUNK_EDGES
+    GP_META_RANK = 8,           // [6]: rows (in degree order) with degree > 128, 64, 32, 16, 8, then N
+    GP_META_ENT_BASE = 16,      // [7]: first descriptor of each class, then the total
+    GP_META_SLOT_BASE = 24,     // [7]: first pair slot of each class, then the total
+    GP_META_WORDS = 32
 };
 
 struct gp_csr {
@@ -27,8 +33,8 @@ struct gp_csr {
     int64_t num_input_edges = 0;
     uint32_t flags = 0;
     int node_bits = 1;          // bits needed for a node id
-    int deg_small_max = GP_DEG_SMALL_MAX_DEFAULT;
-    int deg_large_min = GP_DEG_LARGE_MIN_DEFAULT;
+    int64_t hub_capacity = 0;   // upper bound on rows with degree > GP_CHUNK_EDGES
+    int64_t desc_capacity = 0;  // upper bound on work-list descriptors
     bool built = false;
     bool in_built = false;      // host view of GP_META_IN_BUILT (in-edge CSR materialised)
 
@@ -39,6 +45,8 @@ struct gp_csr {
     int *rowptr_in = nullptr;   // [N + 1]  (== rowptr_out when the graph is symmetric)
     int *col_in = nullptr;      // [key_capacity]
     int *order = nullptr;       // [N] node ids by descending out-degree (ties: ascending id)
+    int4 *desc = nullptr;       // [desc_capacity] {row, first edge, count | chunks << 8, hub index or -1}
+    int *hub_chunk_off = nullptr;  // [hub_capacity + 1] first descriptor of each hub row
     u64 *okeys = nullptr;       // [N] sort keys for `order`
     int *meta = nullptr;        // [GP_META_WORDS]
     u32 *uniq_status = nullptr; // look-back words for gp_unique_sorted

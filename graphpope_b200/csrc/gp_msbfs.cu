@@ -6,23 +6,31 @@
 //
 // Formulation.  Paths run node -> anchor (row = source, utils.py:73), so the frontier moves
 // against the edge direction.  In PULL form a row u ORs the frontier words of its
-// OUT-neighbours: new[u] = (OR_{u->v} frontier[v]) & ~seen[u].  Each row is owned by exactly
-// one thread group, so there are no atomics on the lane state and a level needs one grid
-// barrier.  Rows are visited through the degree-ordered list built with the CSR
-// (gp_csr.cu): hubs get a whole CTA, medium rows a warp, short rows a thread (pair).
+// OUT-neighbours: new[u] = (OR_{u->v} frontier[v]) & ~seen[u].  Each row is finalised by exactly
+// one thread group, so there are no atomics on the lane state and a level needs one grid barrier.
 //
-// Data layout in HBM/L2 (all uint64, node-major so one neighbour gather is one 32-byte
-// sector when wb == 4):
-//   seen / frontier ping / frontier pong : [batches][N][wb]
-//   distance bit planes p = 0..15        : [batches][N][wb], bit j of plane p = bit p of
-//                                          hops(node, anchor j); written only when the lane
-//                                          is first reached (at level L every plane with a
-//                                          set bit in L is OR-ed with the new mask).
-// The uint16 / fp32 matrices are never scattered to: the epilogue (gp_epilogue.cu) decodes
-// the planes row by row with fully coalesced stores.
+// Work decomposition.  On the named graphs the lane state (a few MB) lives in L2 and a level is
+// LATENCY bound (an SM has ~6K neighbour gathers per level, i.e. ~12 per thread pair), so the
+// kernel is organised to keep dependent-load chains short and every gather of a chain in flight
+// at once: the CSR builder (gp_csr.cu) emits a degree-ordered list of 16-byte row descriptors;
+// a row of degree d is served by G = 1,2,4,8,16 "pair slots" of <= 8 edges each (G*8 >= d), hub
+// rows are cut into 128-edge chunks (G = 16) whose partial ORs meet in a small accumulator that
+// the last-arriving chunk finalises.  One slot = descriptor -> <=8 column indices -> <=8 frontier
+// rows (all issued back to back) -> shuffle-OR over the G slots of the row -> finalise.
+//
+// Data layout (all uint64, node-major so one neighbour gather is one 32-byte sector at wb == 4):
+//   result block R, 32 arrays of [batches][N][wb]:
+//     R[0]        reached mask ("seen")
+//     R[l]        l = 1..15: lanes FIRST reached at hop l.  These are simply the frontiers: level l
+//                 writes its next-frontier into R[l] and nothing ever overwrites it, so recording
+//                 the hop count costs no extra traffic at all on shallow graphs.
+//     R[16 + q]   q = 0..15: bit q of the hop count of lanes first reached at hop >= 16 (deep
+//                 graphs only; OR-ed in with fire-and-forget reductions at L2).
+//   plus the seed frontier and two ping-pong frontiers used from hop 16 on.
+// The uint16 / fp32 matrices are never scattered to: the epilogue (gp_epilogue.cu) decodes R row
+// by row with fully coalesced stores.
 #include "gp_msbfs.cuh"
 
-#include <cooperative_groups.h>
 #include <new>
 
 namespace {
@@ -31,20 +39,23 @@ struct BfsParams {
     int n;
     int batches;
     int num_anchors;
-    const int *__restrict__ rowptr;
+    int hub_capacity;
     const int *__restrict__ col;
-    const int *__restrict__ order;
-    const int *__restrict__ meta;   // csr meta words (class boundaries)
+    const int4 *__restrict__ desc;
+    const int *__restrict__ meta;   // csr meta words (class bases)
     const long long *__restrict__ anchors;
-    u64 *seen;
-    u64 *fr_a;
+    u64 *result;                    // R[0..31], see the layout note above
+    u64 *seeds;                     // level-0 frontier (the anchors)
+    u64 *fr_a;                      // ping-pong frontiers for hops >= 16
     u64 *fr_b;
-    u64 *planes;
-    long long plane_stride;         // words per plane = batches * n * wb
+    long long plane_stride;         // words per array = batches * n * wb
     u64 *live;                      // [3][GP_BFS_MAX_LANE_WORDS]
-    u32 *sync_words;
+    u64 *hub_acc;                   // [batches][hub_capacity][wb] partial ORs of hub rows
+    u32 *hub_cnt;                   // [batches][hub_capacity] chunks arrived
+    u64 *bar;                       // [2] grid barrier words (arrivals | any-count << 32), by level parity
     int *status;
     u64 *counters;
+    u64 *trace;                     // optional per-warp phase clocks (diagnostics), else nullptr
 };
 
 template <int VW>
@@ -69,15 +80,68 @@ __device__ __forceinline__ void vstore(u64 *p, const u64 (&v)[VW])
     }
 }
 
+__device__ __forceinline__ void red_or_u64(u64 *p, u64 v)
+{
+    asm volatile("red.relaxed.gpu.global.or.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ u32 atom_add_acq_rel_u32(u32 *p, u32 v)
+{
+    u32 old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p)
+{
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Grid barrier that also tells every CTA whether ANY CTA reached a new lane this level.
+// Word layout: low 32 bits = arrivals (monotone), high 32 bits = CTAs that reported `any`.
+// Two words alternate by level parity, so a CTA that is already one barrier ahead never
+// pollutes the word slower CTAs are still polling.
+__device__ __forceinline__ bool grid_barrier_any(u64 *bar_word, u32 &target, u32 &prev_any, u32 nblocks,
+                                                 bool cta_any, u32 *s_bcast, int *s_any_flag)
+{
+    target += nblocks;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *s_any_flag = 0;  // every thread has read it (before the sync above); next writes come after the sync below
+        const u64 inc = 1ull | ((u64)(cta_any ? 1u : 0u) << 32);
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(bar_word), "l"(inc) : "memory");
+        u64 v;
+        do {
+            v = ld_relaxed_u64(bar_word);  // relaxed polling: an acquire load would flush this SM's L1 each time
+        } while ((u32)v < target);
+        u32 dummy;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dummy) : "l"(bar_word) : "memory");
+        *s_bcast = (u32)(v >> 32);
+    }
+    __syncthreads();
+    const u32 total_any = *s_bcast;
+    const bool any = total_any != prev_any;
+    prev_any = total_any;
+    return any;
+}
+
+#define GP_TRACE(slot)                                                                             \
+    do {                                                                                           \
+        if (p.trace != nullptr && lane == 0 && level <= 32)                                        \
+            p.trace[(((size_t)(level - 1) * total_warps + gwarp) << 2) + (slot)] = (u64)clock64(); \
+    } while (0)
+
 template <int VW>
 struct LevelCtx {
     const u64 *cur;
     u64 *nxt;
     u64 *seen;
-    u64 *planes;
+    u64 *planes;   // R[16]: deep-hop bit planes
     long long plane_stride;
     int level;
-    int zplane;  // plane to clear during this sweep (-1: none)
+    int zero_first, zero_count;  // bit planes [zero_first, zero_first + zero_count) are cleared during this sweep
 };
 
 // Owner-side update of one row's VW lane words.
@@ -92,12 +156,13 @@ __device__ __forceinline__ void finalize_row(const LevelCtx<VW> &c, size_t off, 
         nw[i] = acc[i] & ~seenv[i];
         any |= nw[i] != 0;
     }
-    vstore<VW>(c.nxt + off, nw);
-    if (c.zplane >= 0) {
+    vstore<VW>(c.nxt + off, nw);  // for level <= 15 this IS the record "first reached at hop level"
+    if (c.zero_count > 0) {
         u64 z[VW];
 #pragma unroll
         for (int i = 0; i < VW; ++i) z[i] = 0;
-        vstore<VW>(c.planes + (size_t)c.zplane * c.plane_stride + off, z);
+        for (int q = c.zero_first; q < c.zero_first + c.zero_count; ++q)
+            vstore<VW>(c.planes + (size_t)q * c.plane_stride + off, z);
     }
     if (any) {
 #pragma unroll
@@ -106,43 +171,51 @@ __device__ __forceinline__ void finalize_row(const LevelCtx<VW> &c, size_t off, 
             live_acc[i] |= nw[i];
         }
         vstore<VW>(c.seen + off, seenv);
-        for (int lb = c.level; lb; lb &= lb - 1) {
-            u64 *pp = c.planes + (size_t)(__ffs(lb) - 1) * c.plane_stride + off;
-            u64 t[VW];
-            vload<VW>(pp, t);
+        if (c.level > GP_BFS_LEVEL_ARRAYS) {
+            // deep graphs: OR the new lanes into every bit plane set in `level` (fire-and-forget at L2)
+            for (int lb = c.level; lb; lb &= lb - 1) {
+                u64 *pp = c.planes + (size_t)(__ffs(lb) - 1) * c.plane_stride + off;
 #pragma unroll
-            for (int i = 0; i < VW; ++i) t[i] |= nw[i];
-            vstore<VW>(pp, t);
+                for (int i = 0; i < VW; ++i)
+                    if (nw[i]) red_or_u64(pp + i, nw[i]);
+            }
         }
     }
 }
 
 // WB lane words per node row; TPE threads share one edge (each loads VW = WB/TPE words).
-template <int WB>
-__global__ void __launch_bounds__(GP_BFS_THREADS, 2) msbfs_kernel(BfsParams p)
+template <int WB, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
 {
     constexpr int TPE = (WB == 4) ? 2 : 1;
     constexpr int VW = WB / TPE;
-    constexpr int PAIRS_PER_WARP = 32 / TPE;
-    constexpr int PAIRS_PER_CTA = GP_BFS_THREADS / TPE;
-    constexpr int WARPS = GP_BFS_THREADS / 32;
+    constexpr int PPW = 32 / TPE;  // pair slots per warp iteration
+    constexpr int WARPS = NT / 32;
+    constexpr u32 LEADER_MASK = (TPE == 2) ? 0x3u : 0x1u;
 
     __shared__ u32 s_live32[GP_BFS_MAX_LANE_WORDS * 2];
-    __shared__ u64 s_red[WARPS][WB];
+    __shared__ int s_ent_base[GP_NUM_CLASSES + 1];
+    __shared__ int s_slot_base[GP_NUM_CLASSES + 1];
+    __shared__ u32 s_bcast;
+    __shared__ int s_any;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int half = (TPE == 2) ? (lane & 1) : 0;
     const int woff = half * VW;
     const int pairlane = lane / TPE;
-    const long long gthreads = (long long)gridDim.x * GP_BFS_THREADS;
-    const long long gtid = (long long)blockIdx.x * GP_BFS_THREADS + tid;
+    const long long gthreads = (long long)gridDim.x * NT;
+    const long long gtid = (long long)blockIdx.x * NT + tid;
     const int gwarp = blockIdx.x * WARPS + warp, total_warps = gridDim.x * WARPS;
-    const long long gpair = gtid / TPE, total_pairs = gthreads / TPE;
     const int n = p.n, lw = p.batches * WB;
-    u32 bar_target = 0;
+    u32 bar_target[2] = {0, 0}, bar_prev_any[2] = {0, 0};
     u64 gathers = 0;
 
-    for (int i = tid; i < GP_BFS_MAX_LANE_WORDS * 2; i += GP_BFS_THREADS) s_live32[i] = 0;
+    for (int i = tid; i < GP_BFS_MAX_LANE_WORDS * 2; i += NT) s_live32[i] = 0;
+    if (tid <= GP_NUM_CLASSES) {
+        s_ent_base[tid] = p.meta[GP_META_ENT_BASE + tid];
+        s_slot_base[tid] = p.meta[GP_META_SLOT_BASE + tid];
+    }
+    if (tid == 0) s_any = 0;
 
     // ---- level 0: seed the anchors (duplicates simply set their own lane bits)
     for (long long j = gtid; j < p.num_anchors; j += gthreads) {
@@ -154,35 +227,43 @@ __global__ void __launch_bounds__(GP_BFS_THREADS, 2) msbfs_kernel(BfsParams p)
         const int b = (int)(j / (64 * WB)), w = (int)((j / 64) % WB);
         const u64 bit = 1ull << (j & 63);
         const size_t off = ((size_t)b * n + (size_t)a) * WB + w;
-        atomicOr(p.seen + off, bit);
-        atomicOr(p.fr_a + off, bit);
+        atomicOr(p.result + off, bit);
+        atomicOr(p.seeds + off, bit);
         atomicOr(p.live + 1 * GP_BFS_MAX_LANE_WORDS + b * WB + w, bit);
     }
-    grid_barrier(p.sync_words, bar_target, gridDim.x);
-
-    const int n_large = p.meta[GP_META_N_LARGE];
-    const int n_lm = p.meta[GP_META_N_LARGE_MED];
-    const int n_med = n_lm - n_large, n_small = n - n_lm;
+    grid_barrier_any(p.bar + 0, bar_target[0], bar_prev_any[0], gridDim.x, false, &s_bcast, &s_any);
+    const int total_slots = s_slot_base[GP_NUM_CLASSES];
 
     int level = 1, max_level = 0;
     while (true) {
-        if (level >= (int)GP_UNREACHABLE_U16) {
-            if (gtid == 0) atomicOr(&p.status[GP_BFS_ST_ERROR], GP_DEV_ERR_LEVEL_OVERFLOW);
-            break;
-        }
         LevelCtx<VW> c;
-        c.cur = (level & 1) ? p.fr_a : p.fr_b;
-        c.nxt = (level & 1) ? p.fr_b : p.fr_a;
-        c.seen = p.seen;
-        c.planes = p.planes;
+        // frontier of hop l lives in R[l] for l <= 15, then in the ping-pong pair
+        auto frontier = [&](int l) -> u64 * {
+            if (l == 0) return p.seeds;
+            if (l <= GP_BFS_LEVEL_ARRAYS) return p.result + (size_t)l * p.plane_stride;
+            return (l & 1) ? p.fr_a : p.fr_b;
+        };
+        c.cur = frontier(level - 1);
+        c.nxt = frontier(level);
+        c.seen = p.result;
+        c.planes = p.result + (size_t)(1 + GP_BFS_LEVEL_ARRAYS) * p.plane_stride;
         c.plane_stride = p.plane_stride;
         c.level = level;
-        c.zplane = ((level + 1) & level) == 0 ? (31 - __clz(level + 1)) : -1;
-        if (c.zplane >= GP_BFS_PLANES) c.zplane = -1;
+        // planes are first needed at hop 16 = 2^4: clear planes 0..4 one level ahead, and every
+        // higher plane q one level before hop 2^q first sets it
+        c.zero_first = 0;
+        c.zero_count = 0;
+        if (level == GP_BFS_LEVEL_ARRAYS) {
+            c.zero_count = 5;
+        } else if (level > GP_BFS_LEVEL_ARRAYS && ((level + 1) & level) == 0 && 31 - __clz(level + 1) < GP_BFS_PLANES) {
+            c.zero_first = 31 - __clz(level + 1);
+            c.zero_count = 1;
+        }
         const u64 *live_r = p.live + (level % 3) * GP_BFS_MAX_LANE_WORDS;
         u64 *live_w = p.live + ((level + 1) % 3) * GP_BFS_MAX_LANE_WORDS;
         u64 *live_z = p.live + ((level + 2) % 3) * GP_BFS_MAX_LANE_WORDS;
         if (blockIdx.x == 0 && tid < lw) live_z[tid] = 0;
+        GP_TRACE(0);
 
         for (int b = 0; b < p.batches; ++b) {
             u64 lv[VW], live_acc[VW];
@@ -191,128 +272,141 @@ __global__ void __launch_bounds__(GP_BFS_THREADS, 2) msbfs_kernel(BfsParams p)
                 lv[i] = live_r[b * WB + woff + i];
                 live_acc[i] = 0;
             }
-            const size_t bbase = (size_t)b * n;
+            const u64 *cur_b = c.cur + (size_t)b * n * WB + woff;
 
-            // ---- hubs: one CTA per row
-            for (int k = blockIdx.x; k < n_large; k += gridDim.x) {
-                const int u = p.order[k];
-                const int s = __ldg(p.rowptr + u), e = __ldg(p.rowptr + u + 1);
-                const size_t off = (bbase + u) * WB + woff;
+            // software pipeline: the descriptor of the next warp-iteration is fetched one iteration ahead
+            int t0 = gwarp * PPW;
+            int cls = 0;
+            int4 d_next = make_int4(0, 0, 0, -1);
+            bool act_next = false;
+            int sub_next = 0, gsh_next = 0;
+            auto fetch = [&](int t) {
+                while (t >= s_slot_base[cls + 1]) ++cls;  // regions are GP_SLOT_ALIGN aligned: warp-uniform
+                gsh_next = cls <= 1 ? 4 : 5 - cls;        // log2 of slots per row: 16,16,8,4,2,1
+                const int rel = t - s_slot_base[cls] + pairlane;
+                const int ent = s_ent_base[cls] + (rel >> gsh_next);
+                sub_next = rel & ((1 << gsh_next) - 1);
+                act_next = ent < s_ent_base[cls + 1];
+                d_next = act_next ? __ldg(p.desc + ent) : make_int4(0, 0, 0, -1);
+            };
+            if (t0 < total_slots) fetch(t0);
+            while (t0 < total_slots) {
+                const int4 d = d_next;
+                const bool active = act_next;
+                const int sub = sub_next, gsh = gsh_next;
+                const int cnt = d.z & 0xFF, nch = (d.z >> 8) & 0x3FFFFF;
+                const bool first_chunk = (d.z >> 30) & 1;
+                const size_t off = ((size_t)b * n + (size_t)d.x) * WB + woff;
+                // phase 1: this slot's column indices (sub, sub + G, ...: consecutive slots read consecutive
+                // columns) and the row's seen words, all independent
+                int v[GP_SLOT_EDGES];
+#pragma unroll
+                for (int i = 0; i < GP_SLOT_EDGES; ++i) {
+                    // padding edges point back at the row itself: frontier[u] is a subset of seen[u],
+                    // so it contributes nothing to acc & ~seen and the gathers below need no predicates
+                    const int idx = sub + (i << gsh);
+                    v[i] = idx < cnt ? __ldg(p.col + d.y + idx) : d.x;
+                }
                 u64 seenv[VW], acc[VW];
-                vload<VW>(p.seen + off, seenv);
-                bool need = false;
 #pragma unroll
                 for (int i = 0; i < VW; ++i) {
+                    seenv[i] = ~0ull;
                     acc[i] = 0;
-                    need |= (~seenv[i] & lv[i]) != 0;
                 }
-                if (need) {
-                    for (int j = s + tid / TPE; j < e; j += PAIRS_PER_CTA) {
-                        const int v = __ldg(p.col + j);
-                        u64 t[VW];
-                        vload<VW>(c.cur + (bbase + v) * WB + woff, t);
-#pragma unroll
-                        for (int i = 0; i < VW; ++i) acc[i] |= t[i];
-                        gathers += VW;
-                    }
-                }
-#pragma unroll
-                for (int m = TPE; m < 32; m <<= 1)
-#pragma unroll
-                    for (int i = 0; i < VW; ++i) acc[i] |= shfl_xor_u64(acc[i], m);
-                if (lane < TPE)
-#pragma unroll
-                    for (int i = 0; i < VW; ++i) s_red[warp][woff + i] = acc[i];
-                __syncthreads();
-                if (warp == 0 && lane < TPE) {
-#pragma unroll
-                    for (int w = 1; w < WARPS; ++w)
-#pragma unroll
-                        for (int i = 0; i < VW; ++i) acc[i] |= s_red[w][woff + i];
-                    finalize_row<VW>(c, off, acc, seenv, live_acc);
-                }
-                __syncthreads();
-            }
-
-            // ---- medium rows: one warp per row
-            for (int k = gwarp; k < n_med; k += total_warps) {
-                const int u = p.order[n_large + k];
-                const int s = __ldg(p.rowptr + u), e = __ldg(p.rowptr + u + 1);
-                const size_t off = (bbase + u) * WB + woff;
-                u64 seenv[VW], acc[VW];
-                vload<VW>(p.seen + off, seenv);
+                if (active) vload<VW>(p.result + off, seenv);
+                t0 += total_warps * PPW;
+                if (t0 < total_slots) fetch(t0);
                 bool need = false;
 #pragma unroll
-                for (int i = 0; i < VW; ++i) {
-                    acc[i] = 0;
-                    need |= (~seenv[i] & lv[i]) != 0;
-                }
+                for (int i = 0; i < VW; ++i) need |= (~seenv[i] & lv[i]) != 0;
+                // row-level verdict (both halves of the pair agree on it; used by the hub protocol)
+                bool need_row = need;
+                if constexpr (TPE == 2) need_row |= __shfl_xor_sync(FULL_MASK, (int)need, 1) != 0;
+                // phase 2: all neighbour rows of the slot in flight at once
                 if (need) {
-                    for (int j = s + pairlane; j < e; j += PAIRS_PER_WARP) {
-                        const int v = __ldg(p.col + j);
-                        u64 t[VW];
-                        vload<VW>(c.cur + (bbase + v) * WB + woff, t);
+                    u64 t[GP_SLOT_EDGES][VW];
 #pragma unroll
-                        for (int i = 0; i < VW; ++i) acc[i] |= t[i];
-                        gathers += VW;
-                    }
+                    for (int i = 0; i < GP_SLOT_EDGES; ++i) vload<VW>(cur_b + (size_t)(u32)v[i] * WB, t[i]);
+#pragma unroll
+                    for (int i = 0; i < GP_SLOT_EDGES; ++i)
+#pragma unroll
+                        for (int q = 0; q < VW; ++q) acc[q] |= t[i][q];
+                    gathers += (u64)VW * (u64)max(0, min(GP_SLOT_EDGES, (cnt - sub + (1 << gsh) - 1) >> gsh));
                 }
+                // OR over the G slots of the row (warp-uniform trip count)
+                for (int m = TPE; m < (TPE << gsh); m <<= 1)
 #pragma unroll
-                for (int m = TPE; m < 32; m <<= 1)
-#pragma unroll
-                    for (int i = 0; i < VW; ++i) acc[i] |= shfl_xor_u64(acc[i], m);
-                if (lane < TPE) finalize_row<VW>(c, off, acc, seenv, live_acc);
-            }
+                    for (int q = 0; q < VW; ++q) acc[q] |= shfl_xor_u64(acc[q], m);
 
-            // ---- short rows: one thread (pair) per row, no cross-lane traffic
-            for (long long k = gpair; k < n_small; k += total_pairs) {
-                const int u = p.order[n_lm + k];
-                const int s = __ldg(p.rowptr + u), e = __ldg(p.rowptr + u + 1);
-                const size_t off = (bbase + u) * WB + woff;
-                u64 seenv[VW], acc[VW];
-                vload<VW>(p.seen + off, seenv);
-                bool need = false;
+                if (active && sub == 0) {
+                    if (nch == 0) {
+                        finalize_row<VW>(c, off, acc, seenv, live_acc);
+                    } else if (!need_row) {
+                        // hub row with nothing left to reach (every chunk sees the same seen / live
+                        // words, so all agree): its first chunk alone writes the empty frontier
+                        if (first_chunk) finalize_row<VW>(c, off, acc, seenv, live_acc);
+                    } else {
+                        // hub chunk: deposit the partial OR; the last chunk to arrive finalises the row.
+                        // All traffic on hub_acc / hub_cnt is L2 atomics; waiting for the OR's return
+                        // value orders it before the arrival count without a fence.
+                        const size_t hidx = (size_t)b * p.hub_capacity + (size_t)d.w;
+                        u64 *accp = p.hub_acc + hidx * WB + woff;
+                        u64 dep = 0;
 #pragma unroll
-                for (int i = 0; i < VW; ++i) {
-                    acc[i] = 0;
-                    need |= (~seenv[i] & lv[i]) != 0;
-                }
-                if (need) {
-#pragma unroll 4
-                    for (int j = s; j < e; ++j) {
-                        const int v = __ldg(p.col + j);
-                        u64 t[VW];
-                        vload<VW>(c.cur + (bbase + v) * WB + woff, t);
+                        for (int q = 0; q < VW; ++q)
+                            if (acc[q]) dep |= atomicOr(accp + q, acc[q]);
+                        u32 old = 0;
+                        if constexpr (TPE == 2) {
+                            dep |= __shfl_xor_sync(LEADER_MASK, (u32)dep | (u32)(dep >> 32), 1);  // other half's returns
+                            asm volatile("" ::"l"(dep) : "memory");  // the ORs have returned from L2 before we count
+                            if (half == 0) old = atomicAdd(p.hub_cnt + hidx, 1u);
+                            old = __shfl_sync(LEADER_MASK, old, 0);
+                        } else {
+                            asm volatile("" ::"l"(dep) : "memory");
+                            old = atomicAdd(p.hub_cnt + hidx, 1u);
+                        }
+                        if (old == (u32)nch - 1u) {
+                            u64 comb[VW];
 #pragma unroll
-                        for (int i = 0; i < VW; ++i) acc[i] |= t[i];
+                            for (int q = 0; q < VW; ++q) comb[q] = atomicExch(accp + q, 0ull);
+                            if (half == 0) p.hub_cnt[hidx] = 0;
+                            finalize_row<VW>(c, off, comb, seenv, live_acc);
+                        }
                     }
-                    gathers += (u64)VW * (u64)(e - s);
                 }
-                finalize_row<VW>(c, off, acc, seenv, live_acc);
             }
 
             // ---- fold this batch's newly reached lanes into the CTA's live words
 #pragma unroll
             for (int i = 0; i < VW; ++i) {
-                u64 v = live_acc[i];
+                u64 x = live_acc[i];
 #pragma unroll
-                for (int m = TPE; m < 32; m <<= 1) v |= shfl_xor_u64(v, m);
-                if (lane < TPE && v) {
-                    atomicOr(&s_live32[(b * WB + woff + i) * 2], (u32)v);
-                    atomicOr(&s_live32[(b * WB + woff + i) * 2 + 1], (u32)(v >> 32));
+                for (int m = TPE; m < 32; m <<= 1) x |= shfl_xor_u64(x, m);
+                if (lane < TPE && x) {
+                    atomicOr(&s_live32[(b * WB + woff + i) * 2], (u32)x);
+                    atomicOr(&s_live32[(b * WB + woff + i) * 2 + 1], (u32)(x >> 32));
+                    s_any = 1;
                 }
             }
         }
+        GP_TRACE(3);
         __syncthreads();
         if (tid < lw) {
-            const u64 v = ((u64)s_live32[tid * 2 + 1] << 32) | s_live32[tid * 2];
-            if (v) atomicOr(live_w + tid, v);
+            const u64 x = ((u64)s_live32[tid * 2 + 1] << 32) | s_live32[tid * 2];
+            if (x) atomicOr(live_w + tid, x);
             s_live32[tid * 2] = 0;
             s_live32[tid * 2 + 1] = 0;
         }
-        grid_barrier(p.sync_words, bar_target, gridDim.x);
-        const int any = __syncthreads_or(tid < lw && live_w[tid] != 0);
+        const bool cta_any = s_any != 0;
+        const int par = level & 1;
+        const bool any = grid_barrier_any(p.bar + par, bar_target[par], bar_prev_any[par], gridDim.x, cta_any,
+                                          &s_bcast, &s_any);
         if (!any) break;
+        if (level >= (int)GP_UNREACHABLE_U16) {
+            // a lane was first reached at hop 65535: not representable next to the 0xFFFF sentinel
+            if (gtid == 0) atomicOr(&p.status[GP_BFS_ST_ERROR], GP_DEV_ERR_LEVEL_OVERFLOW);
+            break;
+        }
         max_level = level;
         ++level;
     }
@@ -322,32 +416,51 @@ __global__ void __launch_bounds__(GP_BFS_THREADS, 2) msbfs_kernel(BfsParams p)
     if (lane == 0 && gathers) atomicAdd(p.counters, gathers);
     if (gtid == 0) {
         p.status[GP_BFS_ST_MAX_LEVEL] = max_level;
-        p.status[GP_BFS_ST_LEVELS] = level < (int)GP_UNREACHABLE_U16 ? level : level - 1;
-        p.status[GP_BFS_ST_PULL] = level < (int)GP_UNREACHABLE_U16 ? level : level - 1;
+        p.status[GP_BFS_ST_LEVELS] = level;
+        p.status[GP_BFS_ST_PULL] = level;
     }
 }
 
-template <int WB>
-int launch_bfs(gp_msbfs *h, const BfsParams &p, cudaStream_t stream)
+template <int WB, int NT, int MINB>
+int launch_bfs_cfg(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int cfg_id)
 {
-    if (h->grid_blocks == 0) {
+    if (h->grid_blocks == 0 || h->grid_cfg != cfg_id * 8 + WB) {
         int occ = 0;
-        GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, msbfs_kernel<WB>, GP_BFS_THREADS, 0));
+        GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, msbfs_kernel<WB, NT, MINB>, NT, 0));
         GP_REQUIRE(occ >= 1, GP_ERR_CUDA, "msbfs kernel does not fit on an SM");
-        if (const char *s = getenv("GP_BFS_CTAS_PER_SM")) {
-            const int want = atoi(s);
-            if (want >= 1 && want < occ) occ = want;
-        }
+        if (occ > MINB) occ = MINB;
         h->grid_blocks = occ * gp_sm_count();
+        h->grid_cfg = cfg_id * 8 + WB;
+        h->block_threads = NT;
     }
     BfsParams pp = p;
     void *args[] = {&pp};
     gp_count_launch();
     GP_CUDA_CHECK(cudaEventRecord(h->ev_start, stream));
-    GP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)msbfs_kernel<WB>, dim3(h->grid_blocks),
-                                              dim3(GP_BFS_THREADS), args, 0, stream));
+    GP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)msbfs_kernel<WB, NT, MINB>, dim3(h->grid_blocks),
+                                              dim3(NT), args, 0, stream));
     GP_CUDA_CHECK(cudaEventRecord(h->ev_stop, stream));
     return GP_OK;
+}
+
+// Launch shapes (threads per CTA, CTAs per SM) trade resident warps against registers per thread,
+// i.e. against how many neighbour gathers one thread keeps in flight.  GP_BFS_CFG picks one.
+template <int WB>
+int launch_bfs(gp_msbfs *h, const BfsParams &p, cudaStream_t stream)
+{
+    static int cfg = -1;
+    if (cfg < 0) {
+        const char *s = getenv("GP_BFS_CFG");
+        cfg = s ? atoi(s) : GP_BFS_DEFAULT_CFG;
+        if (cfg < 0 || cfg > 4) cfg = GP_BFS_DEFAULT_CFG;
+    }
+    switch (cfg) {
+        case 0: return launch_bfs_cfg<WB, 512, 2>(h, p, stream, 0);   // 64 regs, 32 warps/SM
+        case 1: return launch_bfs_cfg<WB, 384, 2>(h, p, stream, 1);   // 85 regs, 24 warps/SM
+        case 2: return launch_bfs_cfg<WB, 512, 1>(h, p, stream, 2);   // 128 regs, 16 warps/SM
+        case 3: return launch_bfs_cfg<WB, 1024, 1>(h, p, stream, 3);  // 64 regs, 32 warps/SM, half the CTAs
+        default: return launch_bfs_cfg<WB, 256, 3>(h, p, stream, 4);  // 85 regs, 24 warps/SM
+    }
 }
 
 }  // namespace
@@ -385,14 +498,18 @@ extern "C" int gp_msbfs_create(const gp_csr_t *csr, int64_t max_anchors, gp_msbf
             rc = (e == cudaErrorMemoryAllocation) ? GP_ERR_OOM : GP_ERR_CUDA;
         }
     };
-    // seen is plane 0 of the result; the 16 distance planes follow it contiguously
-    alloc((void **)&h->seen, (size_t)(1 + GP_BFS_PLANES) * words * sizeof(u64));
-    alloc((void **)&h->fr_a, 2 * words * sizeof(u64));
+    // result block R[0..31] (reached mask, 15 first-reached-at-hop arrays, 16 deep-hop bit planes),
+    // then the seed frontier and the ping-pong pair
+    alloc((void **)&h->seen, (size_t)GP_BFS_RESULT_ARRAYS * words * sizeof(u64));
+    alloc((void **)&h->fr_a, 3 * words * sizeof(u64));
     alloc((void **)&h->live, 3 * GP_BFS_MAX_LANE_WORDS * sizeof(u64));
-    alloc((void **)&h->queue, (size_t)(h->num_nodes + 1) * sizeof(int));
-    alloc((void **)&h->sync_words, 64 * sizeof(u32));
+    h->hub_capacity = csr->hub_capacity;
+    alloc((void **)&h->hub_acc, (size_t)h->hub_capacity * (size_t)h->cap_words_per_node * sizeof(u64));
+    alloc((void **)&h->hub_cnt, (size_t)h->hub_capacity * (size_t)h->cap_words_per_node * sizeof(u32));
+    alloc((void **)&h->bar, 8 * sizeof(u64));
     alloc((void **)&h->status, GP_BFS_ST_WORDS * sizeof(int));
     alloc((void **)&h->counters, 4 * sizeof(u64));
+    if (getenv("GP_BFS_TRACE")) alloc((void **)&h->trace, GP_BFS_TRACE_WORDS * sizeof(u64));
     if (rc == GP_OK && (cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess)) {
         gp_set_error("gp_msbfs_create: cudaEventCreate failed");
         rc = GP_ERR_CUDA;
@@ -411,10 +528,12 @@ extern "C" int gp_msbfs_free(gp_msbfs_t *h)
     cudaFree(h->seen);
     cudaFree(h->fr_a);
     cudaFree(h->live);
-    cudaFree(h->queue);
-    cudaFree(h->sync_words);
+    cudaFree(h->hub_acc);
+    cudaFree(h->hub_cnt);
+    cudaFree(h->bar);
     cudaFree(h->status);
     cudaFree(h->counters);
+    cudaFree(h->trace);
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     if (h->ev_stop) cudaEventDestroy(h->ev_stop);
     delete h;
@@ -440,44 +559,46 @@ extern "C" int gp_msbfs_run(gp_msbfs_t *h, const int64_t *d_anchors, int64_t num
     const int64_t n = h->num_nodes;
     const size_t words = (size_t)wb * batches * (size_t)n;
     h->fr_b = h->fr_a + words;
-    h->planes = h->seen + words;
+    h->seeds = h->fr_a + 2 * words;
     GP_CUDA_CHECK(cudaMemsetAsync(h->status, 0, GP_BFS_ST_WORDS * sizeof(int), stream));
     GP_CUDA_CHECK(cudaMemsetAsync(h->counters, 0, 4 * sizeof(u64), stream));
     if (n == 0 || num_anchors == 0) {
         h->ran = true;
         return GP_OK;
     }
-    // seen + distance plane 0 are contiguous; frontier ping separately
-    GP_CUDA_CHECK(cudaMemsetAsync(h->seen, 0, 2 * words * sizeof(u64), stream));
-    GP_CUDA_CHECK(cudaMemsetAsync(h->fr_a, 0, words * sizeof(u64), stream));
+    GP_CUDA_CHECK(cudaMemsetAsync(h->seen, 0, words * sizeof(u64), stream));
+    GP_CUDA_CHECK(cudaMemsetAsync(h->seeds, 0, words * sizeof(u64), stream));
     GP_CUDA_CHECK(cudaMemsetAsync(h->live, 0, 3 * GP_BFS_MAX_LANE_WORDS * sizeof(u64), stream));
-    GP_CUDA_CHECK(cudaMemsetAsync(h->sync_words, 0, 64 * sizeof(u32), stream));
+    GP_CUDA_CHECK(cudaMemsetAsync(h->bar, 0, 8 * sizeof(u64), stream));
+    if (!h->hub_zeroed) {
+        // the kernel leaves these zeroed again (the finalising chunk resets its row's words)
+        GP_CUDA_CHECK(cudaMemsetAsync(h->hub_acc, 0, (size_t)h->hub_capacity * h->cap_words_per_node * sizeof(u64), stream));
+        GP_CUDA_CHECK(cudaMemsetAsync(h->hub_cnt, 0, (size_t)h->hub_capacity * h->cap_words_per_node * sizeof(u32), stream));
+        h->hub_zeroed = true;
+    }
     BfsParams p;
     p.n = (int)n;
     p.batches = batches;
     p.num_anchors = (int)num_anchors;
-    p.rowptr = h->csr->rowptr_out;
+    p.hub_capacity = (int)h->hub_capacity;
+    p.desc = h->csr->desc;
+    p.hub_acc = h->hub_acc;
+    p.hub_cnt = h->hub_cnt;
+    p.bar = h->bar;
     p.col = h->csr->col_out;
-    p.order = h->csr->order;
     p.meta = h->csr->meta;
     p.anchors = (const long long *)d_anchors;
-    p.seen = h->seen;
+    p.result = h->seen;
+    p.seeds = h->seeds;
     p.fr_a = h->fr_a;
     p.fr_b = h->fr_b;
-    p.planes = h->planes;
     p.plane_stride = (long long)words;
     p.live = h->live;
-    p.sync_words = h->sync_words;
     p.status = h->status;
     p.counters = h->counters;
-    int prev_grid = h->grid_blocks;
-    static int grid_for_wb[5] = {0, 0, 0, 0, 0};
-    h->grid_blocks = grid_for_wb[wb];
-    int rc = wb == 1 ? launch_bfs<1>(h, p, stream) : wb == 2 ? launch_bfs<2>(h, p, stream)
-                                                             : launch_bfs<4>(h, p, stream);
-    grid_for_wb[wb] = h->grid_blocks;
-    (void)prev_grid;
-    GP_TRY(rc);
+    p.trace = h->trace;
+    GP_TRY(wb == 1 ? launch_bfs<1>(h, p, stream) : wb == 2 ? launch_bfs<2>(h, p, stream)
+                                                             : launch_bfs<4>(h, p, stream));
     h->ran = true;
     return GP_OK;
 }
@@ -512,6 +633,21 @@ extern "C" int gp_msbfs_stats(gp_msbfs_t *h, gp_msbfs_stats_t *stats, gp_stream_
     return GP_OK;
 }
 
+extern "C" int gp_msbfs_trace(gp_msbfs_t *h, uint64_t *h_out, int64_t cap_words, int32_t *levels, int32_t *warps)
+{
+    GP_REQUIRE(h != nullptr && h_out != nullptr && levels && warps, GP_ERR_INVALID, "gp_msbfs_trace: NULL argument");
+    GP_REQUIRE(h->trace != nullptr, GP_ERR_INVALID, "gp_msbfs_trace: set GP_BFS_TRACE=1 before gp_msbfs_create");
+    gp_msbfs_stats_t st;
+    gp_msbfs_stats(h, &st, nullptr);
+    GP_CUDA_CHECK(cudaDeviceSynchronize());
+    *levels = st.levels_run < 32 ? st.levels_run : 32;
+    *warps = h->grid_blocks * (h->block_threads / 32);
+    const int64_t words = (int64_t)(*levels) * (*warps) * 4;
+    GP_REQUIRE(words <= cap_words && words <= GP_BFS_TRACE_WORDS, GP_ERR_INVALID, "gp_msbfs_trace: buffer too small");
+    GP_CUDA_CHECK(cudaMemcpy(h_out, h->trace, sizeof(u64) * (size_t)words, cudaMemcpyDeviceToHost));
+    return GP_OK;
+}
+
 extern "C" int gp_msbfs_kernel_ms(gp_msbfs_t *h, float *ms)
 {
     GP_REQUIRE(h != nullptr && ms != nullptr, GP_ERR_INVALID, "gp_msbfs_kernel_ms: NULL argument");
@@ -531,11 +667,9 @@ extern "C" int gp_msbfs_planes(gp_msbfs_t *h, const uint64_t **d_planes, int64_t
                GP_ERR_INVALID, "gp_msbfs_planes: NULL argument");
     gp_msbfs_stats_t st;
     GP_TRY(gp_msbfs_stats(h, &st, stream_));
-    int bits = 0;
-    while ((1 << bits) <= st.max_level) ++bits;
     *d_planes = (const uint64_t *)h->seen;
     *plane_stride_words = (int64_t)h->wb * h->batches * h->num_nodes;
-    *num_planes = 1 + bits;
+    *num_planes = st.max_level <= GP_BFS_LEVEL_ARRAYS ? 1 + st.max_level : GP_BFS_RESULT_ARRAYS;
     *batches = h->batches;
     *words_per_batch = h->wb;
     return GP_OK;

@@ -3,9 +3,12 @@
 
 #include "gp_internal.h"
 
-constexpr int GP_BFS_THREADS = 512;
+constexpr int GP_BFS_DEFAULT_CFG = 1;       // see launch_bfs in gp_msbfs.cu
 constexpr int GP_BFS_MAX_LANE_WORDS = 256;  // B * WB cap (K <= 16384 per GPU)
-constexpr int GP_BFS_PLANES = 16;           // distance bit planes (uint16 range)
+constexpr int GP_BFS_PLANES = 16;           // deep-hop distance bit planes (uint16 range)
+constexpr int GP_BFS_LEVEL_ARRAYS = 15;     // hops 1..15 are recorded as write-once frontier arrays
+constexpr int GP_BFS_RESULT_ARRAYS = 1 + GP_BFS_LEVEL_ARRAYS + GP_BFS_PLANES;  // 32
+constexpr long long GP_BFS_TRACE_WORDS = 32ll * 160 * 4 * 32 * 4;  // levels * max warps * 4 slots           // distance bit planes (uint16 range)
 
 enum : int {
     GP_BFS_ST_MAX_LEVEL = 0,
@@ -27,27 +30,33 @@ struct gp_msbfs {
     int batches = 0;   // independent 64*wb-anchor batches
     bool ran = false;
 
-    u64 *seen = nullptr;     // [batches][N][wb]   "reached" masks (plane 0 of the result)
-    u64 *fr_a = nullptr;     // frontier ping
+    u64 *seen = nullptr;     // result block R[0..31], each [batches][N][wb]; R[0] = reached mask (gp_msbfs.cu)
+    u64 *fr_a = nullptr;     // frontier ping (hops >= 16)
     u64 *fr_b = nullptr;     // frontier pong
-    u64 *planes = nullptr;   // [GP_BFS_PLANES][batches][N][wb] bit-sliced hop distance
+    u64 *seeds = nullptr;    // hop-0 frontier
     u64 *live = nullptr;     // [3][GP_BFS_MAX_LANE_WORDS]
-    int *queue = nullptr;    // [N] compacted active rows (push levels)
-    u32 *sync_words = nullptr;  // [0] grid barrier, [1..] queue cursors / counters
+    u64 *hub_acc = nullptr;  // [batches][hub_capacity][wb] partial ORs of hub rows (zero between levels)
+    u32 *hub_cnt = nullptr;  // [batches][hub_capacity] hub chunks arrived (zero between levels)
+    u64 *bar = nullptr;      // grid barrier words
+    int64_t hub_capacity = 0;
+    bool hub_zeroed = false;
     int *status = nullptr;      // [GP_BFS_ST_WORDS]
     u64 *counters = nullptr;    // [4] gathers issued, pushes issued, ...
+    u64 *trace = nullptr;       // [32 levels][warps][4] phase clocks, only with GP_BFS_TRACE=1
     int grid_blocks = 0;
+    int grid_cfg = -1;
+    int block_threads = 512;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;  // bracket the persistent kernel alone
 };
 
 // Fused decode + concat epilogue over `num_ranks` plane sets (1 = local result).
 struct GpDecodeParams {
-    const u64 *planes0;        // plane set of rank 0: [num_planes_alloc][batches][N][wb], plane 0 = reached
-    long long rank_stride;     // words between consecutive ranks' plane sets
-    long long plane_stride;    // words between consecutive planes
+    const u64 *planes0;        // result block of rank 0 (R[0..], gp_msbfs.cu), R[0] = reached mask
+    long long rank_stride;     // words between consecutive ranks' result blocks
+    long long plane_stride;    // words between consecutive arrays of a block
     int num_ranks;
-    int num_dist_planes;       // distance bit planes to read (bit_length(max_level)); <0: read from status
-    const int *status;         // device status words (max level) when num_dist_planes < 0
+    int num_arrays;            // leading arrays of R that are valid (1 + max hop, or 32 if deep); <0: from status
+    const int *status;         // device status words (max level) when num_arrays < 0
     long long n;
     long long anchors_per_rank;
     int wb;

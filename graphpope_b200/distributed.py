@@ -80,7 +80,7 @@ def sharded_geodesic_features(engine, edge_index: torch.Tensor, anchors: torch.T
     meta = engine.bfs.planes()  # syncs: needs max_level
     stride = meta["plane_stride_words"]
     num_planes = agree_num_planes(meta["num_planes"], group, device="cuda")
-    local = _wrap_device_words(meta["ptr"], (1 + 16) * stride)[: num_planes * stride].view(num_planes, stride)
+    local = _wrap_device_words(meta["ptr"], 32 * stride)[: num_planes * stride].view(num_planes, stride)
     if num_planes > meta["num_planes"]:
         local[meta["num_planes"]:].zero_()  # planes this shard never reached hold stale bits
     gathered = gather_planes(local, group)  # [G, P, words] int64

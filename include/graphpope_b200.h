@@ -130,6 +130,9 @@ int gp_msbfs_stats(gp_msbfs_t *bfs, gp_msbfs_stats_t *stats, gp_stream_t stream)
 /* syncs on the kernel's own events.  Device time of the last MS-BFS kernel launch alone (CUDA
  * events recorded on the launch stream right around the persistent kernel), in milliseconds. */
 int gp_msbfs_kernel_ms(gp_msbfs_t *bfs, float *ms);
+/* Diagnostics (needs GP_BFS_TRACE=1 in the environment at gp_msbfs_create): per-warp SM clocks at
+ * the start of each level sweep and after the hub / medium / short row phases.  syncs.        */
+int gp_msbfs_trace(gp_msbfs_t *bfs, uint64_t *h_out, int64_t cap_words, int32_t *levels, int32_t *warps);
 int gp_msbfs_free(gp_msbfs_t *bfs);
 
 /* Bit-sliced result planes of the last run, for the multi-GPU gather
