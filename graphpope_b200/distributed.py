@@ -38,9 +38,10 @@ def agree_num_planes(local_num_planes: int, group=None, device="cpu") -> int:
 def gather_planes(local_planes: torch.Tensor, group=None) -> torch.Tensor:
     """all-gather equal-shaped int64 plane blocks ``[P, words]`` into ``[G, P, words]``."""
     world = dist.get_world_size(group)
-    out = torch.empty((world,) + tuple(local_planes.shape), dtype=local_planes.dtype, device=local_planes.device)
-    dist.all_gather_into_tensor(out, local_planes.contiguous(), group=group)
-    return out
+    flat = local_planes.contiguous().view(-1)
+    out = torch.empty(world * flat.numel(), dtype=flat.dtype, device=flat.device)
+    dist.all_gather_into_tensor(out, flat, group=group)  # flat shapes: accepted by both NCCL and gloo
+    return out.view((world,) + tuple(local_planes.shape))
 
 
 def _wrap_device_words(ptr: int, nwords: int) -> torch.Tensor:

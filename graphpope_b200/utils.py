@@ -73,6 +73,7 @@ def _to_networkx(data):
 
 
 def _device_csr(data) -> _dev.DeviceCsr:
+    _lib.require_cuda()  # no CPU fallback: fail loudly before touching torch.cuda
     ei = _edge_index_of(data).cuda(non_blocking=True)
     csr = _dev.DeviceCsr(int(data.num_nodes), ei.size(1), symmetrize=False)
     return csr.build(ei)

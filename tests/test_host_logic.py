@@ -1,0 +1,113 @@
+"""Host-side logic of the reference-facing mirror (no GPU): signatures, errors, memo, samplers that stay on the host."""
+import inspect
+
+import numpy as np
+import pytest
+import torch
+
+from graphpope_b200 import utils
+
+
+class Data:
+    def __init__(self, edge_index, num_nodes, x=None):
+        self.edge_index = torch.as_tensor(edge_index)
+        self.num_nodes = num_nodes
+        self.x = x
+
+
+def test_signatures_match_the_reference():
+    # utils.py:18,64,83,92,116,129,137,149,182
+    want = {
+        "sample_anchor_nodes": ["data", "num_anchor_nodes", "sampling_method"],
+        "shortest_path_length": ["G", "anchor_nodes", "partition_length"],
+        "merge_dicts": ["dicts"],
+        "all_pairs_shortest_path_length_parallel": ["G", "anchor_nodes", "num_workers"],
+        "get_geodesic_distance_vector": ["data", "num_workers"],
+        "concat_into_features": ["embedding_matrix", "data"],
+        "attach_distance_embedding": ["data", "dataset", "num_anchor_nodes", "sampling_method",
+                                      "distance_function", "num_workers"],
+        "attach_node2vec": ["data", "dataset", "num_anchor_nodes", "sampling_method", "distance_function",
+                            "num_workers"],
+        "Graphpope": ["data", "dataset", "embedding_space", "sampling_method", "num_anchor_nodes",
+                      "distance_function", "num_workers"],
+    }
+    for name, params in want.items():
+        assert list(inspect.signature(getattr(utils, name)).parameters) == params, name
+    sig = inspect.signature(utils.Graphpope)
+    assert sig.parameters["distance_function"].default is None and sig.parameters["num_workers"].default == 4
+
+
+def test_stochastic_sampler_is_the_reference_stream(golden_small):
+    np.random.seed(42)
+    got = utils.sample_anchor_nodes(Data(np.zeros((2, 0), np.int64), 89250), 256, "stochastic")
+    assert isinstance(got, np.ndarray)
+    assert np.array_equal(got, golden_small["samplers/stochastic_89250_256"])
+
+
+def test_unknown_sampler_raises_like_the_reference():
+    with pytest.raises(UnboundLocalError):
+        utils.sample_anchor_nodes(Data(np.zeros((2, 0), np.int64), 5), 2, "kmeans")
+
+
+def test_host_centralities_use_networkx_top_k_rule():
+    import networkx as nx
+    ei = np.array([[0, 1, 1, 2, 2, 3, 3, 4, 1, 3], [1, 0, 2, 1, 3, 2, 4, 3, 3, 1]])
+    data = Data(ei, 6)
+    got = utils.sample_anchor_nodes(data, 3, "closeness_centrality")
+    G = nx.DiGraph(); G.add_nodes_from(range(6)); G.add_edges_from(zip(*ei.tolist()))
+    score = nx.closeness_centrality(G)
+    want = [k for k, _ in sorted(score.items(), key=lambda kv: kv[1])][-3:]
+    assert got == want
+    for method in ("betweenness_centrality", "clustering_coefficient"):
+        assert len(utils.sample_anchor_nodes(data, 2, method)) == 2
+
+
+def test_merge_dicts_and_concat():
+    assert utils.merge_dicts([{0: [1]}, {1: [2], 0: [3]}]) == {0: [3], 1: [2]}
+    assert list(utils.merge_dicts([{2: 0}, {1: 0}])) == [2, 1]
+    d = Data(np.zeros((2, 0), np.int64), 2, torch.tensor([[1.0, 2.0], [3.0, 4.0]]))
+    out = utils.concat_into_features(np.array([[0.5], [0.25]], dtype=np.float32), d)
+    assert out.tolist() == [[1.0, 2.0, 0.5], [3.0, 4.0, 0.25]]
+
+
+def test_graphpope_dispatch_memo_and_errors(monkeypatch):
+    utils.clear_cache()
+    calls = []
+
+    def fake(data, dataset, k, method, fn, num_workers):
+        calls.append((dataset, k, method, fn, num_workers))
+        return torch.full((2, 2), float(len(calls)))
+
+    monkeypatch.setattr(utils, "attach_distance_embedding", fake)
+    monkeypatch.setattr(utils, "attach_node2vec", fake)
+    with pytest.raises(KeyError):
+        utils.Graphpope(None, "flickr", "baseline", "stochastic", 2)
+    a = utils.Graphpope(None, "flickr", "geodesic", "stochastic", 2, None, num_workers=6)
+    b = utils.Graphpope(None, "pubmed", "node2vec", "kmeans", 99, "euclidean")
+    assert a is b and calls == [("flickr", 2, "stochastic", None, 6)]  # memo ignores arguments (utils.py:202-208)
+    utils.clear_cache()
+    c = utils.Graphpope(None, "pubmed", "node2vec", "kmeans", 99, "euclidean")
+    assert c is not a and calls[-1] == ("pubmed", 99, "kmeans", "euclidean", 4)
+    utils.clear_cache()
+
+
+def test_node2vec_unknown_distance_function_is_a_keyerror(tmp_path, monkeypatch):
+    monkeypatch.setenv("GRAPHPOPE_DATA_DIR", str(tmp_path))
+    torch.save(torch.zeros(4, 8), tmp_path / "toy_node2vec.pt")
+    with pytest.raises(KeyError):
+        utils.attach_node2vec(Data(np.zeros((2, 0), np.int64), 4, torch.zeros(4, 1)), "toy", 2, "stochastic", "None", 2)
+    with pytest.raises(FileNotFoundError):
+        utils.attach_node2vec(Data(np.zeros((2, 0), np.int64), 4, torch.zeros(4, 1)), "absent", 2, "stochastic",
+                              "euclidean", 2)
+    assert utils.node2vec_path("flickr").endswith("flickr_node2vec.pt")
+
+
+def test_device_entry_points_fail_loudly_without_a_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    d = Data(np.array([[0], [1]]), 2, torch.zeros(2, 1))
+    d.anchor_nodes = [0]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        utils.get_geodesic_distance_vector(d, 6)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        utils.sample_anchor_nodes(d, 1, "degree_centrality")
