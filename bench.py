@@ -232,14 +232,15 @@ def main():
         else:
             gpd.sharded_geodesic_features(engine, ei_d, a_d, x_d, out_d)
 
+    # clocks are sampled from before the warm-up to the end of the e2e loop (the device-timed region
+    # alone lasts a few milliseconds, shorter than one nvidia-smi sampling period)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         step()
     barrier()
     e_unique = engine.csr.info()["num_edges"]
-
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     bfs_ms = []
@@ -257,7 +258,6 @@ def main():
     launches = dev.launch_count() - launches0
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
     total_ms = float(sum(step_ms))
-    clock_info = clocks.stop() if rank == 0 else None
     stats = engine.bfs.stats()
 
     if world > 1:
@@ -297,6 +297,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = k_total * e_unique / e2e_s / 1e9
+    clock_info = clocks.stop() if rank == 0 else None
 
     if rank == 0:
         peaks = {}
@@ -310,6 +311,11 @@ def main():
         b_bfs = w_words * (4 * (n + 1) + 12 * e_unique + 16 * n) + 2 * n * K_PER_GPU
         bfs_avg_ms = float(np.mean(bfs_ms))
         achieved = b_bfs / (bfs_avg_ms * 1e-3) / 1e9
+        traffic = None  # dram bytes read+written per launch from the committed ncu --set full capture
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "msbfs_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -320,7 +326,7 @@ def main():
                        "step": "csr build + ms-bfs + fused normalise/concat epilogue" +
                                (" + plane all-gather" if world > 1 else "")},
             "roofline": {"bound": "hbm", "kernel": "msbfs_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
                          "algorithmic_bytes": b_bfs, "kernel_ms": bfs_avg_ms,
                          "kernel_share_of_step": bfs_avg_ms / ms_per_step},

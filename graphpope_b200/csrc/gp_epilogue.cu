@@ -40,11 +40,13 @@ __device__ __forceinline__ Valid valid_arrays(const GpDecodeParams &p)
 // Word that holds column j (global anchor index) of node u, and the bit inside it.
 __device__ __forceinline__ const u64 *lane_word(const GpDecodeParams &p, long long u, long long j, int &bit)
 {
-    const long long r = j / p.anchors_per_rank, jl = j - r * p.anchors_per_rank;
-    const long long b = jl / (64 * p.wb);
-    const int w = (int)((jl >> 6) % p.wb);
-    bit = (int)(jl & 63);
-    return p.planes0 + r * p.rank_stride + ((size_t)b * p.n + (size_t)u) * p.wb + w;
+    const u32 kr = (u32)p.anchors_per_rank, jj = (u32)j;  // anchor counts fit 32 bits
+    const u32 r = jj / kr, jl = jj - r * kr;
+    const u32 wsh = p.wb == 4 ? 2 : (p.wb == 2 ? 1 : 0);
+    const u32 b = jl >> (6 + wsh);
+    const u32 w = (jl >> 6) & ((1u << wsh) - 1u);
+    bit = (int)(jl & 63u);
+    return p.planes0 + (size_t)r * p.rank_stride + ((size_t)b * p.n + (size_t)u) * p.wb + w;
 }
 
 // Hop count of one reached lane.
@@ -142,6 +144,85 @@ __global__ void __launch_bounds__(256) decode_features_kernel(GpDecodeParams p, 
     }
 }
 
+// Fast path (anchors_per_rank % 8 == 0, 16-byte aligned rows): one warp per output row; a lane owns
+// 8 consecutive anchor columns = ONE BYTE of every mask array, so the 32 lanes read one 32-byte row
+// sector per array with a single coalesced byte load, bit-slice the hop index of their 8 columns and
+// store two float4.  x is streamed into columns [0, F) by the same warp.
+__global__ void __launch_bounds__(256) decode_features_bytes_kernel(GpDecodeParams p, int vec_x)
+{
+    __shared__ float s_inv[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_inv[i] = inv_hops((u32)i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const Valid va = valid_arrays(p);
+    const int row_bytes = p.wb * 8;                       // bytes of one node row in one batch
+    const int kr = (int)p.anchors_per_rank;
+    const int batches = (kr + 64 * p.wb - 1) / (64 * p.wb);
+    const size_t plane_bytes = (size_t)p.plane_stride * 8;
+    for (long long u = warp; u < p.n; u += nwarps) {
+        float *orow = p.out + (size_t)u * p.ld_out;
+        if (p.x != nullptr) {
+            const float *xrow = p.x + (size_t)u * p.ld_x;
+            if (vec_x) {
+                const float4 *x4 = reinterpret_cast<const float4 *>(xrow);
+                float4 *o4 = reinterpret_cast<float4 *>(orow);
+                const int q = (int)(p.num_features >> 2);
+                for (int i = lane; i < q; i += 32) o4[i] = __ldg(x4 + i);
+                for (int i = (q << 2) + lane; i < (int)p.num_features; i += 32) orow[i] = __ldg(xrow + i);
+            } else {
+                for (int i = lane; i < (int)p.num_features; i += 32) orow[i] = __ldg(xrow + i);
+            }
+        }
+        for (int r = 0; r < p.num_ranks; ++r) {
+            const unsigned char *blk = reinterpret_cast<const unsigned char *>(p.planes0 + (size_t)r * p.rank_stride);
+            for (int b = 0; b < batches; ++b) {
+                const int col0 = b * 64 * p.wb + lane * 8;  // first of this lane's 8 columns inside the rank
+                if (lane >= row_bytes || col0 >= kr) continue;
+                const unsigned char *rowp = blk + ((size_t)b * p.n + (size_t)u) * row_bytes + lane;
+                const u32 reach = rowp[0];
+                u32 m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+                if (reach) {
+#pragma unroll
+                    for (int l = 1; l <= GP_BFS_LEVEL_ARRAYS; ++l) {
+                        if (l <= va.levels) {
+                            const u32 bl = rowp[(size_t)l * plane_bytes];
+                            if (l & 1) m0 |= bl;
+                            if (l & 2) m1 |= bl;
+                            if (l & 4) m2 |= bl;
+                            if (l & 8) m3 |= bl;
+                        }
+                    }
+                }
+                float v[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const u32 d = ((m0 >> c) & 1u) | (((m1 >> c) & 1u) << 1) | (((m2 >> c) & 1u) << 2) |
+                                  (((m3 >> c) & 1u) << 3);
+                    v[c] = ((reach >> c) & 1u) ? s_inv[d] : 0.0f;
+                }
+                if (va.deep && reach) {
+                    const unsigned char *pl = rowp + (size_t)(1 + GP_BFS_LEVEL_ARRAYS) * plane_bytes;
+                    u32 e[GP_BFS_PLANES];
+#pragma unroll
+                    for (int q = 0; q < GP_BFS_PLANES; ++q) e[q] = pl[(size_t)q * plane_bytes];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        u32 dd = 0;
+#pragma unroll
+                        for (int q = 0; q < GP_BFS_PLANES; ++q) dd |= ((e[q] >> c) & 1u) << q;
+                        if (dd) v[c] = dd < 256 ? s_inv[dd] : inv_hops(dd);
+                    }
+                }
+                float4 *dst = reinterpret_cast<float4 *>(orow + p.col_offset + (size_t)r * kr + col0);
+                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) decode_u16_kernel(GpDecodeParams p, long long k_total, uint16_t *dist,
                                                          long long ld, long long col_offset)
 {
@@ -191,7 +272,10 @@ int gp_launch_decode_features(const GpDecodeParams &p, cudaStream_t stream)
                       (p.ld_out % 4 == 0);
     const int vec_f = aligned16(p.out) && (p.ld_out % 4 == 0) && (p.col_offset % 4 == 0) &&
                       (p.anchors_per_rank % 4 == 0 || p.num_ranks == 1);
-    GP_LAUNCH(decode_features_kernel, grid_for(p.n, 8), 256, 0, stream, p, k_total, vec_x, vec_f);
+    if (vec_f && p.anchors_per_rank % 8 == 0 && p.anchors_per_rank > 0)
+        GP_LAUNCH(decode_features_bytes_kernel, grid_for(p.n, 8), 256, 0, stream, p, vec_x);
+    else
+        GP_LAUNCH(decode_features_kernel, grid_for(p.n, 8), 256, 0, stream, p, k_total, vec_x, vec_f);
     GP_CUDA_CHECK(cudaGetLastError());
     return GP_OK;
 }

@@ -140,15 +140,26 @@ onesweep_kernel(const u64 *__restrict__ kin, u64 *__restrict__ kout, const u32 *
             st_relaxed_u32(st, ST_INC | count);
         } else {
             st_relaxed_u32(st, ST_AGG | count);
+            // decoupled look-back, 8 predecessors per round trip: all tiles of a small sort start
+            // together, so a one-at-a-time walk would serialise ~sqrt(2*tiles) L2 latencies
             int p = (int)tile - 1;
-            while (true) {
-                u32 v;
-                do {
-                    v = ld_relaxed_u32(status + (size_t)p * 256 + tid);
-                } while ((v >> ST_FLAG_SHIFT) == 0);
-                excl_prev += v & ST_VAL;
-                if ((v >> ST_FLAG_SHIFT) == 2u) break;
-                --p;
+            bool done = false;
+            while (!done) {
+                u32 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    v[i] = (p - i >= 0) ? ld_relaxed_u32(status + (size_t)(p - i) * 256 + tid) : ST_INC;
+                int used = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (done || used != i) continue;
+                    const u32 f = v[i] >> ST_FLAG_SHIFT;
+                    if (f == 0) continue;  // not published yet: poll again from here
+                    excl_prev += v[i] & ST_VAL;
+                    used = i + 1;
+                    if (f == 2u) done = true;
+                }
+                p -= used;
             }
             st_relaxed_u32(st, ST_INC | (excl_prev + count));
         }
@@ -216,27 +227,32 @@ unique_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const u32 *d_n,
     }
     u32 total;
     const u32 lexcl = block_excl_scan_256(cnt, s_warp, total);
-    if (tid == 0) {
+    if (tid < 32) {
+        // warp-wide look-back over 32 predecessors per round trip
+        const u32 lane = tid;
         u32 *st = status + 1 + tile;
         u32 excl = 0;
-        if (tile == 0) {
-            st_relaxed_u32(st, ST_INC | total);
-        } else {
-            st_relaxed_u32(st, ST_AGG | total);
-            int p = (int)tile - 1;
-            while (true) {
-                u32 v;
-                do {
-                    v = ld_relaxed_u32(status + 1 + p);
-                } while ((v >> ST_FLAG_SHIFT) == 0);
-                excl += v & ST_VAL;
-                if ((v >> ST_FLAG_SHIFT) == 2u) break;
-                --p;
-            }
-            st_relaxed_u32(st, ST_INC | (excl + total));
+        bool done = tile == 0;
+        if (lane == 0) st_relaxed_u32(st, (tile == 0 ? ST_INC : ST_AGG) | total);
+        int p = (int)tile - 1;
+        while (!done) {
+            const int idx = p - (int)lane;
+            const u32 v = idx >= 0 ? ld_relaxed_u32(status + 1 + idx) : ST_INC;
+            const u32 f = v >> ST_FLAG_SHIFT;
+            const u32 empty = __ballot_sync(FULL_MASK, f == 0);
+            const u32 inc = __ballot_sync(FULL_MASK, f == 2u);
+            const int first_empty = empty ? __ffs(empty) - 1 : 32;
+            const int first_inc = inc ? __ffs(inc) - 1 : 32;
+            const int take = first_inc < first_empty ? first_inc + 1 : first_empty;  // usable prefix of the window
+            excl += __reduce_add_sync(FULL_MASK, (int)lane < take ? (v & ST_VAL) : 0u);
+            p -= take;
+            if (first_inc < first_empty) done = true;
         }
-        s_prefix = excl;
-        if (tile == ntiles - 1) *d_m = excl + total;
+        if (lane == 0) {
+            if (tile != 0) st_relaxed_u32(st, ST_INC | (excl + total));
+            s_prefix = excl;
+            if (tile == ntiles - 1) *d_m = excl + total;
+        }
     }
     __syncthreads();
     u32 pos = s_prefix + lexcl;
