@@ -1,0 +1,80 @@
+"""Device degree / PageRank samplers and stable top-k against anchor lists produced by the reference."""
+import numpy as np
+import pytest
+import torch
+
+from graphpope_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from graphpope_b200 import device
+    return device
+
+
+class Data:
+    def __init__(self, ei, n):
+        self.edge_index, self.num_nodes = torch.as_tensor(ei), n
+
+
+def test_degree_scores_and_anchor_lists(dev, golden_small):
+    from graphpope_b200 import utils
+    ei, n = golden_small["samplers/edge_index"], int(golden_small["samplers/n"])
+    csr = dev.DeviceCsr(n, ei.shape[1]).build(torch.as_tensor(ei).cuda())
+    assert np.array_equal(csr.degree().cpu().numpy(), golden_small["samplers/degree"])
+    for k in (1, 16, 64, 256):
+        assert utils.sample_anchor_nodes(Data(ei, n), k, "degree_centrality") == \
+            golden_small[f"samplers/degree_centrality/{k}"].tolist()
+
+
+def test_pagerank_scores_bit_equal_and_anchor_lists(dev, golden_small):
+    from graphpope_b200 import utils
+    ei, n = golden_small["samplers/edge_index"], int(golden_small["samplers/n"])
+    csr = dev.DeviceCsr(n, ei.shape[1]).build(torch.as_tensor(ei).cuda())
+    x, iters = csr.pagerank()
+    want = golden_small["samplers/pagerank_scores"]
+    got = x.cpu().numpy()
+    assert 1 <= iters <= 100
+    assert np.abs(got - want).sum() < 1e-12
+    assert np.array_equal(got, want)  # same operation order as scipy -> identical float64
+    for k in (1, 16, 64, 256):
+        assert utils.sample_anchor_nodes(Data(ei, n), k, "pagerank") == golden_small[f"samplers/pagerank/{k}"].tolist()
+
+
+def test_pagerank_matches_oracle_on_directed_graph_with_dangling_nodes(dev):
+    from oracle import samplers as s
+    n = 3000
+    ei = synth.random_digraph(n, 7000, seed=11)  # asymmetric, many nodes without out-edges
+    csr = dev.DeviceCsr(n, ei.shape[1]).build(torch.as_tensor(ei).cuda())
+    x, iters = csr.pagerank()
+    want, it_want = s.pagerank_scores(ei, n)
+    assert iters == it_want
+    assert np.array_equal(x.cpu().numpy(), want)
+    assert dev.topk_stable(x, 50).cpu().tolist() == s.stable_top_k(want, 50)
+
+
+def test_topk_stable_quirks(dev):
+    score = torch.tensor([3, 1, 3, 2, 3], dtype=torch.int32).cuda()
+    assert dev.topk_stable(score, 2).cpu().tolist() == [2, 4]           # ties -> larger ids, ascending score
+    assert dev.topk_stable(score, 0).cpu().tolist() == [1, 3, 0, 2, 4]  # list[-0:] is everything
+    assert dev.topk_stable(score, 9).cpu().tolist() == [1, 3, 0, 2, 4]
+    f = torch.tensor([0.5, -1.0, 0.5, 0.0, 2.0], dtype=torch.float64).cuda()
+    assert dev.topk_stable(f, 3).cpu().tolist() == [0, 2, 4]
+    big = torch.randint(0, 50, (100000,), dtype=torch.int32, device="cuda")
+    want = np.argsort(big.cpu().numpy(), kind="stable")[-1000:]
+    assert np.array_equal(dev.topk_stable(big, 1000).cpu().numpy(), want)
+
+
+def test_flickr_shape_degree_and_pagerank_1024_anchors(dev):
+    """BASELINE.json configs[3] samplers on the Flickr-shape graph against the CPU oracle."""
+    from oracle import samplers as s
+    shape = synth.FLICKR_SHAPE
+    ei = synth.make_graph(shape)
+    csr = dev.DeviceCsr(shape.num_nodes, ei.shape[1]).build(torch.as_tensor(ei).cuda())
+    deg = csr.degree()
+    assert np.array_equal(deg.cpu().numpy(), s.degree_scores(ei, shape.num_nodes))
+    assert dev.topk_stable(deg, 1024).cpu().tolist() == s.degree_centrality_anchors(ei, shape.num_nodes, 1024)
+    x, _ = csr.pagerank()
+    assert abs(float(x.sum()) - 1.0) < 1e-9
