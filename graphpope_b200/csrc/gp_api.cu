@@ -166,6 +166,17 @@ void copy_rows_parallel(const float *src, int64_t ld_src, float *dst, int64_t ld
 
 }  // namespace
 
+extern "C" int gp_host_concat(const float *h_x, int64_t num_features, const float *h_block, int64_t block_cols,
+                              int64_t num_nodes, float *h_out, int64_t ld_out)
+{
+    GP_REQUIRE(num_nodes >= 0 && num_features >= 0 && block_cols >= 0 && ld_out >= num_features + block_cols,
+               GP_ERR_INVALID, "gp_host_concat: inconsistent sizes");
+    GP_REQUIRE(h_out != nullptr || num_nodes == 0, GP_ERR_INVALID, "gp_host_concat: out is NULL");
+    if (h_x != nullptr) copy_rows_parallel(h_x, num_features, h_out, ld_out, num_nodes, num_features);
+    if (h_block != nullptr) copy_rows_parallel(h_block, block_cols, h_out + num_features, ld_out, num_nodes, block_cols);
+    return GP_OK;
+}
+
 extern "C" int gp_geodesic_embed_host(const int64_t *h_edge_index, int64_t num_edges, int64_t num_nodes,
                                       uint32_t csr_flags, const int64_t *h_anchors, int64_t num_anchors,
                                       const float *h_x, int64_t num_features, float *h_out, int64_t ld_out,

@@ -193,6 +193,15 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
     constexpr int WARPS = NT / 32;
     constexpr u32 LEADER_MASK = (TPE == 2) ? 0x3u : 0x1u;
 
+    constexpr int PAIRS_CTA = NT / TPE;
+    // Work cache: a warp visits the same pair slots every level, so the descriptors and column
+    // indices of its first GP_BFS_CACHE_ITERS warp-iterations are loaded ONCE into shared memory
+    // (48 B per slot); a level then costs a single dependent round trip (gathers + seen together).
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    int4 *s_desc = reinterpret_cast<int4 *>(s_dyn);                                        // [ITERS][PAIRS_CTA]
+    int *s_col = reinterpret_cast<int *>(s_desc + GP_BFS_CACHE_ITERS * PAIRS_CTA);        // [ITERS][8][PAIRS_CTA]
+    unsigned char *s_done = reinterpret_cast<unsigned char *>(s_col + GP_BFS_CACHE_ITERS * GP_SLOT_EDGES * PAIRS_CTA);
+                                                                                           // [DONE_B][ITERS][PAIRS_CTA]
     __shared__ u32 s_live32[GP_BFS_MAX_LANE_WORDS * 2];
     __shared__ int s_ent_base[GP_NUM_CLASSES + 1];
     __shared__ int s_slot_base[GP_NUM_CLASSES + 1];
@@ -231,8 +240,33 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
         atomicOr(p.seeds + off, bit);
         atomicOr(p.live + 1 * GP_BFS_MAX_LANE_WORDS + b * WB + w, bit);
     }
-    grid_barrier_any(p.bar + 0, bar_target[0], bar_prev_any[0], gridDim.x, false, &s_bcast, &s_any);
+    __syncthreads();
     const int total_slots = s_slot_base[GP_NUM_CLASSES];
+    const int pair_cta = tid / TPE;
+    for (int it = 0; it < GP_BFS_CACHE_ITERS; ++it) {
+        const int t0 = (gwarp + it * total_warps) * PPW;
+        if (t0 >= total_slots) break;
+        int cls = 0;
+        while (t0 >= s_slot_base[cls + 1]) ++cls;
+        const int gsh = cls <= 1 ? 4 : 5 - cls;
+        const int rel = t0 - s_slot_base[cls] + pairlane;
+        const int ent = s_ent_base[cls] + (rel >> gsh);
+        const int sub = rel & ((1 << gsh) - 1);
+        const bool active = ent < s_ent_base[cls + 1];
+        const int4 d = active ? __ldg(p.desc + ent) : make_int4(0, 0, 0, -1);
+        if (half == 0) {
+            s_desc[it * PAIRS_CTA + pair_cta] = make_int4(d.x, d.z, d.w, sub | (gsh << 8) | ((int)active << 16));
+            const int cnt = d.z & 0xFF;
+#pragma unroll
+            for (int i = 0; i < GP_SLOT_EDGES; ++i) {
+                const int idx = sub + (i << gsh);
+                // padding edges point back at the row itself (frontier[u] is a subset of seen[u])
+                s_col[(it * GP_SLOT_EDGES + i) * PAIRS_CTA + pair_cta] = idx < cnt ? __ldg(p.col + d.y + idx) : d.x;
+            }
+            for (int b = 0; b < GP_BFS_DONE_BATCHES; ++b) s_done[(b * GP_BFS_CACHE_ITERS + it) * PAIRS_CTA + pair_cta] = 0;
+        }
+    }
+    grid_barrier_any(p.bar + 0, bar_target[0], bar_prev_any[0], gridDim.x, false, &s_bcast, &s_any);
 
     int level = 1, max_level = 0;
     while (true) {
@@ -274,8 +308,96 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
             }
             const u64 *cur_b = c.cur + (size_t)b * n * WB + woff;
 
+            // ---- cached warp-iterations: descriptors / columns from shared memory, one round trip
+            int it = 0;
+            const int cached_iters = b < GP_BFS_DONE_BATCHES ? GP_BFS_CACHE_ITERS : 0;  // untracked batches stream
+            for (; it < cached_iters; ++it) {
+                const int tc = (gwarp + it * total_warps) * PPW;
+                if (tc >= total_slots) break;
+                const int4 cd = s_desc[it * PAIRS_CTA + pair_cta];
+                const int sub = cd.w & 0xFF, gsh = (cd.w >> 8) & 0xFF;
+                const bool active = (cd.w >> 16) & 1;
+                const int nch = (cd.y >> 8) & 0x3FFFFF;
+                const bool first_chunk = (cd.y >> 30) & 1;
+                const bool track = b < GP_BFS_DONE_BATCHES;
+                unsigned char *dflag = s_done + (b * GP_BFS_CACHE_ITERS + it) * PAIRS_CTA;
+                // a row is "done" once every still-live lane has reached it: it never needs gathering again
+                const bool done = track && dflag[pair_cta - sub] != 0;
+                const bool work = active && !done;
+                const size_t off = ((size_t)b * n + (size_t)cd.x) * WB + woff;
+                u64 seenv[VW], acc[VW];
+#pragma unroll
+                for (int i = 0; i < VW; ++i) {
+                    seenv[i] = ~0ull;
+                    acc[i] = 0;
+                }
+                if (work) {
+                    int v[GP_SLOT_EDGES];
+#pragma unroll
+                    for (int i = 0; i < GP_SLOT_EDGES; ++i) v[i] = s_col[(it * GP_SLOT_EDGES + i) * PAIRS_CTA + pair_cta];
+                    u64 t[GP_SLOT_EDGES][VW];
+#pragma unroll
+                    for (int i = 0; i < GP_SLOT_EDGES; ++i) vload<VW>(cur_b + (size_t)(u32)v[i] * WB, t[i]);
+                    if (sub == 0) vload<VW>(p.result + off, seenv);  // only the finalising lanes need it
+#pragma unroll
+                    for (int i = 0; i < GP_SLOT_EDGES; ++i)
+#pragma unroll
+                        for (int q = 0; q < VW; ++q) acc[q] |= t[i][q];
+                    gathers += (u64)VW * GP_SLOT_EDGES;
+                }
+                for (int m = TPE; m < (TPE << gsh); m <<= 1)
+#pragma unroll
+                    for (int q = 0; q < VW; ++q) acc[q] |= shfl_xor_u64(acc[q], m);
+
+                const bool leader = active && sub == 0;
+                const u32 leader_mask = __ballot_sync(FULL_MASK, leader);
+                if (leader) {
+                    bool need = false;
+#pragma unroll
+                    for (int i = 0; i < VW; ++i) need |= work && (~seenv[i] & lv[i]) != 0;
+                    bool need_row = need;
+                    if constexpr (TPE == 2) need_row |= __shfl_xor_sync(leader_mask, (int)need, 1) != 0;
+                    if (!need_row) {
+                        // nothing left to reach here (monotone: seen grows, live shrinks): remember it
+                        if (track && half == 0) dflag[pair_cta] = 1;
+                        if (nch == 0 || first_chunk) {
+#pragma unroll
+                            for (int i = 0; i < VW; ++i) acc[i] = 0;
+                            finalize_row<VW>(c, off, acc, seenv, live_acc);
+                        }
+                    } else if (nch == 0) {
+                        finalize_row<VW>(c, off, acc, seenv, live_acc);
+                    } else {
+                        const size_t hidx = (size_t)b * p.hub_capacity + (size_t)cd.z;
+                        u64 *accp = p.hub_acc + hidx * WB + woff;
+                        u64 dep = 0;
+#pragma unroll
+                        for (int q = 0; q < VW; ++q)
+                            if (acc[q]) dep |= atomicOr(accp + q, acc[q]);
+                        u32 old = 0;
+                        if constexpr (TPE == 2) {
+                            dep |= __shfl_xor_sync(leader_mask, (u32)dep | (u32)(dep >> 32), 1);
+                            asm volatile("" ::"l"(dep) : "memory");  // the ORs have returned from L2 before we count
+                            if (half == 0) old = atomicAdd(p.hub_cnt + hidx, 1u);
+                            old = __shfl_sync(leader_mask, old, lane & ~1);
+                        } else {
+                            asm volatile("" ::"l"(dep) : "memory");
+                            old = atomicAdd(p.hub_cnt + hidx, 1u);
+                        }
+                        if (old == (u32)nch - 1u) {
+                            u64 comb[VW];
+#pragma unroll
+                            for (int q = 0; q < VW; ++q) comb[q] = atomicExch(accp + q, 0ull);
+                            if (half == 0) p.hub_cnt[hidx] = 0;
+                            finalize_row<VW>(c, off, comb, seenv, live_acc);
+                        }
+                    }
+                }
+            }
+
+            // ---- remaining warp-iterations (large graphs): streamed from global memory.
             // software pipeline: the descriptor of the next warp-iteration is fetched one iteration ahead
-            int t0 = gwarp * PPW;
+            int t0 = (gwarp + it * total_warps) * PPW;
             int cls = 0;
             int4 d_next = make_int4(0, 0, 0, -1);
             bool act_next = false;
@@ -421,12 +543,23 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
     }
 }
 
+template <int WB, int NT>
+constexpr size_t bfs_cache_bytes()
+{
+    constexpr int pairs = NT / ((WB == 4) ? 2 : 1);
+    return (size_t)GP_BFS_CACHE_ITERS * pairs * (sizeof(int4) + GP_SLOT_EDGES * sizeof(int)) +
+           (size_t)GP_BFS_DONE_BATCHES * GP_BFS_CACHE_ITERS * pairs;
+}
+
 template <int WB, int NT, int MINB>
 int launch_bfs_cfg(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int cfg_id)
 {
     if (h->grid_blocks == 0 || h->grid_cfg != cfg_id * 8 + WB) {
         int occ = 0;
-        GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, msbfs_kernel<WB, NT, MINB>, NT, 0));
+        GP_CUDA_CHECK(cudaFuncSetAttribute(msbfs_kernel<WB, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)bfs_cache_bytes<WB, NT>()));
+        GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, msbfs_kernel<WB, NT, MINB>, NT,
+                                                                    bfs_cache_bytes<WB, NT>()));
         GP_REQUIRE(occ >= 1, GP_ERR_CUDA, "msbfs kernel does not fit on an SM");
         if (occ > MINB) occ = MINB;
         h->grid_blocks = occ * gp_sm_count();
@@ -438,7 +571,7 @@ int launch_bfs_cfg(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int cfg
     gp_count_launch();
     GP_CUDA_CHECK(cudaEventRecord(h->ev_start, stream));
     GP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)msbfs_kernel<WB, NT, MINB>, dim3(h->grid_blocks),
-                                              dim3(NT), args, 0, stream));
+                                              dim3(NT), args, bfs_cache_bytes<WB, NT>(), stream));
     GP_CUDA_CHECK(cudaEventRecord(h->ev_stop, stream));
     return GP_OK;
 }

@@ -91,3 +91,31 @@ def sharded_geodesic_features(engine, edge_index: torch.Tensor, anchors: torch.T
                                  x.stride(0) if x is not None and n > 1 else f, _ptr(out),
                                  out.stride(0) if n > 1 else f + k, f, _stream()))
     return out
+
+
+def sharded_geodesic_embed_host(engine, edge_index: torch.Tensor, anchors, x: torch.Tensor | None,
+                                out: torch.Tensor, staging: dict, group=None) -> torch.Tensor:
+    """Host-buffer form of the sharded path (what a DataModule calls): HOST ``edge_index`` / ``x`` in,
+    HOST float32 ``[N, F + K]`` out.  ``staging`` caches the device / pinned scratch between calls."""
+    from . import _lib
+    from ._lib import check
+    from .device import _ptr
+
+    n = engine.csr.num_nodes
+    a = torch.as_tensor(anchors)
+    k = a.numel()
+    f = 0 if x is None else x.size(1)
+    if staging.get("shape") != (n, k, edge_index.size(1)):
+        staging.clear()
+        staging["shape"] = (n, k, edge_index.size(1))
+        staging["ei"] = torch.empty_like(edge_index, device="cuda")
+        staging["anchors"] = torch.empty(k, dtype=torch.int64, device="cuda")
+        staging["block_d"] = torch.empty((n, k), dtype=torch.float32, device="cuda")
+        staging["block_h"] = torch.empty((n, k), dtype=torch.float32).pin_memory()
+    staging["ei"].copy_(edge_index, non_blocking=True)
+    staging["anchors"].copy_(a, non_blocking=True)
+    sharded_geodesic_features(engine, staging["ei"], staging["anchors"], None, staging["block_d"], group)
+    staging["block_h"].copy_(staging["block_d"], non_blocking=True)  # one contiguous DMA
+    torch.cuda.current_stream().synchronize()
+    check(_lib.load().gp_host_concat(_ptr(x), f, _ptr(staging["block_h"]), k, n, _ptr(out), out.stride(0)))
+    return out

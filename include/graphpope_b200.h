@@ -168,6 +168,11 @@ int gp_geodesic_embed_host(const int64_t *h_edge_index, int64_t num_edges, int64
                            float *h_out, int64_t ld_out, int64_t col_offset,
                            uint16_t *h_hops, gp_msbfs_stats_t *stats);
 
+/* Host side of concat_into_features (utils.py:129-135) for results that arrive as a separate
+ * [N, block_cols] block: out[:, 0:F] = x, out[:, F:F+block_cols] = block, threaded row copies.      */
+int gp_host_concat(const float *h_x, int64_t num_features, const float *h_block, int64_t block_cols,
+                   int64_t num_nodes, float *h_out, int64_t ld_out);
+
 /* ------------------------------------------------------------------ samplers
  * degree_centrality (utils.py:38-42): in+out degree over de-duplicated edges
  * (a self-loop counts 2).  async.  d_degree int32[N].                           */
