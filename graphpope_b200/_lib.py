@@ -70,6 +70,8 @@ SIGNATURES = {
     "gp_msbfs_features": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p]),
     "gp_msbfs_stats": (c_int, [c_void_p, POINTER(MsbfsStats), c_void_p]),
     "gp_msbfs_free": (c_int, [c_void_p]),
+    "gp_geodesic_run": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                                c_void_p, c_int64, c_int64, c_void_p]),
     "gp_msbfs_planes": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int32),
                                 POINTER(c_int32), POINTER(c_int32), c_void_p]),
     "gp_decode_gathered": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int64, c_int32, c_int32, c_int32,

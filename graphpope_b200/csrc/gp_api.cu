@@ -9,13 +9,23 @@
 #include <thread>
 #include <vector>
 
+bool gp_is_capturing();
+static bool g_capturing_flag_for_count() { return gp_is_capturing(); }
+void gp_count_launches(int n);
+
 namespace {
 thread_local char g_err[512] = "";
 int g_sm_count = 0;
 std::atomic<long long> g_launches{0};
 }  // namespace
 
-void gp_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static int g_capture_count = 0;  // kernels recorded into the graph being captured
+void gp_count_launch()
+{
+    if (g_capturing_flag_for_count()) ++g_capture_count;
+    else g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+void gp_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 extern "C" int64_t gp_launch_count(void) { return (int64_t)g_launches.load(); }
 
@@ -165,6 +175,126 @@ void copy_rows_parallel(const float *src, int64_t ld_src, float *dst, int64_t ld
 }
 
 }  // namespace
+
+// ------------------------------------------------------------------------------------------
+// Whole device pipeline as one call, replayed from a CUDA graph: csr build -> ms-bfs -> epilogue is
+// ~25 small launches whose gaps rival their run time at Flickr size.  The first call with a given
+// argument tuple runs eagerly, the second is stream-captured (on a private stream: the legacy
+// default stream cannot capture), later calls are a single cudaGraphLaunch.
+namespace {
+
+struct PipeKey {
+    const void *csr, *bfs, *ei, *anchors, *x, *out;
+    int64_t e, k, f, ldx, ldo, coff;
+    bool operator==(const PipeKey &o) const { return memcmp(this, &o, sizeof(PipeKey)) == 0; }
+};
+
+struct PipeEntry {
+    PipeKey key;
+    cudaGraphExec_t exec = nullptr;
+    int seen = 0;
+    int kernels = 0;  // kernel nodes in the captured graph
+    uint64_t stamp = 0;
+};
+
+std::vector<PipeEntry> g_pipes;
+std::mutex g_pipe_mutex;
+cudaStream_t g_capture_stream = nullptr;
+uint64_t g_pipe_clock = 0;
+bool g_capturing = false;
+
+int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t e, const int64_t *d_anchors,
+                       int64_t k, const float *d_x, int64_t f, int64_t ldx, float *d_out, int64_t ldo,
+                       int64_t coff, cudaStream_t s)
+{
+    GP_TRY(gp_csr_build(csr, d_ei, e, s));
+    GP_TRY(gp_msbfs_run(bfs, d_anchors, k, s));
+    GP_TRY(gp_msbfs_features(bfs, d_x, f, ldx, d_out, ldo, coff, s));
+    return GP_OK;
+}
+
+}  // namespace
+
+bool gp_is_capturing() { return g_capturing; }
+
+void gp_drop_graphs(const void *handle)
+{
+    std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    for (size_t i = 0; i < g_pipes.size();) {
+        if (g_pipes[i].key.csr == handle || g_pipes[i].key.bfs == handle) {
+            if (g_pipes[i].exec) cudaGraphExecDestroy(g_pipes[i].exec);
+            g_pipes.erase(g_pipes.begin() + i);
+        } else {
+            ++i;
+        }
+    }
+}
+
+extern "C" int gp_geodesic_run(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_edge_index, int64_t num_edges,
+                               const int64_t *d_anchors, int64_t num_anchors, const float *d_x,
+                               int64_t num_features, int64_t ld_x, float *d_out, int64_t ld_out,
+                               int64_t col_offset, gp_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GP_REQUIRE(csr != nullptr && bfs != nullptr, GP_ERR_INVALID, "gp_geodesic_run: NULL handle");
+    static int use_graph = -1;
+    if (use_graph < 0) {
+        const char *e = getenv("GP_USE_GRAPH");
+        use_graph = e ? atoi(e) : 1;
+    }
+    if (!use_graph || csr->num_nodes == 0 || num_anchors == 0)
+        return run_pipeline_eager(csr, bfs, d_edge_index, num_edges, d_anchors, num_anchors, d_x, num_features, ld_x,
+                                  d_out, ld_out, col_offset, stream);
+    std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    PipeKey key;
+    memset(&key, 0, sizeof(key));
+    key.csr = csr; key.bfs = bfs; key.ei = d_edge_index; key.anchors = d_anchors; key.x = d_x; key.out = d_out;
+    key.e = num_edges; key.k = num_anchors; key.f = num_features; key.ldx = ld_x; key.ldo = ld_out; key.coff = col_offset;
+    PipeEntry *ent = nullptr;
+    for (auto &p : g_pipes)
+        if (p.key == key) ent = &p;
+    if (ent == nullptr) {
+        if (g_pipes.size() >= 8) {  // evict the least recently used graph
+            size_t lru = 0;
+            for (size_t i = 1; i < g_pipes.size(); ++i)
+                if (g_pipes[i].stamp < g_pipes[lru].stamp) lru = i;
+            if (g_pipes[lru].exec) cudaGraphExecDestroy(g_pipes[lru].exec);
+            g_pipes.erase(g_pipes.begin() + lru);
+        }
+        g_pipes.emplace_back();
+        ent = &g_pipes.back();
+        ent->key = key;
+    }
+    ent->stamp = ++g_pipe_clock;
+    ent->seen += 1;
+    if (ent->exec == nullptr && ent->seen == 2) {
+        if (g_capture_stream == nullptr)
+            GP_CUDA_CHECK(cudaStreamCreateWithFlags(&g_capture_stream, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(g_capture_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+            g_capturing = true;
+            g_capture_count = 0;
+            const int rc = run_pipeline_eager(csr, bfs, d_edge_index, num_edges, d_anchors, num_anchors, d_x,
+                                              num_features, ld_x, d_out, ld_out, col_offset, g_capture_stream);
+            g_capturing = false;
+            ent->kernels = g_capture_count;
+            const cudaError_t ce = cudaStreamEndCapture(g_capture_stream, &graph);
+            if (rc == GP_OK && ce == cudaSuccess && graph != nullptr) {
+                if (cudaGraphInstantiate(&ent->exec, graph, 0) != cudaSuccess) ent->exec = nullptr;
+            }
+            if (graph) cudaGraphDestroy(graph);
+        }
+        cudaGetLastError();  // a failed capture must not poison later calls; fall back to eager launches
+        if (ent->exec == nullptr) ent->seen = 1 << 20;  // do not retry
+    }
+    if (ent->exec != nullptr) {
+        gp_count_launches(ent->kernels);  // kernels inside the graph
+        GP_CUDA_CHECK(cudaGraphLaunch(ent->exec, stream));
+        return GP_OK;
+    }
+    return run_pipeline_eager(csr, bfs, d_edge_index, num_edges, d_anchors, num_anchors, d_x, num_features, ld_x,
+                              d_out, ld_out, col_offset, stream);
+}
 
 extern "C" int gp_host_concat(const float *h_x, int64_t num_features, const float *h_block, int64_t block_cols,
                               int64_t num_nodes, float *h_out, int64_t ld_out)

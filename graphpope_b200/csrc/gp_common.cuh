@@ -49,6 +49,8 @@ int gp_sm_count();  // cached multiProcessorCount of the current device
 // Every kernel launch of the library goes through GP_LAUNCH so callers (bench.py) can report how
 // many of OUR kernels ran inside a timed region (gp_launch_count in the ABI).
 void gp_count_launch();
+bool gp_is_capturing();            // true while gp_geodesic_run is stream-capturing the pipeline
+void gp_drop_graphs(const void *handle);  // forget cached graphs that reference a handle being freed
 #define GP_LAUNCH(kernel, grid, block, smem, stream, ...)                         \
     do {                                                                          \
         gp_count_launch();                                                        \

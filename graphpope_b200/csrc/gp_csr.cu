@@ -257,6 +257,7 @@ extern "C" int gp_csr_create(int64_t num_nodes, int64_t edge_capacity, uint32_t 
 extern "C" int gp_csr_free(gp_csr_t *c)
 {
     if (!c) return GP_OK;
+    gp_drop_graphs(c);
     cudaFree(c->keys);
     cudaFree(c->ukeys);
     cudaFree(c->rowptr_out);

@@ -569,10 +569,12 @@ int launch_bfs_cfg(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int cfg
     BfsParams pp = p;
     void *args[] = {&pp};
     gp_count_launch();
-    GP_CUDA_CHECK(cudaEventRecord(h->ev_start, stream));
+    // inside a graph capture the timing events become event-record nodes (re-recorded on every replay)
+    const unsigned ev_flags = gp_is_capturing() ? cudaEventRecordExternal : cudaEventRecordDefault;
+    GP_CUDA_CHECK(cudaEventRecordWithFlags(h->ev_start, stream, ev_flags));
     GP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)msbfs_kernel<WB, NT, MINB>, dim3(h->grid_blocks),
                                               dim3(NT), args, bfs_cache_bytes<WB, NT>(), stream));
-    GP_CUDA_CHECK(cudaEventRecord(h->ev_stop, stream));
+    GP_CUDA_CHECK(cudaEventRecordWithFlags(h->ev_stop, stream, ev_flags));
     return GP_OK;
 }
 
@@ -658,6 +660,7 @@ extern "C" int gp_msbfs_create(const gp_csr_t *csr, int64_t max_anchors, gp_msbf
 extern "C" int gp_msbfs_free(gp_msbfs_t *h)
 {
     if (!h) return GP_OK;
+    gp_drop_graphs(h);
     cudaFree(h->seen);
     cudaFree(h->fr_a);
     cudaFree(h->live);

@@ -208,10 +208,33 @@ class GeodesicEngine:
 
     def run(self, edge_index: torch.Tensor, anchors: torch.Tensor, x: torch.Tensor | None = None,
             out: torch.Tensor | None = None) -> torch.Tensor:
-        """edge_index -> [N, F + K] features, all enqueued on the current stream (no host sync)."""
-        self.csr.build(edge_index)
-        self.bfs.run(anchors)
-        return self.bfs.features(x, out)
+        """edge_index -> [N, F + K] features, all enqueued on the current stream (no host sync).
+
+        One C-ABI call (gp_geodesic_run); from the second call with the same tensors on it replays
+        a captured CUDA graph.
+        """
+        n = self.csr.num_nodes
+        if edge_index.dim() != 2 or edge_index.size(0) != 2 or not edge_index.is_cuda or edge_index.dtype != torch.int64:
+            raise TypeError("edge_index must be a cuda int64 tensor of shape [2, E]")
+        if not anchors.is_cuda or anchors.dtype != torch.int64:
+            raise TypeError("anchors must be a cuda int64 tensor")
+        edge_index, anchors = edge_index.contiguous(), anchors.contiguous()
+        k = anchors.numel()
+        f = 0 if x is None else x.size(1)
+        if x is not None:
+            if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or x.size(0) != n:
+                raise TypeError("x must be a cuda float32 tensor of shape [N, F]")
+            if x.stride(1) != 1:
+                x = x.contiguous()
+        if out is None:
+            out = torch.empty((n, f + k), dtype=torch.float32, device="cuda")
+        self.csr._edges, self.bfs._anchors, self._x = edge_index, anchors, x  # keep alive for the stream
+        self.bfs.num_anchors = k
+        check(self.csr._lib.gp_geodesic_run(self.csr._h, self.bfs._h, _ptr(edge_index), edge_index.size(1),
+                                            _ptr(anchors), k, _ptr(x), f,
+                                            x.stride(0) if x is not None and n > 1 else f, _ptr(out),
+                                            out.stride(0) if n > 1 else f + k, f, _stream()))
+        return out
 
 
 def normalize_into(dist_u16: torch.Tensor, out: torch.Tensor, col_offset: int = 0) -> torch.Tensor:

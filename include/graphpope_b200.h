@@ -135,6 +135,12 @@ int gp_msbfs_kernel_ms(gp_msbfs_t *bfs, float *ms);
 int gp_msbfs_trace(gp_msbfs_t *bfs, uint64_t *h_out, int64_t cap_words, int32_t *levels, int32_t *warps);
 int gp_msbfs_free(gp_msbfs_t *bfs);
 
+/* async.  gp_csr_build + gp_msbfs_run + gp_msbfs_features as ONE call.  Repeated calls with the same
+ * arguments replay a captured CUDA graph (one launch instead of ~25); GP_USE_GRAPH=0 disables it.  */
+int gp_geodesic_run(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_edge_index, int64_t num_edges,
+                    const int64_t *d_anchors, int64_t num_anchors, const float *d_x, int64_t num_features,
+                    int64_t ld_x, float *d_out, int64_t ld_out, int64_t col_offset, gp_stream_t stream);
+
 /* Bit-sliced result planes of the last run, for the multi-GPU gather
  * (anchor-sharded ranks exchange these instead of uint16/fp32 columns):
  * plane 0 = "reached" mask, planes 1..num_planes-1 = distance bits 0.. ;
