@@ -76,6 +76,13 @@ SIGNATURES = {
                                 POINTER(c_int32), POINTER(c_int32), c_void_p]),
     "gp_decode_gathered": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int64, c_int32, c_int32, c_int32,
                                    c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p]),
+    "gp_msbfs_pack": (c_int, [c_void_p, c_int32, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int32),
+                              POINTER(c_int32), POINTER(c_void_p), c_void_p]),
+    "gp_msbfs_ipc_export": (c_int, [c_void_p, c_void_p, POINTER(c_int64)]),
+    "gp_ipc_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "gp_ipc_close": (c_int, [c_void_p]),
+    "gp_decode_peers": (c_int, [c_void_p, c_int32, c_int64, c_int64, c_int32, c_int32, c_int64, c_void_p, c_int64,
+                                c_int64, c_void_p, c_int64, c_int64, c_void_p]),
     "gp_normalize_into": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p]),
     "gp_geodesic_embed_host": (c_int, [c_void_p, c_int64, c_int64, c_uint32, c_void_p, c_int64, c_void_p,
                                        c_int64, c_void_p, c_int64, c_int64, c_void_p, POINTER(MsbfsStats)]),

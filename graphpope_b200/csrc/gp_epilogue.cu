@@ -27,6 +27,7 @@ struct Valid {
 __device__ __forceinline__ Valid valid_arrays(const GpDecodeParams &p)
 {
     int na = p.num_arrays;
+    if (p.packed) na = GP_PACKED_ARRAYS;
     if (na < 0) {
         const int ml = p.status[GP_BFS_ST_MAX_LEVEL];
         na = ml <= GP_BFS_LEVEL_ARRAYS ? 1 + ml : GP_BFS_RESULT_ARRAYS;
@@ -176,14 +177,21 @@ __global__ void __launch_bounds__(256) decode_features_bytes_kernel(GpDecodePara
             }
         }
         for (int r = 0; r < p.num_ranks; ++r) {
-            const unsigned char *blk = reinterpret_cast<const unsigned char *>(p.planes0 + (size_t)r * p.rank_stride);
+            const unsigned char *blk = reinterpret_cast<const unsigned char *>(
+                p.packed ? p.rank_ptr[r] : p.planes0 + (size_t)r * p.rank_stride);
             for (int b = 0; b < batches; ++b) {
                 const int col0 = b * 64 * p.wb + lane * 8;  // first of this lane's 8 columns inside the rank
                 if (lane >= row_bytes || col0 >= kr) continue;
                 const unsigned char *rowp = blk + ((size_t)b * p.n + (size_t)u) * row_bytes + lane;
                 const u32 reach = rowp[0];
                 u32 m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-                if (reach) {
+                if (reach && p.packed) {
+                    // hop index already bit-sliced by the owner rank; these loads cross NVLink for peers
+                    m0 = rowp[1 * plane_bytes];
+                    m1 = rowp[2 * plane_bytes];
+                    m2 = rowp[3 * plane_bytes];
+                    m3 = rowp[4 * plane_bytes];
+                } else if (reach) {
 #pragma unroll
                     for (int l = 1; l <= GP_BFS_LEVEL_ARRAYS; ++l) {
                         if (l <= va.levels) {
@@ -202,7 +210,7 @@ __global__ void __launch_bounds__(256) decode_features_bytes_kernel(GpDecodePara
                                   (((m3 >> c) & 1u) << 3);
                     v[c] = ((reach >> c) & 1u) ? s_inv[d] : 0.0f;
                 }
-                if (va.deep && reach) {
+                if (va.deep && reach && !p.packed) {
                     const unsigned char *pl = rowp + (size_t)(1 + GP_BFS_LEVEL_ARRAYS) * plane_bytes;
                     u32 e[GP_BFS_PLANES];
 #pragma unroll
@@ -250,6 +258,33 @@ __global__ void __launch_bounds__(256) normalize_u16_kernel(const uint16_t *__re
         const long long u = i / k, j = i - u * k;
         const u32 d = dist[(size_t)u * ld_dist + j];
         out[(size_t)u * ld_out + col_offset + j] = d == GP_UNREACHABLE_U16 ? 0.0f : inv_hops(d);
+    }
+}
+
+// Exchange format for the multi-GPU assembly: P[0] = reached mask, P[1 + q] = bit q of the hop count
+// (hops <= 15).  Five arrays whatever the depth, so ranks need not agree on a size before exchanging.
+__global__ void __launch_bounds__(256) pack_result_kernel(const u64 *__restrict__ result, long long stride,
+                                                          const int *__restrict__ status, u64 *__restrict__ packed,
+                                                          int *deep_flag)
+{
+    const int ml = status[GP_BFS_ST_MAX_LEVEL];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *deep_flag = ml > GP_BFS_LEVEL_ARRAYS ? 1 : 0;
+    const int levels = min(ml, GP_BFS_LEVEL_ARRAYS);
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < stride; i += step) {
+        u64 m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+        for (int l = 1; l <= levels; ++l) {
+            const u64 w = result[(size_t)l * stride + i];
+            if (l & 1) m0 |= w;
+            if (l & 2) m1 |= w;
+            if (l & 4) m2 |= w;
+            if (l & 8) m3 |= w;
+        }
+        packed[i] = result[i];
+        packed[(size_t)1 * stride + i] = m0;
+        packed[(size_t)2 * stride + i] = m1;
+        packed[(size_t)3 * stride + i] = m2;
+        packed[(size_t)4 * stride + i] = m3;
     }
 }
 
@@ -375,4 +410,99 @@ extern "C" int gp_normalize_into(const uint16_t *d_dist, int64_t num_nodes, int6
     GP_LAUNCH(normalize_u16_kernel, grid_for(num_nodes * num_anchors, 256), 256, 0, (cudaStream_t)stream_, d_dist, num_nodes, num_anchors, ld_dist, d_out, ld_out, col_offset);
     GP_CUDA_CHECK(cudaGetLastError());
     return GP_OK;
+}
+
+// ------------------------------------------------------------------ peer-to-peer assembly
+extern "C" int gp_msbfs_pack(gp_msbfs_t *h, int32_t slot, const uint64_t **d_packed, int64_t *plane_stride_words,
+                             int32_t *batches, int32_t *words_per_batch, const int32_t **d_deep_flag,
+                             gp_stream_t stream_)
+{
+    GP_REQUIRE(h != nullptr && (slot == 0 || slot == 1), GP_ERR_INVALID, "gp_msbfs_pack: bad argument");
+    GP_REQUIRE(h->ran, GP_ERR_INVALID, "gp_msbfs_pack: gp_msbfs_run has not been called");
+    const size_t cap_words = (size_t)h->cap_words_per_node * (size_t)(h->num_nodes > 0 ? h->num_nodes : 1);
+    if (h->packed == nullptr) {
+        GP_CUDA_CHECK(cudaMalloc((void **)&h->packed, 2 * GP_PACKED_ARRAYS * cap_words * sizeof(u64)));
+        GP_CUDA_CHECK(cudaMalloc((void **)&h->deep_flag, sizeof(int)));
+    }
+    const long long stride = (long long)h->wb * h->batches * h->num_nodes;
+    u64 *dst = h->packed + (size_t)slot * GP_PACKED_ARRAYS * cap_words;
+    if (stride > 0 && h->num_anchors > 0)
+        GP_LAUNCH(pack_result_kernel, grid_for(stride, 256), 256, 0, (cudaStream_t)stream_, h->seen, stride, h->status,
+                  dst, h->deep_flag);
+    GP_CUDA_CHECK(cudaGetLastError());
+    if (d_packed) *d_packed = (const uint64_t *)dst;
+    if (plane_stride_words) *plane_stride_words = stride;
+    if (batches) *batches = h->batches;
+    if (words_per_batch) *words_per_batch = h->wb;
+    if (d_deep_flag) *d_deep_flag = h->deep_flag;
+    return GP_OK;
+}
+
+extern "C" int gp_msbfs_ipc_export(gp_msbfs_t *h, uint8_t *handle64, int64_t *slot_stride_words)
+{
+    GP_REQUIRE(h != nullptr && handle64 != nullptr && slot_stride_words != nullptr, GP_ERR_INVALID,
+               "gp_msbfs_ipc_export: NULL argument");
+    const size_t cap_words = (size_t)h->cap_words_per_node * (size_t)(h->num_nodes > 0 ? h->num_nodes : 1);
+    if (h->packed == nullptr) {
+        GP_CUDA_CHECK(cudaMalloc((void **)&h->packed, 2 * GP_PACKED_ARRAYS * cap_words * sizeof(u64)));
+        GP_CUDA_CHECK(cudaMalloc((void **)&h->deep_flag, sizeof(int)));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t hd;
+    GP_CUDA_CHECK(cudaIpcGetMemHandle(&hd, h->packed));
+    memcpy(handle64, &hd, 64);
+    *slot_stride_words = (int64_t)(GP_PACKED_ARRAYS * cap_words);
+    return GP_OK;
+}
+
+extern "C" int gp_ipc_open(const uint8_t *handle64, void **d_ptr)
+{
+    GP_REQUIRE(handle64 != nullptr && d_ptr != nullptr, GP_ERR_INVALID, "gp_ipc_open: NULL argument");
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, 64);
+    GP_CUDA_CHECK(cudaIpcOpenMemHandle(d_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    return GP_OK;
+}
+
+extern "C" int gp_ipc_close(void *d_ptr)
+{
+    if (d_ptr) GP_CUDA_CHECK(cudaIpcCloseMemHandle(d_ptr));
+    return GP_OK;
+}
+
+extern "C" int gp_decode_peers(const uint64_t *const *h_rank_ptrs, int32_t num_ranks, int64_t num_nodes,
+                               int64_t anchors_per_rank, int32_t batches, int32_t words_per_batch,
+                               int64_t plane_stride_words, const float *d_x, int64_t num_features, int64_t ld_x,
+                               float *d_out, int64_t ld_out, int64_t col_offset, gp_stream_t stream_)
+{
+    GP_REQUIRE(h_rank_ptrs != nullptr && d_out != nullptr, GP_ERR_INVALID, "gp_decode_peers: NULL argument");
+    GP_REQUIRE(num_ranks >= 1 && num_ranks <= GP_MAX_RANKS, GP_ERR_UNSUPPORTED, "gp_decode_peers: 1..%d ranks",
+               GP_MAX_RANKS);
+    GP_REQUIRE(num_nodes >= 0 && anchors_per_rank > 0 && anchors_per_rank % 8 == 0 && batches >= 1 &&
+                   (words_per_batch == 1 || words_per_batch == 2 || words_per_batch == 4),
+               GP_ERR_INVALID, "gp_decode_peers: bad shape (anchors per rank must be a multiple of 8)");
+    GP_REQUIRE(ld_out >= col_offset + anchors_per_rank * num_ranks && ld_out % 4 == 0 && col_offset % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0,
+               GP_ERR_INVALID, "gp_decode_peers: output must be 16-byte aligned with ld_out, col_offset multiples of 4");
+    GpDecodeParams p;
+    memset(&p, 0, sizeof(p));
+    p.packed = 1;
+    for (int r = 0; r < num_ranks; ++r) {
+        GP_REQUIRE(h_rank_ptrs[r] != nullptr, GP_ERR_INVALID, "gp_decode_peers: NULL rank pointer");
+        p.rank_ptr[r] = (const u64 *)h_rank_ptrs[r];
+    }
+    p.plane_stride = plane_stride_words;
+    p.num_ranks = num_ranks;
+    p.num_arrays = GP_PACKED_ARRAYS;
+    p.n = num_nodes;
+    p.anchors_per_rank = anchors_per_rank;
+    p.wb = words_per_batch;
+    p.x = d_x;
+    p.num_features = d_x ? num_features : 0;
+    p.ld_x = ld_x;
+    p.out = d_out;
+    p.ld_out = ld_out;
+    p.col_offset = col_offset;
+    (void)batches;
+    return gp_launch_decode_features(p, (cudaStream_t)stream_);
 }

@@ -667,6 +667,8 @@ extern "C" int gp_msbfs_free(gp_msbfs_t *h)
     cudaFree(h->hub_acc);
     cudaFree(h->hub_cnt);
     cudaFree(h->bar);
+    cudaFree(h->packed);
+    cudaFree(h->deep_flag);
     cudaFree(h->status);
     cudaFree(h->counters);
     cudaFree(h->trace);

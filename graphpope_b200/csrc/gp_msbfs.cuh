@@ -9,6 +9,7 @@ constexpr int GP_BFS_PLANES = 16;           // deep-hop distance bit planes (uin
 constexpr int GP_BFS_LEVEL_ARRAYS = 15;     // hops 1..15 are recorded as write-once frontier arrays
 constexpr int GP_BFS_CACHE_ITERS = 4;      // warp-iterations whose work items are cached in shared memory
 constexpr int GP_BFS_DONE_BATCHES = 8;     // batches that keep per-row "done" flags for cached items
+constexpr int GP_MAX_RANKS = 8;             // GPUs of one NVSwitch node
 constexpr int GP_BFS_RESULT_ARRAYS = 1 + GP_BFS_LEVEL_ARRAYS + GP_BFS_PLANES;  // 32
 constexpr long long GP_BFS_TRACE_WORDS = 32ll * 160 * 4 * 32 * 4;  // levels * max warps * 4 slots           // distance bit planes (uint16 range)
 
@@ -42,6 +43,8 @@ struct gp_msbfs {
     u64 *bar = nullptr;      // grid barrier words
     int64_t hub_capacity = 0;
     bool hub_zeroed = false;
+    u64 *packed = nullptr;   // [2 slots][GP_PACKED_ARRAYS][cap words] exchange buffers (allocated on first pack)
+    int *deep_flag = nullptr;  // device int: 1 if the last packed run had hops > 15 (packed format invalid)
     int *status = nullptr;      // [GP_BFS_ST_WORDS]
     u64 *counters = nullptr;    // [4] gathers issued, pushes issued, ...
     u64 *trace = nullptr;       // [32 levels][warps][4] phase clocks, only with GP_BFS_TRACE=1
@@ -66,5 +69,10 @@ struct GpDecodeParams {
     long long num_features, ld_x;
     float *out;
     long long ld_out, col_offset;
+    // packed exchange format (gp_msbfs_pack): 5 arrays per rank = reached mask + 4 hop-index bit planes,
+    // read in place from every rank's buffer (own memory or NVLink peer mappings)
+    int packed;
+    const u64 *rank_ptr[GP_MAX_RANKS];
 };
+constexpr int GP_PACKED_ARRAYS = 5;
 int gp_launch_decode_features(const GpDecodeParams &p, cudaStream_t stream);

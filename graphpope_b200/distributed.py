@@ -119,3 +119,99 @@ def sharded_geodesic_embed_host(engine, edge_index: torch.Tensor, anchors, x: to
     torch.cuda.current_stream().synchronize()
     check(_lib.load().gp_host_concat(_ptr(x), f, _ptr(staging["block_h"]), k, n, _ptr(out), out.stride(0)))
     return out
+
+
+class PeerAssembly:
+    """NVLink peer-to-peer assembly of the sharded result (the B200-native form of the exchange step).
+
+    Instead of all-gathering result masks into a staging buffer and then decoding, every rank maps the
+    other ranks' packed result buffers (CUDA IPC over NVSwitch) once, and the fused epilogue kernel
+    reads them *in place* while it writes the fp32 rows: own shard from HBM, peer shards through
+    NVLink loads, so the transfer overlaps the HBM-bound output writes tile by tile.  Per step there
+    is one tiny NCCL all-reduce (it carries the "hops > 15" flag and doubles as the cross-GPU barrier
+    that orders pack before decode); buffers are double-buffered so no second barrier is needed.
+    """
+
+    def __init__(self, engine, group=None):
+        import ctypes
+
+        from . import _lib
+        from ._lib import check
+
+        self.engine, self.group = engine, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("PeerAssembly covers the GPUs of one NVSwitch node (<= 8 ranks)")
+        self.lib = _lib.load()
+        handle = (ctypes.c_uint8 * 64)()
+        slot_stride = ctypes.c_int64()
+        check(self.lib.gp_msbfs_ipc_export(engine.bfs._h, handle, ctypes.byref(slot_stride)))
+        self.slot_stride_words = slot_stride.value
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device="cuda")
+        every = torch.empty(self.world * 64, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(every, mine, group=group)
+        every = every.cpu().view(self.world, 64)
+        self.base = []
+        self._opened = []
+        for r in range(self.world):
+            if r == self.rank:
+                self.base.append(None)  # filled from gp_msbfs_pack (own allocation)
+                continue
+            buf = (ctypes.c_uint8 * 64)(*every[r].tolist())
+            ptr = ctypes.c_void_p()
+            check(self.lib.gp_ipc_open(buf, ctypes.byref(ptr)))
+            self.base.append(ptr.value)
+            self._opened.append(ptr.value)
+        self.step = 0
+        self.flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def close(self):
+        for p in self._opened:
+            self.lib.gp_ipc_close(c_void_p(p))
+        self._opened = []
+
+    def run(self, edge_index, anchors, x=None, out=None):
+        """Same contract as :func:`sharded_geodesic_features`; returns (out, deep) where ``deep`` is a
+        device int32 that is 1 if some shard had hops > 15 (then the caller must use the gather path)."""
+        import ctypes
+
+        from ._lib import check
+        from .device import _ptr, _stream
+
+        eng = self.engine
+        n = eng.csr.num_nodes
+        k = anchors.numel()
+        f = 0 if x is None else x.size(1)
+        if out is None:
+            out = torch.empty((n, f + k), dtype=torch.float32, device="cuda")
+        lo, hi = shard_bounds(k, self.world, self.rank)
+        slot = self.step & 1
+        self.step += 1
+        eng.csr.build(edge_index)
+        eng.bfs.run(anchors[lo:hi].contiguous())
+        packed, stride = ctypes.c_void_p(), ctypes.c_int64()
+        batches, wb, deep = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_void_p()
+        check(self.lib.gp_msbfs_pack(eng.bfs._h, slot, ctypes.byref(packed), ctypes.byref(stride), ctypes.byref(batches),
+                                     ctypes.byref(wb), ctypes.byref(deep), _stream()))
+        # flag <- max over ranks of "my shard is deep"; stream-ordered, so it is also the barrier between
+        # every rank's pack and every rank's decode
+        self.flag.copy_(_wrap_device_words_i32(deep.value), non_blocking=True)
+        dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.group)
+        ptrs = (ctypes.c_void_p * self.world)()
+        for r in range(self.world):
+            base = packed.value - slot * self.slot_stride_words * 8 if r == self.rank else self.base[r]
+            ptrs[r] = base + slot * self.slot_stride_words * 8
+        check(self.lib.gp_decode_peers(ptrs, self.world, n, hi - lo, batches.value, wb.value, stride.value, _ptr(x), f,
+                                       x.stride(0) if x is not None and n > 1 else f, _ptr(out),
+                                       out.stride(0) if n > 1 else f + k, f, _stream()))
+        return out, self.flag
+
+
+def _wrap_device_words_i32(ptr: int) -> torch.Tensor:
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (1,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(h, device="cuda")

@@ -157,6 +157,22 @@ int gp_decode_gathered(const uint64_t *d_gathered, int64_t rank_stride_words, in
                        const float *d_x, int64_t num_features, int64_t ld_x,
                        float *d_out, int64_t ld_out, int64_t col_offset, gp_stream_t stream);
 
+/* ---- peer-to-peer assembly (NVLink / NVSwitch): no staging buffer, no all-gather.
+ * gp_msbfs_pack (async) rewrites the last result into the fixed-size exchange format (reached mask +
+ * 4 hop-index bit planes, valid for hops <= 15; *d_deep_flag tells on the device if that failed) in one
+ * of two slots; gp_msbfs_ipc_export / gp_ipc_open hand the buffer to the other ranks of the node as CUDA
+ * IPC mappings; gp_decode_peers (async) is the fused epilogue whose loads read every rank's buffer in
+ * place — its own from HBM, the peers' over NVLink — while it writes the [N, F+K] rows.               */
+int gp_msbfs_pack(gp_msbfs_t *bfs, int32_t slot, const uint64_t **d_packed, int64_t *plane_stride_words,
+                  int32_t *batches, int32_t *words_per_batch, const int32_t **d_deep_flag, gp_stream_t stream);
+int gp_msbfs_ipc_export(gp_msbfs_t *bfs, uint8_t *handle64, int64_t *slot_stride_words);
+int gp_ipc_open(const uint8_t *handle64, void **d_ptr);
+int gp_ipc_close(void *d_ptr);
+int gp_decode_peers(const uint64_t *const *h_rank_ptrs, int32_t num_ranks, int64_t num_nodes,
+                    int64_t anchors_per_rank, int32_t batches, int32_t words_per_batch, int64_t plane_stride_words,
+                    const float *d_x, int64_t num_features, int64_t ld_x, float *d_out, int64_t ld_out,
+                    int64_t col_offset, gp_stream_t stream);
+
 /* async.  Stand-alone epilogue from a uint16 hop matrix (utils.py:73,76,125). */
 int gp_normalize_into(const uint16_t *d_dist, int64_t num_nodes, int64_t num_anchors, int64_t ld_dist,
                       float *d_out, int64_t ld_out, int64_t col_offset, gp_stream_t stream);

@@ -32,7 +32,19 @@ for name, k_total in (("pubmed-shape", 256), ("flickr-shape", 1024), ("flickr-sh
     dist.barrier(); torch.cuda.synchronize(); ev0.record()
     for _ in range(10): gpd.sharded_geodesic_features(eng, ei_d, a_d, x_d, out)
     ev1.record(); torch.cuda.synchronize()
-    if rank == 0: print(f"    sharded step {ev0.elapsed_time(ev1) / 10:.3f} ms", flush=True)
+    if rank == 0: print(f"    sharded step (NCCL all-gather of masks) {ev0.elapsed_time(ev1) / 10:.3f} ms", flush=True)
+    # peer-to-peer assembly: epilogue reads the other ranks' packed buffers over NVLink
+    peer = gpd.PeerAssembly(eng)
+    out2, deep = peer.run(ei_d, a_d, x_d)
+    torch.cuda.synchronize()
+    same_p2p = bool(torch.equal(out2, ref)) and int(deep.item()) == 0
+    ok &= same_p2p
+    for _ in range(3): peer.run(ei_d, a_d, x_d, out2)
+    dist.barrier(); torch.cuda.synchronize(); ev0.record()
+    for _ in range(10): peer.run(ei_d, a_d, x_d, out2)
+    ev1.record(); torch.cuda.synchronize()
+    if rank == 0: print(f"    p2p == 1-GPU: {same_p2p}; p2p step {ev0.elapsed_time(ev1) / 10:.3f} ms", flush=True)
+    dist.barrier(); peer.close()
 t = torch.tensor([int(ok)], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0: print("DIST CHECK", "PASSED" if int(t.item()) else "FAILED", flush=True)
 dist.destroy_process_group()
