@@ -226,11 +226,16 @@ def main():
     engine = dev.GeodesicEngine(n, ei.shape[1], K_PER_GPU)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 
+    peer = gpd.PeerAssembly(engine) if world > 1 else None
+    deep_flags = []
+
     def step():
         if world == 1:
             engine.run(ei_d, a_d, x_d, out_d)
         else:
-            gpd.sharded_geodesic_features(engine, ei_d, a_d, x_d, out_d)
+            # NVLink peer-to-peer assembly; the flag says (on the device) whether the packed
+            # hop format was valid (hops <= 15) — checked once after the timed loop
+            deep_flags.append(peer.run(ei_d, a_d, x_d, out_d)[1])
 
     # clocks are sampled from before the warm-up to the end of the e2e loop (the device-timed region
     # alone lasts a few milliseconds, shorter than one nvidia-smi sampling period)
@@ -256,6 +261,9 @@ def main():
         bfs_ms.append(engine.bfs.kernel_ms())
     barrier()
     launches = dev.launch_count() - launches0
+    if world > 1 and int(deep_flags[-1].item()) != 0:
+        raise RuntimeError("a shard had hops > 15: the packed exchange is invalid for this graph; use "
+                           "distributed.sharded_geodesic_features (all-gather path)")
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
     total_ms = float(sum(step_ms))
     stats = engine.bfs.stats()
@@ -279,7 +287,7 @@ def main():
         if world == 1:
             dev.geodesic_embed_host(ei_h, n, anchors, x_h, out=out_h)
         else:
-            gpd.sharded_geodesic_embed_host(engine, ei_h, anchors, x_h, out_h, e2e_staging)
+            gpd.sharded_geodesic_embed_host(engine, ei_h, anchors, x_h, out_h, e2e_staging, peer=peer)
 
     for _ in range(3):
         e2e_step()
@@ -322,7 +330,7 @@ def main():
                        "dedup_edges": e_unique, "parallelism": f"anchor-shard x{world}",
                        "l2": "256 MiB buffer written between steps (untimed) to flush L2",
                        "step": "csr build + ms-bfs + fused normalise/concat epilogue" +
-                               (" + plane all-gather" if world > 1 else "")},
+                               (" + pack + NVLink peer-to-peer assembly in the epilogue" if world > 1 else "")},
             "roofline": {"bound": "hbm", "kernel": "msbfs_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",

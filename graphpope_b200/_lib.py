@@ -78,6 +78,9 @@ SIGNATURES = {
                                    c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p]),
     "gp_msbfs_pack": (c_int, [c_void_p, c_int32, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int32),
                               POINTER(c_int32), POINTER(c_void_p), c_void_p]),
+    "gp_geodesic_run_packed": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p]),
+    "gp_msbfs_packed_info": (c_int, [c_void_p, c_int32, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int32),
+                                     POINTER(c_int32), POINTER(c_void_p)]),
     "gp_msbfs_ipc_export": (c_int, [c_void_p, c_void_p, POINTER(c_int64)]),
     "gp_ipc_open": (c_int, [c_void_p, POINTER(c_void_p)]),
     "gp_ipc_close": (c_int, [c_void_p]),

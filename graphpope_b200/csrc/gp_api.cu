@@ -209,7 +209,8 @@ int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t 
 {
     GP_TRY(gp_csr_build(csr, d_ei, e, s));
     GP_TRY(gp_msbfs_run(bfs, d_anchors, k, s));
-    GP_TRY(gp_msbfs_features(bfs, d_x, f, ldx, d_out, ldo, coff, s));
+    if (d_out != nullptr) GP_TRY(gp_msbfs_features(bfs, d_x, f, ldx, d_out, ldo, coff, s));
+    else GP_TRY(gp_msbfs_pack(bfs, (int32_t)coff, nullptr, nullptr, nullptr, nullptr, nullptr, s));  // coff = slot
     return GP_OK;
 }
 
@@ -294,6 +295,15 @@ extern "C" int gp_geodesic_run(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_
     }
     return run_pipeline_eager(csr, bfs, d_edge_index, num_edges, d_anchors, num_anchors, d_x, num_features, ld_x,
                               d_out, ld_out, col_offset, stream);
+}
+
+// Sharded form: csr build + ms-bfs + pack into exchange slot `slot` (graph-replayed like gp_geodesic_run).
+extern "C" int gp_geodesic_run_packed(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_edge_index, int64_t num_edges,
+                                      const int64_t *d_anchors, int64_t num_anchors, int32_t slot, gp_stream_t stream)
+{
+    GP_REQUIRE(slot == 0 || slot == 1, GP_ERR_INVALID, "gp_geodesic_run_packed: slot must be 0 or 1");
+    return gp_geodesic_run(csr, bfs, d_edge_index, num_edges, d_anchors, num_anchors, nullptr, 0, 0, nullptr, 0, slot,
+                           stream);
 }
 
 extern "C" int gp_host_concat(const float *h_x, int64_t num_features, const float *h_block, int64_t block_cols,

@@ -438,6 +438,20 @@ extern "C" int gp_msbfs_pack(gp_msbfs_t *h, int32_t slot, const uint64_t **d_pac
     return GP_OK;
 }
 
+extern "C" int gp_msbfs_packed_info(gp_msbfs_t *h, int32_t slot, const uint64_t **d_packed, int64_t *plane_stride_words,
+                                    int32_t *batches, int32_t *words_per_batch, const int32_t **d_deep_flag)
+{
+    GP_REQUIRE(h != nullptr && (slot == 0 || slot == 1), GP_ERR_INVALID, "gp_msbfs_packed_info: bad argument");
+    GP_REQUIRE(h->packed != nullptr, GP_ERR_INVALID, "gp_msbfs_packed_info: nothing has been packed yet");
+    const size_t cap_words = (size_t)h->cap_words_per_node * (size_t)(h->num_nodes > 0 ? h->num_nodes : 1);
+    if (d_packed) *d_packed = (const uint64_t *)(h->packed + (size_t)slot * GP_PACKED_ARRAYS * cap_words);
+    if (plane_stride_words) *plane_stride_words = (int64_t)h->wb * h->batches * h->num_nodes;
+    if (batches) *batches = h->batches;
+    if (words_per_batch) *words_per_batch = h->wb;
+    if (d_deep_flag) *d_deep_flag = h->deep_flag;
+    return GP_OK;
+}
+
 extern "C" int gp_msbfs_ipc_export(gp_msbfs_t *h, uint8_t *handle64, int64_t *slot_stride_words)
 {
     GP_REQUIRE(h != nullptr && handle64 != nullptr && slot_stride_words != nullptr, GP_ERR_INVALID,

@@ -94,7 +94,7 @@ def sharded_geodesic_features(engine, edge_index: torch.Tensor, anchors: torch.T
 
 
 def sharded_geodesic_embed_host(engine, edge_index: torch.Tensor, anchors, x: torch.Tensor | None,
-                                out: torch.Tensor, staging: dict, group=None) -> torch.Tensor:
+                                out: torch.Tensor, staging: dict, group=None, peer=None) -> torch.Tensor:
     """Host-buffer form of the sharded path (what a DataModule calls): HOST ``edge_index`` / ``x`` in,
     HOST float32 ``[N, F + K]`` out.  ``staging`` caches the device / pinned scratch between calls."""
     from . import _lib
@@ -114,9 +114,17 @@ def sharded_geodesic_embed_host(engine, edge_index: torch.Tensor, anchors, x: to
         staging["block_h"] = torch.empty((n, k), dtype=torch.float32).pin_memory()
     staging["ei"].copy_(edge_index, non_blocking=True)
     staging["anchors"].copy_(a, non_blocking=True)
-    sharded_geodesic_features(engine, staging["ei"], staging["anchors"], None, staging["block_d"], group)
+    if peer is not None:
+        _, deep = peer.run(staging["ei"], staging["anchors"], None, staging["block_d"])
+    else:
+        deep = None
+        sharded_geodesic_features(engine, staging["ei"], staging["anchors"], None, staging["block_d"], group)
     staging["block_h"].copy_(staging["block_d"], non_blocking=True)  # one contiguous DMA
     torch.cuda.current_stream().synchronize()
+    if deep is not None and int(deep.item()) != 0:  # hops > 15 somewhere: redo through the all-gather path
+        sharded_geodesic_features(engine, staging["ei"], staging["anchors"], None, staging["block_d"], group)
+        staging["block_h"].copy_(staging["block_d"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
     check(_lib.load().gp_host_concat(_ptr(x), f, _ptr(staging["block_h"]), k, n, _ptr(out), out.stride(0)))
     return out
 
@@ -188,12 +196,17 @@ class PeerAssembly:
         lo, hi = shard_bounds(k, self.world, self.rank)
         slot = self.step & 1
         self.step += 1
-        eng.csr.build(edge_index)
-        eng.bfs.run(anchors[lo:hi].contiguous())
+        key = (anchors.data_ptr(), lo, hi)
+        if getattr(self, "_shard_key", None) != key:  # keep the shard tensor alive and its pointer stable (graph key)
+            self._shard_key, self._shard = key, anchors[lo:hi].contiguous()
+        edge_index = edge_index.contiguous()
+        eng.csr._edges, eng.bfs._anchors, eng.bfs.num_anchors = edge_index, self._shard, hi - lo
+        check(self.lib.gp_geodesic_run_packed(eng.csr._h, eng.bfs._h, _ptr(edge_index), edge_index.size(1),
+                                              _ptr(self._shard), hi - lo, slot, _stream()))
         packed, stride = ctypes.c_void_p(), ctypes.c_int64()
         batches, wb, deep = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_void_p()
-        check(self.lib.gp_msbfs_pack(eng.bfs._h, slot, ctypes.byref(packed), ctypes.byref(stride), ctypes.byref(batches),
-                                     ctypes.byref(wb), ctypes.byref(deep), _stream()))
+        check(self.lib.gp_msbfs_packed_info(eng.bfs._h, slot, ctypes.byref(packed), ctypes.byref(stride),
+                                            ctypes.byref(batches), ctypes.byref(wb), ctypes.byref(deep)))
         # flag <- max over ranks of "my shard is deep"; stream-ordered, so it is also the barrier between
         # every rank's pack and every rank's decode
         self.flag.copy_(_wrap_device_words_i32(deep.value), non_blocking=True)

@@ -165,6 +165,13 @@ int gp_decode_gathered(const uint64_t *d_gathered, int64_t rank_stride_words, in
  * place — its own from HBM, the peers' over NVLink — while it writes the [N, F+K] rows.               */
 int gp_msbfs_pack(gp_msbfs_t *bfs, int32_t slot, const uint64_t **d_packed, int64_t *plane_stride_words,
                   int32_t *batches, int32_t *words_per_batch, const int32_t **d_deep_flag, gp_stream_t stream);
+/* async.  gp_csr_build + gp_msbfs_run + gp_msbfs_pack(slot) as one graph-replayed call (a rank's share of
+ * a sharded step up to the exchange).                                                                */
+int gp_geodesic_run_packed(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_edge_index, int64_t num_edges,
+                           const int64_t *d_anchors, int64_t num_anchors, int32_t slot, gp_stream_t stream);
+/* Pointers / shape of exchange slot `slot` without launching anything. */
+int gp_msbfs_packed_info(gp_msbfs_t *bfs, int32_t slot, const uint64_t **d_packed, int64_t *plane_stride_words,
+                         int32_t *batches, int32_t *words_per_batch, const int32_t **d_deep_flag);
 int gp_msbfs_ipc_export(gp_msbfs_t *bfs, uint8_t *handle64, int64_t *slot_stride_words);
 int gp_ipc_open(const uint8_t *handle64, void **d_ptr);
 int gp_ipc_close(void *d_ptr);
