@@ -80,7 +80,7 @@ __global__ void order_kernel(const u64 *__restrict__ okeys, long long n, int *__
         // rank boundary: number of rows with degree > thr  <=>  key high half < 65535 - thr
         int cnt = (int)n;
         if (gid < GP_NUM_CLASSES - 1) {
-            const int thr = GP_CHUNK_EDGES >> gid;  // 128, 64, 32, 16, 8
+            const int thr = GP_CHUNK_EDGES >> gid;  // 128, 64, 32, 16, 8, 4
             cnt = (int)lower_bound_u64(okeys, (u32)n, (u64)(65535u - (u32)thr) << 32);
         }
         meta[GP_META_RANK + gid] = cnt;
@@ -133,7 +133,7 @@ hub_scan_kernel(const int *__restrict__ order, const int *__restrict__ rowptr, i
         int ent = 0, slot = 0;
         for (int c = 0; c < GP_NUM_CLASSES; ++c) {
             const int rows = c == 0 ? chunks : meta[GP_META_RANK + c] - meta[GP_META_RANK + c - 1];
-            const int g = c <= 1 ? 16 : (16 >> (c - 1));
+            const int g = c <= 1 ? 32 : (32 >> (c - 1));
             meta[GP_META_ENT_BASE + c] = ent;
             meta[GP_META_SLOT_BASE + c] = slot;
             ent += rows;

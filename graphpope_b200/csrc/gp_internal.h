@@ -4,13 +4,14 @@
 #include "gp_common.cuh"
 #include "gp_sort.cuh"
 
-// Work list of the MS-BFS (see gp_msbfs.cu).  A "pair slot" gathers at most GP_SLOT_EDGES
-// neighbour rows; a row of degree d is served by G = 1,2,4,8,16 slots (G * GP_SLOT_EDGES >= d),
-// rows above 16 * GP_SLOT_EDGES edges are cut into chunks of that size (class 0).
-constexpr int GP_SLOT_EDGES = 8;
-constexpr int GP_CHUNK_EDGES = 16 * GP_SLOT_EDGES;  // 128
-constexpr int GP_NUM_CLASSES = 6;   // 0: chunks of hub rows (G=16), 1: G=16, 2: G=8, 3: G=4, 4: G=2, 5: G=1
-constexpr int GP_SLOT_ALIGN = 32;   // class regions start on a multiple of this many slots
+// Work list of the MS-BFS (see gp_msbfs.cu).  A "slot" is one thread gathering at most
+// GP_SLOT_EDGES neighbour rows; a row of degree d is served by G = 1,2,4,8,16,32 slots
+// (G * GP_SLOT_EDGES >= d), rows above 32 * GP_SLOT_EDGES edges are cut into chunks of that
+// size (class 0), one warp-wide tile each.
+constexpr int GP_SLOT_EDGES = 4;
+constexpr int GP_CHUNK_EDGES = 32 * GP_SLOT_EDGES;  // 128
+constexpr int GP_NUM_CLASSES = 7;   // 0: chunks of hub rows (G=32), 1: G=32, 2: G=16, 3: G=8, 4: G=4, 5: G=2, 6: G=1
+constexpr int GP_SLOT_ALIGN = 32;   // class regions start on a multiple of this many slots (one warp tile)
 
 // Device-resident metadata words of a CSR (int32 each).
 enum : int {
@@ -20,9 +21,9 @@ enum : int {
     GP_META_IS_SYMMETRIC = 5,
     GP_META_IN_BUILT = 6,
     GP_META_NUM_HUB_ROWS = 7,   // rows with degree > GP_CHUNK_EDGES
-    GP_META_RANK = 8,           // [6]: rows (in degree order) with degree > 128, 64, 32, 16, 8, then N
-    GP_META_ENT_BASE = 16,      // [7]: first descriptor of each class, then the total
-    GP_META_SLOT_BASE = 24,     // [7]: first pair slot of each class, then the total
+    GP_META_RANK = 8,           // [7]: rows (in degree order) with degree > 128, 64, 32, 16, 8, 4, then N
+    GP_META_ENT_BASE = 16,      // [8]: first descriptor of each class, then the total
+    GP_META_SLOT_BASE = 24,     // [8]: first slot of each class, then the total
     GP_META_WORDS = 32
 };
 

@@ -9,14 +9,23 @@
 // OUT-neighbours: new[u] = (OR_{u->v} frontier[v]) & ~seen[u].  Each row is finalised by exactly
 // one thread group, so there are no atomics on the lane state and a level needs one grid barrier.
 //
-// Work decomposition.  On the named graphs the lane state (a few MB) lives in L2 and a level is
-// LATENCY bound (an SM has ~6K neighbour gathers per level, i.e. ~12 per thread pair), so the
-// kernel is organised to keep dependent-load chains short and every gather of a chain in flight
-// at once: the CSR builder (gp_csr.cu) emits a degree-ordered list of 16-byte row descriptors;
-// a row of degree d is served by G = 1,2,4,8,16 "pair slots" of <= 8 edges each (G*8 >= d), hub
-// rows are cut into 128-edge chunks (G = 16) whose partial ORs meet in a small accumulator that
-// the last-arriving chunk finalises.  One slot = descriptor -> <=8 column indices -> <=8 frontier
-// rows (all issued back to back) -> shuffle-OR over the G slots of the row -> finalise.
+// Work decomposition.  On the named graphs the lane state (a few MB) lives in L2.  A dense level is
+// bound by the rate at which an SM can gather random 32-byte rows out of L2 (~1.1 SM-cycles per row,
+// tools/microbench/gather_rate.cu); every other level is bound by instruction issue and the grid
+// barrier, so the kernel (a) gathers only what can matter and (b) keeps the per-slot instruction
+// count small.  The CSR builder (gp_csr.cu) emits a degree-ordered list of 16-byte row descriptors;
+// a row of degree d is served by G = 1,2,4,...,32 "slots" (threads) of <= 4 edges each (4G >= d), hub
+// rows are cut into 128-edge chunks (G = 32, one warp) whose partial ORs meet in a small accumulator
+// that the last-arriving chunk finalises.  One slot = <= 4 column indices -> <= 4 whole frontier rows
+// (one 256-bit load each at 256 anchors per batch, all issued back to back) -> shuffle-OR over the G
+// slots of the row -> finalise.  Three filters cut the gathers to the ones that can matter:
+//   * a per-hop bitmap of non-zero frontier rows, staged in shared memory every level: a neighbour
+//     whose frontier row is zero is not gathered (the first and last levels touch almost nothing);
+//   * per-row "done" flags: a row every still-live lane has reached is never gathered again;
+//   * a per-word "live" mask (lanes whose frontier is non-empty anywhere).
+// Tiles (32 slots of one class) are dealt round-robin to the CTAs, heaviest classes first, and the
+// warps of a CTA pull them from a shared-memory queue, so hub tiles start first and no warp idles
+// while another still has two tiles to go.
 //
 // Data layout (all uint64, node-major so one neighbour gather is one 32-byte sector at wb == 4):
 //   result block R, 32 arrays of [batches][N][wb]:
@@ -52,7 +61,11 @@ struct BfsParams {
     u64 *live;                      // [3][GP_BFS_MAX_LANE_WORDS]
     u64 *hub_acc;                   // [batches][hub_capacity][wb] partial ORs of hub rows
     u32 *hub_cnt;                   // [batches][hub_capacity] chunks arrived
-    u64 *bar;                       // [2] grid barrier words (arrivals | any-count << 32), by level parity
+    u64 *bar;                       // [3] grid barrier words, rotating by level % 3 (see grid_barrier_flags)
+    u32 *nzmap;                     // [3][batches][nzwords] bit u set <=> frontier row u of that hop is non-zero
+    int nzwords;                    // words per batch map = ceil(n / 32)
+    int map_stride;                 // words between the three rotating map sets (batches * nzwords, padded to 4)
+    int map_smem_words;             // map_stride if the maps are staged in shared memory, else 0 (maps off)
     int *status;
     u64 *counters;
     u64 *trace;                     // optional per-warp phase clocks (diagnostics), else nullptr
@@ -61,22 +74,24 @@ struct BfsParams {
 template <int VW>
 __device__ __forceinline__ void vload(const u64 *p, u64 (&v)[VW])
 {
-    if constexpr (VW == 2) {
-        const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(p);
-        v[0] = t.x;
-        v[1] = t.y;
+    if constexpr (VW == 4) {  // one 256-bit load (LDG.E.ENL2.256): a whole 256-anchor row in one request
+        asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+    } else if constexpr (VW == 2) {
+        asm volatile("ld.global.v2.u64 {%0,%1}, [%2];" : "=l"(v[0]), "=l"(v[1]) : "l"(p));
     } else {
-        v[0] = *p;
+        asm volatile("ld.global.u64 %0, [%1];" : "=l"(v[0]) : "l"(p));
     }
 }
 
 template <int VW>
 __device__ __forceinline__ void vstore(u64 *p, const u64 (&v)[VW])
 {
-    if constexpr (VW == 2) {
-        *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(v[0], v[1]);
+    if constexpr (VW == 4) {
+        asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(v[0]), "l"(v[1]), "l"(v[2]), "l"(v[3]) : "memory");
+    } else if constexpr (VW == 2) {
+        asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(v[0]), "l"(v[1]) : "memory");
     } else {
-        *p = v[0];
+        asm volatile("st.global.u64 [%0], %1;" ::"l"(p), "l"(v[0]) : "memory");
     }
 }
 
@@ -99,33 +114,45 @@ __device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p)
     return v;
 }
 
-// Grid barrier that also tells every CTA whether ANY CTA reached a new lane this level.
-// Word layout: low 32 bits = arrivals (monotone), high 32 bits = CTAs that reported `any`.
-// Two words alternate by level parity, so a CTA that is already one barrier ahead never
-// pollutes the word slower CTAs are still polling.
-__device__ __forceinline__ bool grid_barrier_any(u64 *bar_word, u32 &target, u32 &prev_any, u32 nblocks,
-                                                 bool cta_any, u32 *s_bcast, int *s_any_flag)
+__device__ __forceinline__ void red_or_u32(u32 *p, u32 v)
 {
-    target += nblocks;
+    asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Grid barrier that also tells every CTA (a) whether ANY CTA reached a new lane this level,
+// (b) whether ANY CTA still owns a row that can gain lanes and (c) how many rows of the frontier
+// just written are non-zero.  One 64-bit word per level, three words rotating by level % 3 (CTA 0
+// clears the word two levels ahead), so every level starts from zero:
+//   bits [0,12) arrivals, [12,24) CTAs reporting `any`, [24,36) CTAs reporting `notdone`,
+//   [36,64) non-zero frontier rows.  (The launch keeps the grid below 4096 CTAs.)
+constexpr u64 GP_BAR_FIELD = (1ull << 12) - 1ull;
+__device__ __forceinline__ u64 grid_barrier_flags(u64 *bar_word, u32 nblocks, bool cta_any, bool cta_notdone,
+                                                  u64 *s_bcast, int *s_any_flag, int *s_notdone_flag, int *s_nzrows,
+                                                  int *s_queue, int nqueues)
+{
     __syncthreads();
+    if (threadIdx.x < nqueues) s_queue[threadIdx.x] = 0;  // the CTA's tile queues restart with the next level
     if (threadIdx.x == 0) {
-        *s_any_flag = 0;  // every thread has read it (before the sync above); next writes come after the sync below
-        const u64 inc = 1ull | ((u64)(cta_any ? 1u : 0u) << 32);
+        const u64 inc = 1ull | ((u64)(cta_any ? 1u : 0u) << 12) | ((u64)(cta_notdone ? 1u : 0u) << 24) |
+                        ((u64)(u32)*s_nzrows << 36);
+        *s_any_flag = 0;  // every thread has read the flags (before the sync above); next writes come after the sync below
+        *s_notdone_flag = 0;
+        *s_nzrows = 0;
         asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(bar_word), "l"(inc) : "memory");
         u64 v;
         do {
             v = ld_relaxed_u64(bar_word);  // relaxed polling: an acquire load would flush this SM's L1 each time
-        } while ((u32)v < target);
+        } while ((u32)(v & GP_BAR_FIELD) < nblocks);
         u32 dummy;
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dummy) : "l"(bar_word) : "memory");
-        *s_bcast = (u32)(v >> 32);
+        *s_bcast = v;
     }
     __syncthreads();
-    const u32 total_any = *s_bcast;
-    const bool any = total_any != prev_any;
-    prev_any = total_any;
-    return any;
+    return *s_bcast;
 }
+__device__ __forceinline__ bool bar_any(u64 v) { return ((v >> 12) & GP_BAR_FIELD) != 0; }
+__device__ __forceinline__ bool bar_notdone(u64 v) { return ((v >> 24) & GP_BAR_FIELD) != 0; }
+__device__ __forceinline__ long long bar_nzrows(u64 v) { return (long long)(v >> 36); }
 
 #define GP_TRACE(slot)                                                                             \
     do {                                                                                           \
@@ -142,12 +169,14 @@ struct LevelCtx {
     long long plane_stride;
     int level;
     int zero_first, zero_count;  // bit planes [zero_first, zero_first + zero_count) are cleared during this sweep
+    u32 *map_w;    // non-zero-row bitmap of the frontier being written (this batch), or nullptr
 };
 
-// Owner-side update of one row's VW lane words.
+// Owner-side update of one row's VW lane words.  Returns true if the row can still gain lanes
+// (some lane that is live this level has not reached it yet).
 template <int VW>
-__device__ __forceinline__ void finalize_row(const LevelCtx<VW> &c, size_t off, const u64 (&acc)[VW],
-                                             u64 (&seenv)[VW], u64 (&live_acc)[VW])
+__device__ __forceinline__ bool finalize_row(const LevelCtx<VW> &c, size_t off, int row, const u64 (&acc)[VW],
+                                             u64 (&seenv)[VW], u64 (&live_acc)[VW], const u64 (&lv)[VW], int &nzrows)
 {
     u64 nw[VW];
     bool any = false;
@@ -171,6 +200,8 @@ __device__ __forceinline__ void finalize_row(const LevelCtx<VW> &c, size_t off, 
             live_acc[i] |= nw[i];
         }
         vstore<VW>(c.seen + off, seenv);
+        ++nzrows;
+        if (c.map_w != nullptr) red_or_u32(c.map_w + (row >> 5), 1u << (row & 31));
         if (c.level > GP_BFS_LEVEL_ARRAYS) {
             // deep graphs: OR the new lanes into every bit plane set in `level` (fire-and-forget at L2)
             for (int lb = c.level; lb; lb &= lb - 1) {
@@ -181,42 +212,68 @@ __device__ __forceinline__ void finalize_row(const LevelCtx<VW> &c, size_t off, 
             }
         }
     }
+    bool incomplete = false;
+#pragma unroll
+    for (int i = 0; i < VW; ++i) incomplete |= (~seenv[i] & lv[i]) != 0;
+    return incomplete;
 }
 
-// WB lane words per node row; TPE threads share one edge (each loads VW = WB/TPE words).
+// Descriptor and column indices of the 32 slots of tile `t0 / 32` (one degree class per tile).
+//   lead = {row or -1, count | chunks << 8 | first << 30, hub index, log2 G}, cols = <= 4 columns or -1.
+__device__ __forceinline__ void load_tile(const BfsParams &p, const int *s_ent_base, const int *s_slot_base, int t0,
+                                          int lane, int4 &lead, int4 &cols)
+{
+    int cls = 0;
+    while (t0 >= s_slot_base[cls + 1]) ++cls;  // regions are GP_SLOT_ALIGN aligned: warp-uniform
+    const int gsh = cls <= 1 ? 5 : 6 - cls;    // log2 of slots per row: 32,32,16,8,4,2,1
+    const int rel = t0 - s_slot_base[cls] + lane;
+    const int ent = s_ent_base[cls] + (rel >> gsh);
+    const int sub = rel & ((1 << gsh) - 1);
+    const bool active = ent < s_ent_base[cls + 1];
+    const int4 d = active ? __ldg(p.desc + ent) : make_int4(-1, 0, 0, -1);
+    lead = make_int4(active ? d.x : -1, d.z, d.w, gsh);
+    const int cnt = d.z & 0xFF;
+    int c[GP_SLOT_EDGES];
+#pragma unroll
+    for (int i = 0; i < GP_SLOT_EDGES; ++i) {
+        const int idx = sub + (i << gsh);  // consecutive slots read consecutive columns
+        c[i] = (active && idx < cnt) ? __ldg(p.col + d.y + idx) : -1;
+    }
+    cols = make_int4(c[0], c[1], c[2], c[3]);
+}
+
+// WB lane words per node row = one thread loads a whole row (8, 16 or 32 bytes).
 template <int WB, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
 {
-    constexpr int TPE = (WB == 4) ? 2 : 1;
-    constexpr int VW = WB / TPE;
-    constexpr int PPW = 32 / TPE;  // pair slots per warp iteration
+    constexpr int VW = WB;
     constexpr int WARPS = NT / 32;
-    constexpr u32 LEADER_MASK = (TPE == 2) ? 0x3u : 0x1u;
-
-    constexpr int PAIRS_CTA = NT / TPE;
-    // Work cache: a warp visits the same pair slots every level, so the descriptors and column
-    // indices of its first GP_BFS_CACHE_ITERS warp-iterations are loaded ONCE into shared memory
-    // (48 B per slot); a level then costs a single dependent round trip (gathers + seen together).
+    constexpr int JT = GP_BFS_CACHE_ITERS * WARPS;  // tiles of this CTA whose work items live in shared memory
+    static_assert(GP_SLOT_EDGES == 4, "slot layout is int4");
+    // Work cache: a CTA visits the same tiles every level, so the descriptors and column indices of
+    // its first JT tiles are loaded ONCE into shared memory; a level then costs a single dependent
+    // round trip (gathers + seen together).
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    int4 *s_desc = reinterpret_cast<int4 *>(s_dyn);                                        // [ITERS][PAIRS_CTA]
-    int *s_col = reinterpret_cast<int *>(s_desc + GP_BFS_CACHE_ITERS * PAIRS_CTA);        // [ITERS][8][PAIRS_CTA]
-    unsigned char *s_done = reinterpret_cast<unsigned char *>(s_col + GP_BFS_CACHE_ITERS * GP_SLOT_EDGES * PAIRS_CTA);
-                                                                                           // [DONE_B][ITERS][PAIRS_CTA]
+    int4 *s_lead = reinterpret_cast<int4 *>(s_dyn);                 // [JT][32]
+    int4 *s_cols = s_lead + JT * 32;                                // [JT][32]
+    unsigned char *s_done = reinterpret_cast<unsigned char *>(s_cols + JT * 32);  // [DONE_B][JT][32]
+    u32 *s_map = reinterpret_cast<u32 *>(s_done + GP_BFS_DONE_BATCHES * JT * 32);  // [batches][nzwords] or absent
     __shared__ u32 s_live32[GP_BFS_MAX_LANE_WORDS * 2];
     __shared__ int s_ent_base[GP_NUM_CLASSES + 1];
     __shared__ int s_slot_base[GP_NUM_CLASSES + 1];
-    __shared__ u32 s_bcast;
+    __shared__ u64 s_bcast;
+    __shared__ u64 s_lv[GP_BFS_MAX_LANE_WORDS];
     __shared__ int s_any;
+    __shared__ int s_notdone;
+    __shared__ int s_nzrows;
+    __shared__ int s_queue[GP_BFS_MAX_LANE_WORDS];  // one tile queue per batch
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int half = (TPE == 2) ? (lane & 1) : 0;
-    const int woff = half * VW;
-    const int pairlane = lane / TPE;
     const long long gthreads = (long long)gridDim.x * NT;
     const long long gtid = (long long)blockIdx.x * NT + tid;
     const int gwarp = blockIdx.x * WARPS + warp, total_warps = gridDim.x * WARPS;
     const int n = p.n, lw = p.batches * WB;
-    u32 bar_target[2] = {0, 0}, bar_prev_any[2] = {0, 0};
+    const bool use_map = p.map_smem_words > 0;
     u64 gathers = 0;
 
     for (int i = tid; i < GP_BFS_MAX_LANE_WORDS * 2; i += NT) s_live32[i] = 0;
@@ -224,7 +281,12 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
         s_ent_base[tid] = p.meta[GP_META_ENT_BASE + tid];
         s_slot_base[tid] = p.meta[GP_META_SLOT_BASE + tid];
     }
-    if (tid == 0) s_any = 0;
+    if (tid == 0) {
+        s_any = 0;
+        s_notdone = 0;
+        s_nzrows = 0;
+    }
+    if (tid < GP_BFS_MAX_LANE_WORDS) s_queue[tid] = 0;
 
     // ---- level 0: seed the anchors (duplicates simply set their own lane bits)
     for (long long j = gtid; j < p.num_anchors; j += gthreads) {
@@ -239,36 +301,24 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
         atomicOr(p.result + off, bit);
         atomicOr(p.seeds + off, bit);
         atomicOr(p.live + 1 * GP_BFS_MAX_LANE_WORDS + b * WB + w, bit);
+        if (use_map) atomicOr(p.nzmap + (size_t)b * p.nzwords + (size_t)(a >> 5), 1u << (a & 31));  // map of hop 0
     }
     __syncthreads();
-    const int total_slots = s_slot_base[GP_NUM_CLASSES];
-    const int pair_cta = tid / TPE;
-    for (int it = 0; it < GP_BFS_CACHE_ITERS; ++it) {
-        const int t0 = (gwarp + it * total_warps) * PPW;
-        if (t0 >= total_slots) break;
-        int cls = 0;
-        while (t0 >= s_slot_base[cls + 1]) ++cls;
-        const int gsh = cls <= 1 ? 4 : 5 - cls;
-        const int rel = t0 - s_slot_base[cls] + pairlane;
-        const int ent = s_ent_base[cls] + (rel >> gsh);
-        const int sub = rel & ((1 << gsh) - 1);
-        const bool active = ent < s_ent_base[cls + 1];
-        const int4 d = active ? __ldg(p.desc + ent) : make_int4(0, 0, 0, -1);
-        if (half == 0) {
-            s_desc[it * PAIRS_CTA + pair_cta] = make_int4(d.x, d.z, d.w, sub | (gsh << 8) | ((int)active << 16));
-            const int cnt = d.z & 0xFF;
-#pragma unroll
-            for (int i = 0; i < GP_SLOT_EDGES; ++i) {
-                const int idx = sub + (i << gsh);
-                // padding edges point back at the row itself (frontier[u] is a subset of seen[u])
-                s_col[(it * GP_SLOT_EDGES + i) * PAIRS_CTA + pair_cta] = idx < cnt ? __ldg(p.col + d.y + idx) : d.x;
-            }
-            for (int b = 0; b < GP_BFS_DONE_BATCHES; ++b) s_done[(b * GP_BFS_CACHE_ITERS + it) * PAIRS_CTA + pair_cta] = 0;
-        }
+    const int total_tiles = s_slot_base[GP_NUM_CLASSES] / 32;
+    // tile j of this CTA is global tile blockIdx.x + gridDim.x * j
+    const int tiles_cta = total_tiles > (int)blockIdx.x ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int cached_tiles = tiles_cta < JT ? tiles_cta : JT;
+    for (int j = warp; j < cached_tiles; j += WARPS) {
+        int4 lead, cols;
+        load_tile(p, s_ent_base, s_slot_base, ((int)blockIdx.x + (int)gridDim.x * j) * 32, lane, lead, cols);
+        s_lead[j * 32 + lane] = lead;
+        s_cols[j * 32 + lane] = cols;
+        for (int b = 0; b < GP_BFS_DONE_BATCHES; ++b) s_done[(b * JT + j) * 32 + lane] = lead.x < 0 ? 1 : 0;
     }
-    grid_barrier_any(p.bar + 0, bar_target[0], bar_prev_any[0], gridDim.x, false, &s_bcast, &s_any);
+    grid_barrier_flags(p.bar + 0, gridDim.x, false, false, &s_bcast, &s_any, &s_notdone, &s_nzrows, s_queue, p.batches);
 
     int level = 1, max_level = 0;
+    long long nz_prev = p.num_anchors;  // non-zero rows of the frontier about to be read (hop 0: the anchors)
     while (true) {
         LevelCtx<VW> c;
         // frontier of hop l lives in R[l] for l <= 15, then in the ping-pong pair
@@ -297,219 +347,189 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
         u64 *live_w = p.live + ((level + 1) % 3) * GP_BFS_MAX_LANE_WORDS;
         u64 *live_z = p.live + ((level + 2) % 3) * GP_BFS_MAX_LANE_WORDS;
         if (blockIdx.x == 0 && tid < lw) live_z[tid] = 0;
+        if (gtid == 0) p.bar[(level + 1) % 3] = 0;  // last used two levels ago; next used one level from now
+        // maps rotate like the barrier words: hop h lives in map h % 3.  A dense frontier (most rows
+        // non-zero) makes the map useless, so it is staged only when it can filter something.
+        const bool map_level = use_map && nz_prev * 2 < (long long)n * p.batches;
+        u32 *map_w = use_map ? p.nzmap + (size_t)(level % 3) * p.map_stride : nullptr;
+        if (use_map) {
+            uint4 *map_z = reinterpret_cast<uint4 *>(p.nzmap + (size_t)((level + 1) % 3) * p.map_stride);
+            const int quads = p.map_stride >> 2;  // padded to a multiple of 4 words
+            for (long long i = gtid; i < quads; i += gthreads) map_z[i] = make_uint4(0, 0, 0, 0);
+            if (map_level) {
+                const uint4 *map_r = reinterpret_cast<const uint4 *>(p.nzmap + (size_t)((level - 1) % 3) * p.map_stride);
+                uint4 *s_map4 = reinterpret_cast<uint4 *>(s_map);
+#pragma unroll 4
+                for (int i = tid; i < quads; i += NT) s_map4[i] = __ldcg(map_r + i);
+            }
+        }
+        if (tid < lw) s_lv[tid] = ld_relaxed_u64(live_r + tid);  // one L2 read per CTA instead of one per warp
+        __syncthreads();
         GP_TRACE(0);
 
+        u32 tr_tiles = 0, tr_fast = 0;
+        u64 tr_pack = 0;
+        const long long tr_t0 = p.trace != nullptr ? clock64() : 0;
+        auto tr_mark = [&](int k) {  // diagnostics: 16-bit cycle stamps of the first tiles of the level
+            if (p.trace != nullptr && k < 4) tr_pack |= (u64)min(65535ll, clock64() - tr_t0) << (16 * k);
+        };
+        int nzrows = 0;
         for (int b = 0; b < p.batches; ++b) {
             u64 lv[VW], live_acc[VW];
 #pragma unroll
             for (int i = 0; i < VW; ++i) {
-                lv[i] = live_r[b * WB + woff + i];
+                lv[i] = s_lv[b * WB + i];
                 live_acc[i] = 0;
             }
-            const u64 *cur_b = c.cur + (size_t)b * n * WB + woff;
+            const u64 *cur_b_rows = c.cur + (size_t)b * n * WB;
+            const u32 *s_map_b = s_map + (size_t)b * p.nzwords;
+            c.map_w = use_map ? map_w + (size_t)b * p.nzwords : nullptr;
+            // tile queue of this batch: every warp starts with tile `warp`, the rest are handed out on
+            // demand; the index of the NEXT tile is requested before the current one is processed
+            int j_next = 0;
+            for (int j = warp; j < tiles_cta; j = __shfl_sync(FULL_MASK, j_next, 0)) {
+                if (lane == 0) j_next = atomicAdd(&s_queue[b], 1) + WARPS;
+                if (tr_tiles == 0) tr_mark(0);
 
-            // ---- cached warp-iterations: descriptors / columns from shared memory, one round trip
-            int it = 0;
-            const int cached_iters = b < GP_BFS_DONE_BATCHES ? GP_BFS_CACHE_ITERS : 0;  // untracked batches stream
-            for (; it < cached_iters; ++it) {
-                const int tc = (gwarp + it * total_warps) * PPW;
-                if (tc >= total_slots) break;
-                const int4 cd = s_desc[it * PAIRS_CTA + pair_cta];
-                const int sub = cd.w & 0xFF, gsh = (cd.w >> 8) & 0xFF;
-                const bool active = (cd.w >> 16) & 1;
-                const int nch = (cd.y >> 8) & 0x3FFFFF;
-                const bool first_chunk = (cd.y >> 30) & 1;
-                const bool track = b < GP_BFS_DONE_BATCHES;
-                unsigned char *dflag = s_done + (b * GP_BFS_CACHE_ITERS + it) * PAIRS_CTA;
-                // a row is "done" once every still-live lane has reached it: it never needs gathering again
-                const bool done = track && dflag[pair_cta - sub] != 0;
-                const bool work = active && !done;
-                const size_t off = ((size_t)b * n + (size_t)cd.x) * WB + woff;
-                u64 seenv[VW], acc[VW];
-#pragma unroll
-                for (int i = 0; i < VW; ++i) {
-                    seenv[i] = ~0ull;
-                    acc[i] = 0;
-                }
-                if (work) {
-                    int v[GP_SLOT_EDGES];
-#pragma unroll
-                    for (int i = 0; i < GP_SLOT_EDGES; ++i) v[i] = s_col[(it * GP_SLOT_EDGES + i) * PAIRS_CTA + pair_cta];
-                    u64 t[GP_SLOT_EDGES][VW];
-#pragma unroll
-                    for (int i = 0; i < GP_SLOT_EDGES; ++i) vload<VW>(cur_b + (size_t)(u32)v[i] * WB, t[i]);
-                    if (sub == 0) vload<VW>(p.result + off, seenv);  // only the finalising lanes need it
-#pragma unroll
-                    for (int i = 0; i < GP_SLOT_EDGES; ++i)
-#pragma unroll
-                        for (int q = 0; q < VW; ++q) acc[q] |= t[i][q];
-                    gathers += (u64)VW * GP_SLOT_EDGES;
-                }
-                for (int m = TPE; m < (TPE << gsh); m <<= 1)
-#pragma unroll
-                    for (int q = 0; q < VW; ++q) acc[q] |= shfl_xor_u64(acc[q], m);
-
-                const bool leader = active && sub == 0;
-                const u32 leader_mask = __ballot_sync(FULL_MASK, leader);
-                if (leader) {
-                    bool need = false;
-#pragma unroll
-                    for (int i = 0; i < VW; ++i) need |= work && (~seenv[i] & lv[i]) != 0;
-                    bool need_row = need;
-                    if constexpr (TPE == 2) need_row |= __shfl_xor_sync(leader_mask, (int)need, 1) != 0;
-                    if (!need_row) {
-                        // nothing left to reach here (monotone: seen grows, live shrinks): remember it
-                        if (track && half == 0) dflag[pair_cta] = 1;
-                        if (nch == 0 || first_chunk) {
-#pragma unroll
-                            for (int i = 0; i < VW; ++i) acc[i] = 0;
-                            finalize_row<VW>(c, off, acc, seenv, live_acc);
-                        }
-                    } else if (nch == 0) {
-                        finalize_row<VW>(c, off, acc, seenv, live_acc);
-                    } else {
-                        const size_t hidx = (size_t)b * p.hub_capacity + (size_t)cd.z;
-                        u64 *accp = p.hub_acc + hidx * WB + woff;
-                        u64 dep = 0;
-#pragma unroll
-                        for (int q = 0; q < VW; ++q)
-                            if (acc[q]) dep |= atomicOr(accp + q, acc[q]);
-                        u32 old = 0;
-                        if constexpr (TPE == 2) {
-                            dep |= __shfl_xor_sync(leader_mask, (u32)dep | (u32)(dep >> 32), 1);
-                            asm volatile("" ::"l"(dep) : "memory");  // the ORs have returned from L2 before we count
-                            if (half == 0) old = atomicAdd(p.hub_cnt + hidx, 1u);
-                            old = __shfl_sync(leader_mask, old, lane & ~1);
-                        } else {
-                            asm volatile("" ::"l"(dep) : "memory");
-                            old = atomicAdd(p.hub_cnt + hidx, 1u);
-                        }
-                        if (old == (u32)nch - 1u) {
-                            u64 comb[VW];
-#pragma unroll
-                            for (int q = 0; q < VW; ++q) comb[q] = atomicExch(accp + q, 0ull);
-                            if (half == 0) p.hub_cnt[hidx] = 0;
-                            finalize_row<VW>(c, off, comb, seenv, live_acc);
-                        }
-                    }
-                }
+            int4 lead, cols;
+            unsigned char *dflag = nullptr;
+            if (j < JT) {
+                lead = s_lead[j * 32 + lane];
+                cols = s_cols[j * 32 + lane];
+                if (b < GP_BFS_DONE_BATCHES) dflag = s_done + (b * JT + j) * 32;
+            } else {
+                load_tile(p, s_ent_base, s_slot_base, ((int)blockIdx.x + (int)gridDim.x * j) * 32, lane, lead, cols);
             }
-
-            // ---- remaining warp-iterations (large graphs): streamed from global memory.
-            // software pipeline: the descriptor of the next warp-iteration is fetched one iteration ahead
-            int t0 = (gwarp + it * total_warps) * PPW;
-            int cls = 0;
-            int4 d_next = make_int4(0, 0, 0, -1);
-            bool act_next = false;
-            int sub_next = 0, gsh_next = 0;
-            auto fetch = [&](int t) {
-                while (t >= s_slot_base[cls + 1]) ++cls;  // regions are GP_SLOT_ALIGN aligned: warp-uniform
-                gsh_next = cls <= 1 ? 4 : 5 - cls;        // log2 of slots per row: 16,16,8,4,2,1
-                const int rel = t - s_slot_base[cls] + pairlane;
-                const int ent = s_ent_base[cls] + (rel >> gsh_next);
-                sub_next = rel & ((1 << gsh_next) - 1);
-                act_next = ent < s_ent_base[cls + 1];
-                d_next = act_next ? __ldg(p.desc + ent) : make_int4(0, 0, 0, -1);
-            };
-            if (t0 < total_slots) fetch(t0);
-            while (t0 < total_slots) {
-                const int4 d = d_next;
-                const bool active = act_next;
-                const int sub = sub_next, gsh = gsh_next;
-                const int cnt = d.z & 0xFF, nch = (d.z >> 8) & 0x3FFFFF;
-                const bool first_chunk = (d.z >> 30) & 1;
-                const size_t off = ((size_t)b * n + (size_t)d.x) * WB + woff;
-                // phase 1: this slot's column indices (sub, sub + G, ...: consecutive slots read consecutive
-                // columns) and the row's seen words, all independent
-                int v[GP_SLOT_EDGES];
+            const int gsh = lead.w;
+            const int sub = lane & ((1 << gsh) - 1);
+            const bool leader = sub == 0 && lead.x >= 0;
+            const int nch = (lead.y >> 8) & 0x3FFFFF;
+            const bool writes_empty = nch == 0 || ((lead.y >> 30) & 1);  // chunked rows: the first chunk writes the empty frontier
+            const size_t off = ((size_t)b * n + (size_t)(lead.x >= 0 ? lead.x : 0)) * WB;
+            // a row is "done" once every still-live lane has reached it: it never needs gathering again
+            const bool done = dflag != nullptr ? dflag[lane - sub] != 0 : lead.x < 0;
+            u64 seenv[VW], acc[VW];
+#pragma unroll
+            for (int i = 0; i < VW; ++i) {
+                seenv[i] = ~0ull;
+                acc[i] = 0;
+            }
+            ++tr_tiles;
+            if (__all_sync(FULL_MASK, done)) {
+                ++tr_fast;
+                if (tr_tiles == 1) tr_mark(1);
+                // whole tile finished: only the empty next-frontier rows have to be written
+                if (leader && writes_empty) finalize_row<VW>(c, off, lead.x, acc, seenv, live_acc, lv, nzrows);
+                if (tr_tiles == 1) tr_mark(2);
+                if (tr_tiles == 2) tr_mark(3);
+                continue;
+            }
+            const int v[GP_SLOT_EDGES] = {cols.x, cols.y, cols.z, cols.w};
+            u32 needbits = 0;
+            if (!done) {
 #pragma unroll
                 for (int i = 0; i < GP_SLOT_EDGES; ++i) {
-                    // padding edges point back at the row itself: frontier[u] is a subset of seen[u],
-                    // so it contributes nothing to acc & ~seen and the gathers below need no predicates
-                    const int idx = sub + (i << gsh);
-                    v[i] = idx < cnt ? __ldg(p.col + d.y + idx) : d.x;
-                }
-                u64 seenv[VW], acc[VW];
-#pragma unroll
-                for (int i = 0; i < VW; ++i) {
-                    seenv[i] = ~0ull;
-                    acc[i] = 0;
-                }
-                if (active) vload<VW>(p.result + off, seenv);
-                t0 += total_warps * PPW;
-                if (t0 < total_slots) fetch(t0);
-                bool need = false;
-#pragma unroll
-                for (int i = 0; i < VW; ++i) need |= (~seenv[i] & lv[i]) != 0;
-                // row-level verdict (both halves of the pair agree on it; used by the hub protocol)
-                bool need_row = need;
-                if constexpr (TPE == 2) need_row |= __shfl_xor_sync(FULL_MASK, (int)need, 1) != 0;
-                // phase 2: all neighbour rows of the slot in flight at once
-                if (need) {
-                    u64 t[GP_SLOT_EDGES][VW];
-#pragma unroll
-                    for (int i = 0; i < GP_SLOT_EDGES; ++i) vload<VW>(cur_b + (size_t)(u32)v[i] * WB, t[i]);
-#pragma unroll
-                    for (int i = 0; i < GP_SLOT_EDGES; ++i)
-#pragma unroll
-                        for (int q = 0; q < VW; ++q) acc[q] |= t[i][q];
-                    gathers += (u64)VW * (u64)max(0, min(GP_SLOT_EDGES, (cnt - sub + (1 << gsh) - 1) >> gsh));
-                }
-                // OR over the G slots of the row (warp-uniform trip count)
-                for (int m = TPE; m < (TPE << gsh); m <<= 1)
-#pragma unroll
-                    for (int q = 0; q < VW; ++q) acc[q] |= shfl_xor_u64(acc[q], m);
-
-                if (active && sub == 0) {
-                    if (nch == 0) {
-                        finalize_row<VW>(c, off, acc, seenv, live_acc);
-                    } else if (!need_row) {
-                        // hub row with nothing left to reach (every chunk sees the same seen / live
-                        // words, so all agree): its first chunk alone writes the empty frontier
-                        if (first_chunk) finalize_row<VW>(c, off, acc, seenv, live_acc);
-                    } else {
-                        // hub chunk: deposit the partial OR; the last chunk to arrive finalises the row.
-                        // All traffic on hub_acc / hub_cnt is L2 atomics; waiting for the OR's return
-                        // value orders it before the arrival count without a fence.
-                        const size_t hidx = (size_t)b * p.hub_capacity + (size_t)d.w;
-                        u64 *accp = p.hub_acc + hidx * WB + woff;
-                        u64 dep = 0;
-#pragma unroll
-                        for (int q = 0; q < VW; ++q)
-                            if (acc[q]) dep |= atomicOr(accp + q, acc[q]);
-                        u32 old = 0;
-                        if constexpr (TPE == 2) {
-                            dep |= __shfl_xor_sync(LEADER_MASK, (u32)dep | (u32)(dep >> 32), 1);  // other half's returns
-                            asm volatile("" ::"l"(dep) : "memory");  // the ORs have returned from L2 before we count
-                            if (half == 0) old = atomicAdd(p.hub_cnt + hidx, 1u);
-                            old = __shfl_sync(LEADER_MASK, old, 0);
-                        } else {
-                            asm volatile("" ::"l"(dep) : "memory");
-                            old = atomicAdd(p.hub_cnt + hidx, 1u);
-                        }
-                        if (old == (u32)nch - 1u) {
-                            u64 comb[VW];
-#pragma unroll
-                            for (int q = 0; q < VW; ++q) comb[q] = atomicExch(accp + q, 0ull);
-                            if (half == 0) p.hub_cnt[hidx] = 0;
-                            finalize_row<VW>(c, off, comb, seenv, live_acc);
-                        }
-                    }
+                    // gather only neighbours whose frontier row is non-zero at this hop
+                    const bool nz = v[i] >= 0 && (!map_level || ((s_map_b[v[i] >> 5] >> (v[i] & 31)) & 1u));
+                    needbits |= (u32)nz << i;
                 }
             }
-
+            const u32 bal = __ballot_sync(FULL_MASK, needbits != 0);
+            const u32 gmask = gsh == 5 ? FULL_MASK : (((1u << (1 << gsh)) - 1u) << (lane - sub));
+            const bool group_need = (bal & gmask) != 0;
+            u64 t[GP_SLOT_EDGES][VW];
+#pragma unroll
+            for (int i = 0; i < GP_SLOT_EDGES; ++i) {
+#pragma unroll
+                for (int q = 0; q < VW; ++q) t[i][q] = 0;
+                if ((needbits >> i) & 1u) vload<VW>(cur_b_rows + (size_t)(u32)v[i] * WB, t[i]);
+            }
+            // the finalising lane needs the reached mask; chunks of a hub row always take part in the
+            // arrival protocol (every chunk reads the same mask before the last one updates it)
+            const bool eval = leader && !done && (group_need || nch > 0);
+            if (eval) vload<VW>(p.result + off, seenv);
+#pragma unroll
+            for (int i = 0; i < GP_SLOT_EDGES; ++i)
+#pragma unroll
+                for (int q = 0; q < VW; ++q) acc[q] |= t[i][q];
+            gathers += (u64)VW * (u64)__popc(needbits);
+            if (bal != 0) {
+                if (gsh == 5) {
+#pragma unroll
+                    for (int q = 0; q < VW; ++q) acc[q] = warp_or_u64(acc[q]);
+                } else {
+                    for (int m = 1; m < (1 << gsh); m <<= 1)
+#pragma unroll
+                        for (int q = 0; q < VW; ++q) acc[q] |= shfl_xor_u64(acc[q], m);
+                }
+            }
+            if (!leader) continue;
+            if (!eval) {
+                // done, or not done but no neighbour has anything new: the row's next frontier is empty
+                if (!done) s_notdone = 1;  // flags are set as soon as a row completes, so this row still lacks lanes
+                if (writes_empty) {
+#pragma unroll
+                    for (int i = 0; i < VW; ++i) acc[i] = 0;
+                    finalize_row<VW>(c, off, lead.x, acc, seenv, live_acc, lv, nzrows);
+                }
+                continue;
+            }
+            bool need_row = false;
+#pragma unroll
+            for (int i = 0; i < VW; ++i) need_row |= (~seenv[i] & lv[i]) != 0;
+            if (!need_row) {
+                // nothing left to reach here (monotone: seen grows, live shrinks): remember it
+                if (dflag != nullptr) dflag[lane] = 1;
+                else s_notdone = 1;  // untracked rows cannot prove the end of the search
+                if (writes_empty) {
+#pragma unroll
+                    for (int i = 0; i < VW; ++i) acc[i] = 0;
+                    finalize_row<VW>(c, off, lead.x, acc, seenv, live_acc, lv, nzrows);
+                }
+            } else if (nch == 0) {
+                if (finalize_row<VW>(c, off, lead.x, acc, seenv, live_acc, lv, nzrows) || dflag == nullptr) s_notdone = 1;
+                else dflag[lane] = 1;
+            } else {
+                // hub chunk: deposit the partial OR; the last chunk to arrive finalises the row.  All
+                // traffic on hub_acc / hub_cnt is L2 atomics; waiting for the OR's return value orders
+                // it before the arrival count without a fence.
+                const size_t hidx = (size_t)b * p.hub_capacity + (size_t)lead.z;
+                u64 *accp = p.hub_acc + hidx * WB;
+                u64 dep = 0;
+#pragma unroll
+                for (int q = 0; q < VW; ++q)
+                    if (acc[q]) dep |= atomicOr(accp + q, acc[q]);
+                asm volatile("" ::"l"(dep) : "memory");  // the ORs have returned from L2 before we count
+                const u32 old = atomicAdd(p.hub_cnt + hidx, 1u);
+                if (old == (u32)nch - 1u) {
+                    u64 comb[VW];
+#pragma unroll
+                    for (int q = 0; q < VW; ++q) comb[q] = atomicExch(accp + q, 0ull);
+                    p.hub_cnt[hidx] = 0;
+                    if (finalize_row<VW>(c, off, lead.x, comb, seenv, live_acc, lv, nzrows) || dflag == nullptr) s_notdone = 1;
+                    else dflag[lane] = 1;
+                } else {
+                    s_notdone = 1;  // only the finalising chunk sees the updated mask
+                }
+            }
+            }
             // ---- fold this batch's newly reached lanes into the CTA's live words
 #pragma unroll
             for (int i = 0; i < VW; ++i) {
-                u64 x = live_acc[i];
-#pragma unroll
-                for (int m = TPE; m < 32; m <<= 1) x |= shfl_xor_u64(x, m);
-                if (lane < TPE && x) {
-                    atomicOr(&s_live32[(b * WB + woff + i) * 2], (u32)x);
-                    atomicOr(&s_live32[(b * WB + woff + i) * 2 + 1], (u32)(x >> 32));
+                const u64 x = warp_or_u64(live_acc[i]);
+                if (lane == 0 && x) {
+                    atomicOr(&s_live32[(b * WB + i) * 2], (u32)x);
+                    atomicOr(&s_live32[(b * WB + i) * 2 + 1], (u32)(x >> 32));
                     s_any = 1;
                 }
             }
+        }
+        nzrows = __reduce_add_sync(FULL_MASK, nzrows);
+        if (lane == 0 && nzrows) atomicAdd(&s_nzrows, nzrows);
+        if (p.trace != nullptr && lane == 0 && level <= 32)
+        {
+            p.trace[(((size_t)(level - 1) * total_warps + gwarp) << 2) + 2] = ((u64)tr_fast << 32) | tr_tiles;
+            p.trace[(((size_t)(level - 1) * total_warps + gwarp) << 2) + 1] = tr_pack;
         }
         GP_TRACE(3);
         __syncthreads();
@@ -519,17 +539,18 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
             s_live32[tid * 2] = 0;
             s_live32[tid * 2 + 1] = 0;
         }
-        const bool cta_any = s_any != 0;
-        const int par = level & 1;
-        const bool any = grid_barrier_any(p.bar + par, bar_target[par], bar_prev_any[par], gridDim.x, cta_any,
-                                          &s_bcast, &s_any);
-        if (!any) break;
+        const bool cta_any = s_any != 0, cta_notdone = s_notdone != 0;
+        const u64 fl = grid_barrier_flags(p.bar + level % 3, gridDim.x, cta_any, cta_notdone, &s_bcast, &s_any,
+                                          &s_notdone, &s_nzrows, s_queue, p.batches);
+        nz_prev = bar_nzrows(fl);
+        if (!bar_any(fl)) break;  // no lane reached a new row: the frontier just written is empty
         if (level >= (int)GP_UNREACHABLE_U16) {
             // a lane was first reached at hop 65535: not representable next to the 0xFFFF sentinel
             if (gtid == 0) atomicOr(&p.status[GP_BFS_ST_ERROR], GP_DEV_ERR_LEVEL_OVERFLOW);
             break;
         }
         max_level = level;
+        if (!bar_notdone(fl)) break;  // every row already holds all live lanes: the next level cannot find anything
         ++level;
     }
 
@@ -546,34 +567,53 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
 template <int WB, int NT>
 constexpr size_t bfs_cache_bytes()
 {
-    constexpr int pairs = NT / ((WB == 4) ? 2 : 1);
-    return (size_t)GP_BFS_CACHE_ITERS * pairs * (sizeof(int4) + GP_SLOT_EDGES * sizeof(int)) +
-           (size_t)GP_BFS_DONE_BATCHES * GP_BFS_CACHE_ITERS * pairs;
+    constexpr int tiles = GP_BFS_CACHE_ITERS * (NT / 32);
+    return (size_t)tiles * 32 * (2 * sizeof(int4) + GP_BFS_DONE_BATCHES);
 }
 
 template <int WB, int NT, int MINB>
 int launch_bfs_cfg(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int cfg_id)
 {
-    if (h->grid_blocks == 0 || h->grid_cfg != cfg_id * 8 + WB) {
-        int occ = 0;
-        GP_CUDA_CHECK(cudaFuncSetAttribute(msbfs_kernel<WB, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)bfs_cache_bytes<WB, NT>()));
+    // Frontier bitmaps are staged in shared memory when they fit without costing a resident CTA.
+    const int want_map = (int)((size_t)p.map_stride * sizeof(u32));
+    const int key = (cfg_id * 8 + WB) * 4 + 1;
+    if (h->grid_blocks == 0 || h->grid_cfg != key || h->map_want_bytes != want_map) {
+        int occ = 0, occ_map = 0;
+        cudaFuncAttributes fa;
+        GP_CUDA_CHECK(cudaFuncGetAttributes(&fa, msbfs_kernel<WB, NT, MINB>));
+        int smem_optin = 0, dev = 0;
+        GP_CUDA_CHECK(cudaGetDevice(&dev));
+        GP_CUDA_CHECK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        const int dyn_room = smem_optin - (int)fa.sharedSizeBytes;
+        const int cache_bytes = (int)bfs_cache_bytes<WB, NT>();
+        int dyn_max = cache_bytes + GP_BFS_MAP_SMEM_MAX;
+        if (dyn_max > dyn_room) dyn_max = dyn_room;
+        GP_REQUIRE(dyn_max >= cache_bytes, GP_ERR_CUDA, "msbfs work cache does not fit in shared memory");
+        GP_CUDA_CHECK(cudaFuncSetAttribute(msbfs_kernel<WB, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
         GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, msbfs_kernel<WB, NT, MINB>, NT,
                                                                     bfs_cache_bytes<WB, NT>()));
         GP_REQUIRE(occ >= 1, GP_ERR_CUDA, "msbfs kernel does not fit on an SM");
         if (occ > MINB) occ = MINB;
+        h->map_smem_bytes = 0;
+        if (cache_bytes + want_map <= dyn_max && getenv("GP_BFS_NO_MAP") == nullptr) {
+            GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_map, msbfs_kernel<WB, NT, MINB>, NT,
+                                                                        bfs_cache_bytes<WB, NT>() + want_map));
+            if (occ_map >= occ) h->map_smem_bytes = want_map;
+        }
         h->grid_blocks = occ * gp_sm_count();
-        h->grid_cfg = cfg_id * 8 + WB;
+        h->grid_cfg = key;
+        h->map_want_bytes = want_map;
         h->block_threads = NT;
     }
     BfsParams pp = p;
+    pp.map_smem_words = h->map_smem_bytes > 0 ? p.map_stride : 0;
     void *args[] = {&pp};
     gp_count_launch();
     // inside a graph capture the timing events become event-record nodes (re-recorded on every replay)
     const unsigned ev_flags = gp_is_capturing() ? cudaEventRecordExternal : cudaEventRecordDefault;
     GP_CUDA_CHECK(cudaEventRecordWithFlags(h->ev_start, stream, ev_flags));
     GP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)msbfs_kernel<WB, NT, MINB>, dim3(h->grid_blocks),
-                                              dim3(NT), args, bfs_cache_bytes<WB, NT>(), stream));
+                                              dim3(NT), args, bfs_cache_bytes<WB, NT>() + h->map_smem_bytes, stream));
     GP_CUDA_CHECK(cudaEventRecordWithFlags(h->ev_stop, stream, ev_flags));
     return GP_OK;
 }
@@ -590,11 +630,11 @@ int launch_bfs(gp_msbfs *h, const BfsParams &p, cudaStream_t stream)
         if (cfg < 0 || cfg > 4) cfg = GP_BFS_DEFAULT_CFG;
     }
     switch (cfg) {
-        case 0: return launch_bfs_cfg<WB, 512, 2>(h, p, stream, 0);   // 64 regs, 32 warps/SM
+        case 0: return launch_bfs_cfg<WB, 768, 1>(h, p, stream, 0);   // 85 regs, 24 warps/SM, one tile queue per SM
         case 1: return launch_bfs_cfg<WB, 384, 2>(h, p, stream, 1);   // 85 regs, 24 warps/SM
         case 2: return launch_bfs_cfg<WB, 512, 1>(h, p, stream, 2);   // 128 regs, 16 warps/SM
-        case 3: return launch_bfs_cfg<WB, 1024, 1>(h, p, stream, 3);  // 64 regs, 32 warps/SM, half the CTAs
-        default: return launch_bfs_cfg<WB, 256, 3>(h, p, stream, 4);  // 85 regs, 24 warps/SM
+        case 3: return launch_bfs_cfg<WB, 1024, 1>(h, p, stream, 3);  // 64 regs, 32 warps/SM
+        default: return launch_bfs_cfg<WB, 512, 2>(h, p, stream, 4);  // 64 regs, 32 warps/SM, two queues
     }
 }
 
@@ -642,6 +682,8 @@ extern "C" int gp_msbfs_create(const gp_csr_t *csr, int64_t max_anchors, gp_msbf
     alloc((void **)&h->hub_acc, (size_t)h->hub_capacity * (size_t)h->cap_words_per_node * sizeof(u64));
     alloc((void **)&h->hub_cnt, (size_t)h->hub_capacity * (size_t)h->cap_words_per_node * sizeof(u32));
     alloc((void **)&h->bar, 8 * sizeof(u64));
+    h->nzwords = (h->num_nodes + 31) / 32;
+    alloc((void **)&h->nzmap, 3 * ((size_t)batches * (size_t)h->nzwords + 4) * sizeof(u32));
     alloc((void **)&h->status, GP_BFS_ST_WORDS * sizeof(int));
     alloc((void **)&h->counters, 4 * sizeof(u64));
     if (getenv("GP_BFS_TRACE")) alloc((void **)&h->trace, GP_BFS_TRACE_WORDS * sizeof(u64));
@@ -667,6 +709,7 @@ extern "C" int gp_msbfs_free(gp_msbfs_t *h)
     cudaFree(h->hub_acc);
     cudaFree(h->hub_cnt);
     cudaFree(h->bar);
+    cudaFree(h->nzmap);
     cudaFree(h->packed);
     cudaFree(h->deep_flag);
     cudaFree(h->status);
@@ -708,6 +751,7 @@ extern "C" int gp_msbfs_run(gp_msbfs_t *h, const int64_t *d_anchors, int64_t num
     GP_CUDA_CHECK(cudaMemsetAsync(h->seeds, 0, words * sizeof(u64), stream));
     GP_CUDA_CHECK(cudaMemsetAsync(h->live, 0, 3 * GP_BFS_MAX_LANE_WORDS * sizeof(u64), stream));
     GP_CUDA_CHECK(cudaMemsetAsync(h->bar, 0, 8 * sizeof(u64), stream));
+    GP_CUDA_CHECK(cudaMemsetAsync(h->nzmap, 0, 3 * (((size_t)batches * (size_t)h->nzwords + 3) / 4 * 4) * sizeof(u32), stream));
     if (!h->hub_zeroed) {
         // the kernel leaves these zeroed again (the finalising chunk resets its row's words)
         GP_CUDA_CHECK(cudaMemsetAsync(h->hub_acc, 0, (size_t)h->hub_capacity * h->cap_words_per_node * sizeof(u64), stream));
@@ -723,6 +767,10 @@ extern "C" int gp_msbfs_run(gp_msbfs_t *h, const int64_t *d_anchors, int64_t num
     p.hub_acc = h->hub_acc;
     p.hub_cnt = h->hub_cnt;
     p.bar = h->bar;
+    p.nzmap = h->nzmap;
+    p.nzwords = (int)h->nzwords;
+    p.map_stride = (int)(((int64_t)batches * h->nzwords + 3) / 4 * 4);
+    p.map_smem_words = 0;  // decided per launch configuration (launch_bfs_cfg)
     p.col = h->csr->col_out;
     p.meta = h->csr->meta;
     p.anchors = (const long long *)d_anchors;

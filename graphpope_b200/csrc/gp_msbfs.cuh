@@ -8,10 +8,11 @@ constexpr int GP_BFS_MAX_LANE_WORDS = 256;  // B * WB cap (K <= 16384 per GPU)
 constexpr int GP_BFS_PLANES = 16;           // deep-hop distance bit planes (uint16 range)
 constexpr int GP_BFS_LEVEL_ARRAYS = 15;     // hops 1..15 are recorded as write-once frontier arrays
 constexpr int GP_BFS_CACHE_ITERS = 4;      // warp-iterations whose work items are cached in shared memory
+constexpr int GP_BFS_MAP_SMEM_MAX = 64 * 1024;  // largest set of frontier bitmaps staged in shared memory
 constexpr int GP_BFS_DONE_BATCHES = 8;     // batches that keep per-row "done" flags for cached items
 constexpr int GP_MAX_RANKS = 8;             // GPUs of one NVSwitch node
 constexpr int GP_BFS_RESULT_ARRAYS = 1 + GP_BFS_LEVEL_ARRAYS + GP_BFS_PLANES;  // 32
-constexpr long long GP_BFS_TRACE_WORDS = 32ll * 160 * 4 * 32 * 4;  // levels * max warps * 4 slots           // distance bit planes (uint16 range)
+constexpr long long GP_BFS_TRACE_WORDS = 32ll * 160 * 4 * 32 * 4;  // levels * max warps * 4 slots
 
 enum : int {
     GP_BFS_ST_MAX_LEVEL = 0,
@@ -41,6 +42,10 @@ struct gp_msbfs {
     u64 *hub_acc = nullptr;  // [batches][hub_capacity][wb] partial ORs of hub rows (zero between levels)
     u32 *hub_cnt = nullptr;  // [batches][hub_capacity] hub chunks arrived (zero between levels)
     u64 *bar = nullptr;      // grid barrier words
+    u32 *nzmap = nullptr;    // [3][lane-word batches][ceil(N/32)] non-zero-row bitmaps of the last three frontiers
+    int64_t nzwords = 0;     // ceil(N / 32)
+    int map_smem_bytes = 0;  // shared memory the launch reserves for the maps (0: maps off for this size)
+    int map_want_bytes = -1; // map size the cached launch configuration was computed for
     int64_t hub_capacity = 0;
     bool hub_zeroed = false;
     u64 *packed = nullptr;   // [2 slots][GP_PACKED_ARRAYS][cap words] exchange buffers (allocated on first pack)
