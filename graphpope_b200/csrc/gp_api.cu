@@ -289,6 +289,8 @@ extern "C" int gp_geodesic_run(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_
         if (ent->exec == nullptr) ent->seen = 1 << 20;  // do not retry
     }
     if (ent->exec != nullptr) {
+        csr->in_built = false;  // the replay rebuilds the out-edge CSR from the (possibly changed) edge buffer
+        csr->num_input_edges = num_edges;
         gp_count_launches(ent->kernels);  // kernels inside the graph
         GP_CUDA_CHECK(cudaGraphLaunch(ent->exec, stream));
         return GP_OK;

@@ -2,203 +2,662 @@
 // also :27,33,39,45,51,57).  DiGraph semantics: nodes 0..N-1, parallel edges collapse,
 // self-loops stay, no symmetrisation unless GP_CSR_SYMMETRIZE.
 //
-//   edge_index int64 [2,E] --pack--> (src << nb | dst) keys --onesweep radix sort-->
-//   --fused unique--> sorted distinct keys --unpack--> col_out + rowptr_out (lower bounds)
-//   --degree keys + 2-pass sort--> degree-ordered row list with class boundaries.
-// The in-edge CSR (push direction, PageRank pull) is a stable re-sort of the distinct
-// keys by dst only, built on demand.  Everything is stream-ordered; counts stay on device.
+// The build is a counting sort by source row followed by a small sort inside every row:
+//   count   cnt[src]++ for every column of edge_index                       (L2 reductions)
+//   scan    raw_ptr = exclusive prefix of cnt (single-pass chained scan)    cursor = raw_ptr
+//   scatter raw_col[atomicAdd(&cursor[src], 1)] = dst                       (arbitrary order inside a row)
+//   rowsort every row segment sorted ascending and de-duplicated in place; rows of <= 32 edges in
+//           registers by one warp (a sorting network over shuffles), longer rows by one CTA in
+//           shared memory (a node bitmap for long rows, a sorting network otherwise) or in place in
+//           global memory; deg[r] = distinct count
+//   scan    nine prefix sums over the rows in ONE chained scan: edges (-> E'), work-list entries of
+//           each of the seven degree classes (-> position of the row in the MS-BFS work list), hub
+//           rows (-> index of the row's accumulator)
+//   desc    the row's work-list descriptor(s)
+// The CSR stays "gapped": row r is col[row_start[r] .. row_start[r] + deg[r]) and the slack left by
+// dropped duplicates is never squeezed out (gp_csr_export compacts on request), so no column is
+// moved twice.  The result is deterministic (rows ascending and unique, work list in ascending node
+// order per class) although the scatter is not.  Seven launches over E + N ints replace the seven
+// radix passes over 8-byte keys of the first version.  Everything is stream-ordered and
+// graph-capturable; counts stay on the device.
+//
+// The in-edge CSR (PageRank pull, in-degrees) is the same pipeline run on the transposed edges of
+// the finished CSR, built on demand.
 #include "gp_internal.h"
 
 #include <new>
 
 namespace {
 
-__global__ void pack_keys_kernel(const long long *__restrict__ ei, long long e, long long n, int nb,
-                                 int symmetrize, u64 *__restrict__ keys, int *meta)
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_IPT = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_IPT;  // elements per tile
+constexpr int ROW_CH = 9;                           // channels of the row scan (see RowScanIo)
+constexpr int BIG_THREADS = 256;
+constexpr int BIG_SMEM_ELEMS = 8192;                // longest row sorted in shared memory
+
+int launch_blocks(int64_t work, int threads)
+{
+    int64_t b = gp_ceil_div(work > 0 ? work : 1, threads);
+    const int64_t cap = (int64_t)gp_sm_count() * 32;  // latency-bound (atomics, dependent loads): a thread per item
+    return (int)(b < cap ? b : cap);
+}
+
+// Grid for warp-per-row kernels.  They are chains of dependent loads per row, so every row gets its
+// own warp while that still fits a few waves of resident CTAs.
+int row_blocks(int64_t rows)
+{
+    int64_t b = gp_ceil_div(rows > 0 ? rows : 1, 8);  // 8 warps per 256-thread CTA
+    const int64_t cap = (int64_t)gp_sm_count() * 64;
+    return (int)(b < cap ? b : cap);
+}
+
+// ---------------------------------------------------------------- count / scatter
+__global__ void count_edges_kernel(const long long *__restrict__ ei, long long e, long long n, int symmetrize,
+                                   int *__restrict__ cnt, int *meta)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
     bool bad = false;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += stride) {
-        long long s = ei[i], d = ei[e + i];
+        const long long s = ei[i], d = ei[e + i];
         if (s < 0 || d < 0 || s >= n || d >= n) {
             bad = true;
-            s = 0;
-            d = 0;
+            continue;
         }
-        keys[i] = ((u64)s << nb) | (u64)d;
-        if (symmetrize) keys[e + i] = ((u64)d << nb) | (u64)s;
+        atomicAdd(cnt + s, 1);
+        if (symmetrize) atomicAdd(cnt + d, 1);
     }
     if (__any_sync(FULL_MASK, bad) && lane_id() == 0) atomicOr(&meta[GP_META_ERROR], GP_DEV_ERR_EDGE_RANGE);
 }
 
-__device__ __forceinline__ u32 lower_bound_u64(const u64 *__restrict__ a, u32 n, u64 key)
-{
-    u32 lo = 0, hi = n;
-    while (lo < hi) {
-        const u32 mid = (lo + hi) >> 1;
-        if (__ldg(a + mid) < key) lo = mid + 1;
-        else hi = mid;
-    }
-    return lo;
-}
-
-// col[i] = low half of key i; rowptr[r] = first key whose high half is >= r.
-__global__ void unpack_csr_kernel(const u64 *__restrict__ ukeys, const int *__restrict__ meta, long long n,
-                                  int nb, long long cap, int *__restrict__ rowptr, int *__restrict__ col)
-{
-    const u32 m = (u32)meta[GP_META_NUM_EDGES];
-    const u64 mask = (1ull << nb) - 1ull;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long work = cap > n + 1 ? cap : n + 1;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < work; i += stride) {
-        if (i < (long long)m) col[i] = (int)(ukeys[i] & mask);
-        if (i <= n) rowptr[i] = (int)lower_bound_u64(ukeys, m, (u64)i << nb);
-    }
-}
-
-__global__ void degree_keys_kernel(const int *__restrict__ rowptr, long long n, u64 *__restrict__ okeys,
-                                   int *meta)
+__global__ void scatter_edges_kernel(const long long *__restrict__ ei, long long e, long long n, int symmetrize,
+                                     int *__restrict__ cursor, int *__restrict__ raw_col)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    int mx = 0;
-    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < n; u += stride) {
-        const int deg = rowptr[u + 1] - rowptr[u];
-        mx = max(mx, deg);
-        const u32 capped = deg > 65535 ? 65535u : (u32)deg;
-        okeys[u] = ((u64)(65535u - capped) << 32) | (u64)(u32)u;  // ascending key = descending degree
-    }
-    mx = __reduce_max_sync(FULL_MASK, mx);
-    if (lane_id() == 0 && mx > 0) atomicMax(&meta[GP_META_MAX_DEGREE], mx);
-}
-
-__global__ void order_kernel(const u64 *__restrict__ okeys, long long n, int *__restrict__ order, int *meta)
-{
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (long long i = gid; i < n; i += stride) order[i] = (int)(u32)okeys[i];
-    if (gid < GP_NUM_CLASSES) {
-        // rank boundary: number of rows with degree > thr  <=>  key high half < 65535 - thr
-        int cnt = (int)n;
-        if (gid < GP_NUM_CLASSES - 1) {
-            const int thr = GP_CHUNK_EDGES >> gid;  // 128, 64, 32, 16, 8, 4
-            cnt = (int)lower_bound_u64(okeys, (u32)n, (u64)(65535u - (u32)thr) << 32);
-        }
-        meta[GP_META_RANK + gid] = cnt;
-        if (gid == 0) meta[GP_META_NUM_HUB_ROWS] = cnt;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += stride) {
+        const long long s = ei[i], d = ei[e + i];
+        if (s < 0 || d < 0 || s >= n || d >= n) continue;  // latched by count_edges_kernel
+        raw_col[atomicAdd(cursor + s, 1)] = (int)d;
+        if (symmetrize) raw_col[atomicAdd(cursor + d, 1)] = (int)s;
     }
 }
 
-// Exclusive prefix over the hub rows (degree order) of their chunk counts; one block, running carry.
-__global__ void __launch_bounds__(1024)
-hub_scan_kernel(const int *__restrict__ order, const int *__restrict__ rowptr, int *meta,
-                int *__restrict__ chunk_off)
+// Transposed counting / scatter from a finished CSR (warp per row).
+__global__ void count_in_kernel(const int *__restrict__ row_start, const int *__restrict__ deg,
+                                const int *__restrict__ col, long long n, int *__restrict__ cnt)
 {
-    __shared__ int s_warp[32];
-    __shared__ int s_carry;
-    const int nh = meta[GP_META_NUM_HUB_ROWS];
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int lane = lane_id();
+    for (long long u = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < n; u += warps) {
+        const int s = row_start[u], t = s + deg[u];
+        for (int j = s + lane; j < t; j += 32) atomicAdd(cnt + col[j], 1);
+    }
+}
+
+__global__ void scatter_in_kernel(const int *__restrict__ row_start, const int *__restrict__ deg,
+                                  const int *__restrict__ col, long long n, int *__restrict__ cursor,
+                                  int *__restrict__ col_in)
+{
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int lane = lane_id();
+    for (long long u = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < n; u += warps) {
+        const int s = row_start[u], t = s + deg[u];
+        for (int j = s + lane; j < t; j += 32) col_in[atomicAdd(cursor + col[j], 1)] = (int)u;
+    }
+}
+
+// ---------------------------------------------------------------- single-pass chained scan
+// Status words of tile t: [t * STRIDE] flag (0 nothing, 1 aggregate, 2 inclusive prefix), then CHN
+// aggregates, then CHN inclusive prefixes.  Tiles take their ids from a ticket counter, so every
+// predecessor of a running tile is running or finished and the look-back cannot starve.
+template <int CHN>
+struct ScanStatus {
+    static constexpr int STRIDE = 1 + 2 * CHN;
+};
+
+__device__ __forceinline__ int ld_acquire_i32(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_i32(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// IO: struct with
+//   __device__ void load(long long i, int (&v)[CHN]) const      contribution of element i (v arrives zeroed)
+//   __device__ void store(long long i, const int (&excl)[CHN], const int (&v)[CHN]) const
+//   __device__ void finish(const int (&total)[CHN]) const        called once, by the last tile
+template <int CHN, class IO>
+__global__ void __launch_bounds__(SCAN_THREADS) chained_scan_kernel(IO io, long long count, int *status, int *ticket)
+{
+    constexpr int STRIDE = ScanStatus<CHN>::STRIDE;
+    __shared__ int s_tile;
+    __shared__ int s_warp[SCAN_THREADS / 32][CHN];
+    __shared__ int s_prefix[CHN];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = 0;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1);
     __syncthreads();
-    for (int base = 0; base < nh; base += 1024) {
-        const int k = base + tid;
-        int v = 0;
-        if (k < nh) {
-            const int u = order[k];
-            v = (rowptr[u + 1] - rowptr[u] + GP_CHUNK_EDGES - 1) / GP_CHUNK_EDGES;
-        }
-        int x = v;
+    const int tile = s_tile;
+    const long long ntiles = (count + SCAN_TILE - 1) / SCAN_TILE;
+    if (tile >= ntiles) return;
+
+    const long long base = (long long)tile * SCAN_TILE + (long long)tid * SCAN_IPT;
+    int v[SCAN_IPT][CHN], tsum[CHN];
+#pragma unroll
+    for (int c = 0; c < CHN; ++c) tsum[c] = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; ++k) {
+#pragma unroll
+        for (int c = 0; c < CHN; ++c) v[k][c] = 0;
+        if (base + k < count) io.load(base + k, v[k]);
+#pragma unroll
+        for (int c = 0; c < CHN; ++c) tsum[c] += v[k][c];
+    }
+    // block-wide exclusive scan of the per-thread sums, channel by channel
+    int texcl[CHN];
+#pragma unroll
+    for (int c = 0; c < CHN; ++c) {
+        int x = tsum[c];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int y = __shfl_up_sync(FULL_MASK, x, o);
             if (lane >= o) x += y;
         }
-        if (lane == 31) s_warp[warp] = x;
-        __syncthreads();
+        if (lane == 31) s_warp[warp][c] = x;
+        texcl[c] = x - tsum[c];
+    }
+    __syncthreads();
+    int agg[CHN];
+#pragma unroll
+    for (int c = 0; c < CHN; ++c) {
         int wbase = 0, tot = 0;
-        for (int w = 0; w < 32; ++w) {
-            const int t = s_warp[w];
+#pragma unroll
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+            const int t = s_warp[w][c];
             if (w < warp) wbase += t;
             tot += t;
         }
-        const int carry = s_carry;
-        if (k < nh) chunk_off[k] = carry + wbase + x - v;
-        __syncthreads();
-        if (tid == 0) s_carry = carry + tot;
-        __syncthreads();
+        texcl[c] += wbase;
+        agg[c] = tot;
     }
-    if (tid == 0) {
-        const int chunks = s_carry;
-        chunk_off[nh] = chunks;
-        // class c: descriptors [ent_base[c], ent_base[c+1]), G(c) slots each, regions aligned
+    // publish the aggregate, then warp 0 looks back over 32 predecessors per round trip
+    int *st = status + (size_t)tile * STRIDE;
+    if (warp == 0) {
+        if (tile > 0) {
+            if (lane < CHN) {
+                int mine = 0;
+#pragma unroll
+                for (int c = 0; c < CHN; ++c)
+                    if (c == lane) mine = agg[c];
+                st[1 + lane] = mine;
+                __threadfence();
+            }
+            __syncwarp();
+            if (lane == 0) st_release_i32(st, 1);
+        }
+        int run[CHN];
+#pragma unroll
+        for (int c = 0; c < CHN; ++c) run[c] = 0;
+        for (int t = tile - 1; t >= 0; t -= 32) {
+            const int idx = t - lane;
+            const int *pt = status + (size_t)(idx >= 0 ? idx : 0) * STRIDE;
+            int f = idx >= 0 ? ld_acquire_i32(pt) : 2;  // tiles before the first count as a zero inclusive prefix
+            while (__any_sync(FULL_MASK, f == 0))
+                if (f == 0) f = ld_acquire_i32(pt);
+            const u32 inc_mask = __ballot_sync(FULL_MASK, f == 2);
+            const int first = inc_mask ? __ffs(inc_mask) - 1 : 32;  // nearest predecessor with an inclusive prefix
+#pragma unroll
+            for (int c = 0; c < CHN; ++c) {
+                int val = 0;
+                if (idx >= 0 && lane <= first) val = pt[1 + (lane == first ? CHN : 0) + c];
+                run[c] += __reduce_add_sync(FULL_MASK, val);
+            }
+            if (inc_mask) break;
+        }
+        if (lane < CHN) {
+            int mine = 0, r = 0;
+#pragma unroll
+            for (int c = 0; c < CHN; ++c)
+                if (c == lane) {
+                    mine = agg[c];
+                    r = run[c];
+                }
+            st[1 + CHN + lane] = r + mine;
+            s_prefix[lane] = r;
+            __threadfence();
+        }
+        __syncwarp();
+        if (lane == 0) st_release_i32(st, 2);
+    }
+    __syncthreads();
+    int excl[CHN];
+#pragma unroll
+    for (int c = 0; c < CHN; ++c) excl[c] = s_prefix[c] + texcl[c];
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; ++k) {
+        if (base + k < count) io.store(base + k, excl, v[k]);
+#pragma unroll
+        for (int c = 0; c < CHN; ++c) excl[c] += v[k][c];
+    }
+    if (tile == ntiles - 1 && tid == 0) {
+        int total[CHN];
+#pragma unroll
+        for (int c = 0; c < CHN; ++c) total[c] = s_prefix[c] + agg[c];
+        io.finish(total);
+    }
+}
+
+// cnt[0..n) -> ptr[0..n] (exclusive prefix, ptr[n] = total) and a copy in cursor[0..n).
+struct PtrScanIo {
+    const int *cnt;
+    int *ptr;
+    int *cursor;
+    long long n;
+    __device__ void load(long long i, int (&v)[1]) const
+    {
+        if (i < n) v[0] = cnt[i];
+    }
+    __device__ void store(long long i, const int (&excl)[1], const int (&)[1]) const
+    {
+        ptr[i] = excl[0];
+        if (i < n) cursor[i] = excl[0];
+    }
+    __device__ void finish(const int (&)[1]) const {}
+};
+
+__device__ __forceinline__ int degree_class(int d)
+{
+    // 0: hub rows (cut into GP_CHUNK_EDGES chunks), then G = 32, 16, 8, 4, 2, 1 slots of GP_SLOT_EDGES edges
+    return d > GP_CHUNK_EDGES ? 0 : d > 64 ? 1 : d > 32 ? 2 : d > 16 ? 3 : d > 8 ? 4 : d > 4 ? 5 : 6;
+}
+
+// Row scan: channel 0 edges, 1..7 work-list entries of class 0..6, 8 hub rows.
+struct RowScanIo {
+    const int *deg;
+    int *rank;     // [n] position of the row among the entries of its class
+    int *hubidx;   // [n] index among the hub rows (hub rows only)
+    int *meta;
+    long long n;
+    __device__ void load(long long i, int (&v)[ROW_CH]) const
+    {
+        const int d = deg[i];
+        const int c = degree_class(d);
+        v[0] = d;
+#pragma unroll
+        for (int k = 0; k < GP_NUM_CLASSES; ++k)
+            if (k == c) v[1 + k] = c == 0 ? (d + GP_CHUNK_EDGES - 1) / GP_CHUNK_EDGES : 1;
+        v[8] = c == 0 ? 1 : 0;
+    }
+    __device__ void store(long long i, const int (&excl)[ROW_CH], const int (&v)[ROW_CH]) const
+    {
+        const int c = degree_class(v[0]);
+        int r = 0;
+#pragma unroll
+        for (int k = 0; k < GP_NUM_CLASSES; ++k)
+            if (k == c) r = excl[1 + k];
+        rank[i] = r;
+        if (c == 0) hubidx[i] = excl[8];
+    }
+    __device__ void finish(const int (&total)[ROW_CH]) const
+    {
+        meta[GP_META_NUM_EDGES] = total[0];
+        meta[GP_META_NUM_HUB_ROWS] = total[8];
+        // class c: descriptors [ent_base[c], ent_base[c+1]), G(c) slots each, regions tile aligned
         int ent = 0, slot = 0;
         for (int c = 0; c < GP_NUM_CLASSES; ++c) {
-            const int rows = c == 0 ? chunks : meta[GP_META_RANK + c] - meta[GP_META_RANK + c - 1];
             const int g = c <= 1 ? 32 : (32 >> (c - 1));
             meta[GP_META_ENT_BASE + c] = ent;
             meta[GP_META_SLOT_BASE + c] = slot;
-            ent += rows;
-            slot += (rows * g + GP_SLOT_ALIGN - 1) / GP_SLOT_ALIGN * GP_SLOT_ALIGN;
+            ent += total[1 + c];
+            slot += (int)(((long long)total[1 + c] * g + GP_SLOT_ALIGN - 1) / GP_SLOT_ALIGN * GP_SLOT_ALIGN);
         }
         meta[GP_META_ENT_BASE + GP_NUM_CLASSES] = ent;
         meta[GP_META_SLOT_BASE + GP_NUM_CLASSES] = slot;
     }
+};
+
+// ---------------------------------------------------------------- sort inside the rows
+// Sorting network with every comparator pointing the same way (the lower index keeps the smaller
+// key): for k = 2, 4, ...: partner = i ^ (k - 1) ("flip"), then partner = i ^ j for j = k/4, ..., 1
+// ("disperse").  Indices >= len act as +infinity and are never moved, so any length sorts in place.
+__device__ __forceinline__ int warp_sort32(int v, int lane)
+{
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+        {
+            const int o = __shfl_xor_sync(FULL_MASK, v, k - 1);
+            v = (lane & (k >> 1)) ? max(v, o) : min(v, o);
+        }
+#pragma unroll
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            const int o = __shfl_xor_sync(FULL_MASK, v, j);
+            v = (lane & j) ? max(v, o) : min(v, o);
+        }
+    }
+    return v;
 }
 
-// One descriptor per row (degree order), hub rows expanded into GP_CHUNK_EDGES-edge chunks.
-__global__ void desc_kernel(const int *__restrict__ order, const int *__restrict__ rowptr,
-                            const int *__restrict__ meta, const int *__restrict__ chunk_off, long long n,
-                            int4 *__restrict__ desc)
+// The same network over E * 32 keys held E per lane: key i lives in register i / 32 of lane i % 32,
+// so partners at distance < 32 are one shuffle away and partners at distance >= 32 sit in another
+// register (of the mirrored lane for a flip step).
+template <int E>
+__device__ __forceinline__ void warp_sort_multi(int (&v)[E], int lane)
 {
-    const int nh = meta[GP_META_NUM_HUB_ROWS];
-    const int chunks = chunk_off[nh];
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
-        const int u = order[k];
-        const int s = rowptr[u], d = rowptr[u + 1] - s;
-        if (k >= nh) {
-            desc[chunks + (k - nh)] = make_int4(u, s, d, -1);
+#pragma unroll
+    for (int k = 2; k <= 32 * E; k <<= 1) {
+        // flip: partner = i ^ (k - 1)
+        if (k <= 32) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int o = __shfl_xor_sync(FULL_MASK, v[e], k - 1);
+                v[e] = (lane & (k >> 1)) ? max(v[e], o) : min(v[e], o);
+            }
         } else {
-            const int nch = (d + GP_CHUNK_EDGES - 1) / GP_CHUNK_EDGES;
-            const int off = chunk_off[k];
-            for (int c = 0; c < nch; ++c) {
-                const int cnt = min(GP_CHUNK_EDGES, d - c * GP_CHUNK_EDGES);
-                desc[off + c] = make_int4(u, s + c * GP_CHUNK_EDGES, cnt | (nch << 8) | (c == 0 ? 1 << 30 : 0), (int)k);
+            const int em = (k >> 5) - 1;  // register index bits flipped by this block size
+            int o[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) o[e] = __shfl_xor_sync(FULL_MASK, v[e ^ em], 31);
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = (e & (k >> 6)) ? max(v[e], o[e]) : min(v[e], o[e]);
+        }
+        // disperse: partner = i ^ j
+#pragma unroll
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int ej = j >> 5;
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (!(e & ej)) {
+                        const int lo = min(v[e], v[e | ej]), hi = max(v[e], v[e | ej]);
+                        v[e] = lo;
+                        v[e | ej] = hi;
+                    }
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int o = __shfl_xor_sync(FULL_MASK, v[e], j);
+                    v[e] = (lane & j) ? max(v[e], o) : min(v[e], o);
+                }
             }
         }
     }
 }
 
-__global__ void transpose_keys_kernel(const u64 *__restrict__ ukeys, const int *__restrict__ meta, int nb,
-                                      long long cap, u64 *__restrict__ tkeys)
+// Sort + unique of one row of <= 32 * E edges by one warp, in registers; returns the distinct count.
+template <int E>
+__device__ __forceinline__ int warp_row_sort_unique(int *colbuf, int s, int len, int lane)
 {
-    const u32 m = (u32)meta[GP_META_NUM_EDGES];
-    const u64 mask = (1ull << nb) - 1ull;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride)
-        if (i < (long long)m) {
-            const u64 k = ukeys[i];
-            tkeys[i] = ((k & mask) << nb) | (k >> nb);
+    int v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = e * 32 + lane < len ? colbuf[s + e * 32 + lane] : 0x7FFFFFFF;
+    if constexpr (E == 1) v[0] = warp_sort32(v[0], lane);
+    else warp_sort_multi<E>(v, lane);
+    int base = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        int prev = __shfl_up_sync(FULL_MASK, v[e], 1);
+        if (e > 0) {
+            const int last = __shfl_sync(FULL_MASK, v[e - 1], 31);
+            if (lane == 0) prev = last;
         }
+        const bool head = e * 32 + lane < len && ((e == 0 && lane == 0) || v[e] != prev);
+        const u32 heads = __ballot_sync(FULL_MASK, head);
+        // in place is safe: every key of the row is already in registers
+        if (head) colbuf[s + base + __popc(heads & ((1u << lane) - 1u))] = v[e];
+        base += __popc(heads);
+    }
+    return base;
 }
 
-__global__ void symmetric_check_kernel(const u64 *__restrict__ ukeys, const u64 *__restrict__ tkeys,
-                                       long long cap, int *meta)
+// Rows of <= 128 edges: one warp, registers only.  Longer rows are queued for rowsort_big_kernel.
+__global__ void rowsort_small_kernel(const int *__restrict__ ptr, const int *len_in, int *__restrict__ colbuf,
+                                     long long n, int *deg, int *__restrict__ biglist, int *meta, int max_word)
 {
-    const u32 m = (u32)meta[GP_META_NUM_EDGES];
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int lane = lane_id();
+    int mx = 0;
+    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+        const int s = ptr[r], len = len_in[r];
+        if (len > 128) {
+            if (lane == 0) biglist[atomicAdd(&meta[GP_META_NUM_BIG_ROWS], 1)] = (int)r;
+            continue;
+        }
+        if (len == 0) continue;  // deg[r] already holds 0
+        int d;
+        if (len <= 32) d = warp_row_sort_unique<1>(colbuf, s, len, lane);
+        else if (len <= 64) d = warp_row_sort_unique<2>(colbuf, s, len, lane);
+        else d = warp_row_sort_unique<4>(colbuf, s, len, lane);
+        if (lane == 0 && d != len) deg[r] = d;
+        mx = max(mx, d);
+    }
+    // one same-address atomic per warp would serialise in L2: only warps that raise the maximum issue one
+    if (lane == 0 && mx > 0 && mx > *(volatile int *)&meta[max_word]) atomicMax(&meta[max_word], mx);
+}
+
+// One step of the network over a[0..len): `sh` = log2 of the half block (flip) or of the stride
+// (disperse).  Thread t handles comparator pairs t, t + T, ...; four pairs are loaded before any is
+// written so the loads overlap.
+template <bool FLIP>
+__device__ __forceinline__ void network_step(int *a, int len, int pairs, int sh, int tid, int nthreads)
+{
+    const int h = 1 << sh;
+    for (int p0 = tid; p0 < pairs; p0 += 4 * nthreads) {
+        int i[4], o[4], x[4], y[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int p = p0 + q * nthreads;
+            const int blk = p >> sh, off = p & (h - 1);
+            i[q] = (blk << (sh + 1)) + off;
+            o[q] = FLIP ? (blk << (sh + 1)) + 2 * h - 1 - off : i[q] + h;
+            if (p >= pairs) o[q] = len;  // inactive
+            if (o[q] < len) {
+                x[q] = a[i[q]];
+                y[q] = a[o[q]];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (o[q] < len && x[q] > y[q]) {
+                a[i[q]] = y[q];
+                a[o[q]] = x[q];
+            }
+    }
+}
+
+// One CTA per queued row.  Long rows of a graph whose node bitmap fits in shared memory are sorted
+// and de-duplicated by setting one bit per neighbour and reading the bits back in order; the others
+// go through the sorting network (shared memory up to BIG_SMEM_ELEMS, else in place) and a head-flag
+// scan.  Dynamic shared memory: max(BIG_SMEM_ELEMS ints, bitmap_words words).
+__global__ void __launch_bounds__(BIG_THREADS)
+rowsort_big_kernel(const int *__restrict__ ptr, const int *len_in, int *colbuf, int *deg,
+                   const int *__restrict__ biglist, int *meta, int max_word, int bitmap_words)
+{
+    extern __shared__ __align__(16) int s_buf[];
+    __shared__ int s_warp[BIG_THREADS / 32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nbig = meta[GP_META_NUM_BIG_ROWS];
+    for (int q = blockIdx.x; q < nbig; q += gridDim.x) {
+        const int r = biglist[q];
+        const int s = ptr[r], len = len_in[r];
+        __syncthreads();  // previous row done with s_buf / s_carry
+        if (bitmap_words > 0 && (long long)len * 32 >= bitmap_words) {
+            // ---- bitmap path
+            u32 *bm = reinterpret_cast<u32 *>(s_buf);
+            for (int i = tid; i < bitmap_words; i += BIG_THREADS) bm[i] = 0;
+            __syncthreads();
+            for (int i = tid; i < len; i += BIG_THREADS) {
+                const int v = colbuf[s + i];
+                atomicOr(&bm[v >> 5], 1u << (v & 31));
+            }
+            __syncthreads();
+            // thread t owns the contiguous words [t * wpt, (t + 1) * wpt)
+            const int wpt = (bitmap_words + BIG_THREADS - 1) / BIG_THREADS;
+            const int w0 = tid * wpt, w1 = min(bitmap_words, w0 + wpt);
+            int cnt = 0;
+            for (int w = w0; w < w1; ++w) cnt += __popc(bm[w]);
+            int x = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(FULL_MASK, x, o);
+                if (lane >= o) x += y;
+            }
+            if (lane == 31) s_warp[warp] = x;
+            __syncthreads();
+            int wbase = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < BIG_THREADS / 32; ++w) {
+                const int t = s_warp[w];
+                if (w < warp) wbase += t;
+                tot += t;
+            }
+            int pos = s + wbase + x - cnt;
+            for (int w = w0; w < w1; ++w) {
+                u32 bits = bm[w];
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    colbuf[pos++] = (w << 5) + b;
+                }
+            }
+            if (tid == 0) {
+                if (tot != len) deg[r] = tot;
+                if (tot > *(volatile int *)&meta[max_word]) atomicMax(&meta[max_word], tot);
+            }
+            continue;
+        }
+        // ---- network path
+        const bool in_smem = len <= BIG_SMEM_ELEMS;
+        int *a = in_smem ? s_buf : colbuf + s;
+        if (in_smem)
+            for (int i = tid; i < len; i += BIG_THREADS) s_buf[i] = colbuf[s + i];
+        __syncthreads();
+        int lg = 1;
+        while ((1 << lg) < len) ++lg;  // network over 2^lg >= len virtual elements
+        const int pairs = 1 << (lg - 1);
+        for (int kb = 1; kb <= lg; ++kb) {  // block size k = 2^kb
+            network_step<true>(a, len, pairs, kb - 1, tid, BIG_THREADS);
+            __syncthreads();
+            for (int jb = kb - 2; jb >= 0; --jb) {
+                network_step<false>(a, len, pairs, jb, tid, BIG_THREADS);
+                __syncthreads();
+            }
+        }
+        // unique: out position = number of heads before i; chunks of BIG_THREADS with a running carry.
+        // Writing in place is safe: position <= i, and a chunk is written only after it was read.
+        if (tid == 0) s_carry = 0;
+        __syncthreads();
+        for (int base = 0; base < len; base += BIG_THREADS) {
+            const int i = base + tid;
+            int v = 0;
+            bool head = false;
+            if (i < len) {
+                v = a[i];
+                head = i == 0 || a[i - 1] != v;
+            }
+            const u32 heads = __ballot_sync(FULL_MASK, head);
+            if (lane == 0) s_warp[warp] = __popc(heads);
+            __syncthreads();  // every a[i], a[i-1] of this chunk has been read
+            int wbase = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < BIG_THREADS / 32; ++w) {
+                const int t = s_warp[w];
+                if (w < warp) wbase += t;
+                tot += t;
+            }
+            const int carry = s_carry;
+            if (head) colbuf[s + carry + wbase + __popc(heads & ((1u << lane) - 1u))] = v;
+            __syncthreads();
+            if (tid == 0) s_carry = carry + tot;
+            __syncthreads();
+        }
+        if (tid == 0) {
+            if (s_carry != len) deg[r] = s_carry;
+            if (s_carry > *(volatile int *)&meta[max_word]) atomicMax(&meta[max_word], s_carry);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- work-list descriptors
+// desc = {row, first edge, count | chunks << 8 | first << 30, hub index or -1}, one per row, hub rows
+// one per GP_CHUNK_EDGES-edge chunk.
+__global__ void desc_kernel(const int *__restrict__ row_start, const int *__restrict__ deg,
+                            const int *__restrict__ rank, const int *__restrict__ hubidx,
+                            const int *__restrict__ meta, long long n, int4 *__restrict__ desc)
+{
+    __shared__ int s_ent[GP_NUM_CLASSES];
+    if (threadIdx.x < GP_NUM_CLASSES) s_ent[threadIdx.x] = meta[GP_META_ENT_BASE + threadIdx.x];
+    __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+        const int s = row_start[r], d = deg[r];
+        const int c = degree_class(d);
+        const int ent = s_ent[c] + rank[r];
+        if (c != 0) {
+            desc[ent] = make_int4((int)r, s, d, -1);
+        } else {
+            const int nch = (d + GP_CHUNK_EDGES - 1) / GP_CHUNK_EDGES;
+            const int h = hubidx[r];
+            for (int k = 0; k < nch; ++k) {
+                const int cnt = min(GP_CHUNK_EDGES, d - k * GP_CHUNK_EDGES);
+                desc[ent + k] = make_int4((int)r, s + k * GP_CHUNK_EDGES, cnt | (nch << 8) | (k == 0 ? 1 << 30 : 0), h);
+            }
+        }
+    }
+}
+
+// is_symmetric: every row of the out-edge CSR equals the same row of the in-edge CSR (warp per row).
+__global__ void compare_csr_kernel(const int *__restrict__ row_start, const int *__restrict__ deg,
+                                   const int *__restrict__ col, const int *__restrict__ rowptr_in,
+                                   const int *__restrict__ col_in, long long n, int *meta)
+{
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int lane = lane_id();
     bool diff = false;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride)
-        if (i < (long long)m && ukeys[i] != tkeys[i]) diff = true;
-    if (__any_sync(FULL_MASK, diff) && lane_id() == 0) atomicExch(&meta[GP_META_IS_SYMMETRIC], 0);
+    for (long long u = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < n; u += warps) {
+        const int s = row_start[u], d = deg[u], si = rowptr_in[u];
+        if (rowptr_in[u + 1] - si != d) {
+            diff = true;
+            continue;
+        }
+        for (int j = lane; j < d; j += 32)
+            if (col[s + j] != col_in[si + j]) diff = true;
+    }
+    if (__any_sync(FULL_MASK, diff) && lane == 0) atomicExch(&meta[GP_META_IS_SYMMETRIC], 0);
+}
+
+// Compacting copy for gp_csr_export (warp per row).
+__global__ void gather_rows_kernel(const int *__restrict__ row_start, const int *__restrict__ deg,
+                                   const int *__restrict__ col, const int *__restrict__ rowptr, long long n,
+                                   int *__restrict__ out)
+{
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int lane = lane_id();
+    for (long long u = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < n; u += warps) {
+        const int s = row_start[u], d = deg[u], t = rowptr[u];
+        for (int j = lane; j < d; j += 32) out[t + j] = col[s + j];
+    }
 }
 
 __global__ void set_meta_kernel(int *meta, int idx, int value) { meta[idx] = value; }
 
-int launch_blocks(int64_t work, int threads)
+int scan_tiles(int64_t count) { return (int)gp_ceil_div(count > 0 ? count : 1, SCAN_TILE); }
+
+// Sorts (and de-duplicates) the row segments [ptr[r], ptr[r] + len[r]) of colbuf in place; len[r] is
+// overwritten with the distinct count where it shrinks; meta[max_word] = max distinct count.
+int sort_rows(gp_csr *c, const int *ptr, int *len, int *colbuf, int max_word, cudaStream_t stream)
 {
-    int64_t b = gp_ceil_div(work > 0 ? work : 1, threads);
-    const int64_t cap = (int64_t)gp_sm_count() * 8;
-    return (int)(b < cap ? b : cap);
+    const int64_t n = c->num_nodes;
+    GP_LAUNCH(set_meta_kernel, 1, 1, 0, stream, c->meta, GP_META_NUM_BIG_ROWS, 0);
+    GP_LAUNCH(rowsort_small_kernel, row_blocks(n), 256, 0, stream, ptr, len, colbuf, n, len, c->biglist, c->meta,
+              max_word);
+    GP_LAUNCH(rowsort_big_kernel, gp_sm_count() * 4, BIG_THREADS, c->big_smem_bytes, stream, ptr, len, colbuf, len,
+              c->biglist, c->meta, max_word, c->bitmap_words);
+    return GP_OK;
 }
 
 }  // namespace
@@ -218,11 +677,19 @@ extern "C" int gp_csr_create(int64_t num_nodes, int64_t edge_capacity, uint32_t 
     c->edge_capacity = edge_capacity;
     c->key_capacity = kcap;
     c->flags = flags;
-    int nb = 1;
-    while ((1ll << nb) < num_nodes) ++nb;
-    c->node_bits = nb;
     c->hub_capacity = kcap / (GP_CHUNK_EDGES + 1) + 1;
     c->desc_capacity = num_nodes + kcap / GP_CHUNK_EDGES + 2;
+    c->big_capacity = kcap / 129 + 1;
+    // node bitmap for the long-row sort, if it fits next to a few resident CTAs
+    const int64_t words = (num_nodes + 31) / 32;
+    c->bitmap_words = words * 4 <= 96 * 1024 ? (int)words : 0;
+    c->big_smem_bytes = BIG_SMEM_ELEMS * (int)sizeof(int);
+    if (c->bitmap_words * 4 > c->big_smem_bytes) c->big_smem_bytes = (c->bitmap_words * 4 + 15) / 16 * 16;
+    if (cudaFuncSetAttribute(rowsort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) {
+        cudaGetLastError();
+        c->bitmap_words = c->bitmap_words * 4 <= BIG_SMEM_ELEMS * (int)sizeof(int) ? c->bitmap_words : 0;
+        c->big_smem_bytes = BIG_SMEM_ELEMS * (int)sizeof(int);
+    }
     const size_t kc = (size_t)(kcap > 0 ? kcap : 1), nn = (size_t)num_nodes;
     int rc = GP_OK;
     auto alloc = [&](void **p, size_t bytes) {
@@ -233,19 +700,16 @@ extern "C" int gp_csr_create(int64_t num_nodes, int64_t edge_capacity, uint32_t 
             rc = (e == cudaErrorMemoryAllocation) ? GP_ERR_OOM : GP_ERR_CUDA;
         }
     };
-    alloc((void **)&c->keys, kc * sizeof(u64));
-    alloc((void **)&c->ukeys, kc * sizeof(u64));
-    alloc((void **)&c->rowptr_out, (nn + 1) * sizeof(int));
-    alloc((void **)&c->col_out, kc * sizeof(int));
-    alloc((void **)&c->rowptr_in, (nn + 1) * sizeof(int));
-    alloc((void **)&c->col_in, kc * sizeof(int));
-    alloc((void **)&c->order, (nn + 1) * sizeof(int));
-    alloc((void **)&c->okeys, (nn + 1) * sizeof(u64));
+    alloc((void **)&c->deg, (nn + 1) * sizeof(int));
+    alloc((void **)&c->row_start, (nn + 1) * sizeof(int));
+    alloc((void **)&c->cursor, (nn + 1) * sizeof(int));
+    alloc((void **)&c->col, kc * sizeof(int));
+    alloc((void **)&c->hubidx, (nn + 1) * sizeof(int));
+    alloc((void **)&c->biglist, (size_t)c->big_capacity * sizeof(int));
     alloc((void **)&c->desc, (size_t)c->desc_capacity * sizeof(int4));
-    alloc((void **)&c->hub_chunk_off, (size_t)(c->hub_capacity + 1) * sizeof(int));
     alloc((void **)&c->meta, GP_META_WORDS * sizeof(int));
-    alloc((void **)&c->uniq_status, (size_t)(gp_ceil_div((int64_t)kc, GP_SORT_TILE) + 2) * sizeof(u32));
-    if (rc == GP_OK) rc = gp_sort_workspace_create(&c->sort_ws, (int64_t)(kc > nn ? kc : nn), false);
+    c->scan_status_words = (size_t)scan_tiles(num_nodes + 1) * ScanStatus<ROW_CH>::STRIDE + 8;
+    alloc((void **)&c->scan_status, c->scan_status_words * sizeof(int));
     if (rc != GP_OK) {
         gp_csr_free(c);
         return rc;
@@ -258,19 +722,18 @@ extern "C" int gp_csr_free(gp_csr_t *c)
 {
     if (!c) return GP_OK;
     gp_drop_graphs(c);
-    cudaFree(c->keys);
-    cudaFree(c->ukeys);
-    cudaFree(c->rowptr_out);
-    cudaFree(c->col_out);
+    cudaFree(c->deg);
+    cudaFree(c->row_start);
+    cudaFree(c->cursor);
+    cudaFree(c->col);
     cudaFree(c->rowptr_in);
     cudaFree(c->col_in);
-    cudaFree(c->order);
-    cudaFree(c->okeys);
+    cudaFree(c->deg_in);
+    cudaFree(c->hubidx);
+    cudaFree(c->biglist);
     cudaFree(c->desc);
-    cudaFree(c->hub_chunk_off);
     cudaFree(c->meta);
-    cudaFree(c->uniq_status);
-    gp_sort_workspace_free(&c->sort_ws);
+    cudaFree(c->scan_status);
     delete c;
     return GP_OK;
 }
@@ -284,30 +747,35 @@ extern "C" int gp_csr_build(gp_csr_t *c, const int64_t *d_edge_index, int64_t nu
                (long long)num_edges, (long long)c->edge_capacity);
     GP_REQUIRE(num_edges == 0 || d_edge_index != nullptr, GP_ERR_INVALID, "gp_csr_build: edge_index is NULL");
     const int sym = (c->flags & GP_CSR_SYMMETRIZE) ? 1 : 0;
-    const int64_t nkeys = num_edges * (sym ? 2 : 1);
-    const int nb = c->node_bits;
     const int64_t n = c->num_nodes;
     c->num_input_edges = num_edges;
     c->built = false;
     c->in_built = false;
     GP_CUDA_CHECK(cudaMemsetAsync(c->meta, 0, GP_META_WORDS * sizeof(int), stream));
-    if (num_edges > 0)
-        GP_LAUNCH(pack_keys_kernel, launch_blocks(num_edges, 256), 256, 0, stream, (const long long *)d_edge_index, num_edges, n, nb, sym, c->keys, c->meta);
-    u64 *sorted = c->keys;
-    GP_TRY(gp_radix_sort(&c->sort_ws, c->keys, nullptr, nullptr, nkeys, 0, 2 * nb, stream, &sorted, nullptr));
-    GP_TRY(gp_unique_sorted(sorted, c->ukeys, nullptr, nkeys, (u32 *)&c->meta[GP_META_NUM_EDGES],
-                            c->uniq_status, stream));
-    const int64_t work = nkeys > n + 1 ? nkeys : n + 1;
-    GP_LAUNCH(unpack_csr_kernel, launch_blocks(work, 256), 256, 0, stream, c->ukeys, c->meta, n, nb, nkeys,
-                                                                    c->rowptr_out, c->col_out);
     if (n > 0) {
-        GP_LAUNCH(degree_keys_kernel, launch_blocks(n, 256), 256, 0, stream, c->rowptr_out, n, c->okeys, c->meta);
-        u64 *osorted = c->okeys;
-        GP_TRY(gp_radix_sort(&c->sort_ws, c->okeys, nullptr, nullptr, n, 32, 48, stream, &osorted, nullptr));
-        GP_LAUNCH(order_kernel, launch_blocks(n, 256), 256, 0, stream, osorted, n, c->order, c->meta);
-        GP_LAUNCH(hub_scan_kernel, 1, 1024, 0, stream, c->order, c->rowptr_out, c->meta, c->hub_chunk_off);
-        GP_LAUNCH(desc_kernel, launch_blocks(n, 256), 256, 0, stream, c->order, c->rowptr_out, c->meta,
-                  c->hub_chunk_off, n, c->desc);
+        const long long *ei = (const long long *)d_edge_index;
+        const int tiles = scan_tiles(n + 1);
+        int *ticket_a = c->scan_status + c->scan_status_words - 8, *ticket_b = ticket_a + 1;
+        GP_CUDA_CHECK(cudaMemsetAsync(c->deg, 0, (size_t)(n + 1) * sizeof(int), stream));
+        GP_CUDA_CHECK(cudaMemsetAsync(c->scan_status, 0, c->scan_status_words * sizeof(int), stream));
+        if (num_edges > 0)
+            GP_LAUNCH(count_edges_kernel, launch_blocks(num_edges, 256), 256, 0, stream, ei, num_edges, n, sym, c->deg,
+                      c->meta);
+        PtrScanIo pio{c->deg, c->row_start, c->cursor, n};
+        gp_count_launch();
+        chained_scan_kernel<1, PtrScanIo><<<tiles, SCAN_THREADS, 0, stream>>>(pio, n + 1, c->scan_status, ticket_a);
+        if (num_edges > 0)
+            GP_LAUNCH(scatter_edges_kernel, launch_blocks(num_edges, 256), 256, 0, stream, ei, num_edges, n, sym,
+                      c->cursor, c->col);
+        GP_TRY(sort_rows(c, c->row_start, c->deg, c->col, GP_META_MAX_DEGREE, stream));  // deg := distinct degree
+        // the first scan used the leading status words: clear them again for the row scan
+        GP_CUDA_CHECK(cudaMemsetAsync(c->scan_status, 0, (size_t)tiles * ScanStatus<1>::STRIDE * sizeof(int), stream));
+        RowScanIo rio{c->deg, c->cursor, c->hubidx, c->meta, n};  // cursor := rank of the row inside its class
+        gp_count_launch();
+        chained_scan_kernel<ROW_CH, RowScanIo><<<scan_tiles(n), SCAN_THREADS, 0, stream>>>(rio, n, c->scan_status,
+                                                                                         ticket_b);
+        GP_LAUNCH(desc_kernel, launch_blocks(n, 256), 256, 0, stream, c->row_start, c->deg, c->cursor, c->hubidx, c->meta,
+                  n, c->desc);
     }
     GP_CUDA_CHECK(cudaGetLastError());
     c->built = true;
@@ -318,20 +786,33 @@ int gp_csr_ensure_in(gp_csr *c, cudaStream_t stream)
 {
     GP_REQUIRE(c != nullptr && c->built, GP_ERR_INVALID, "in-edge CSR requested before gp_csr_build");
     if (c->in_built) return GP_OK;
-    const int nb = c->node_bits;
     const int64_t n = c->num_nodes;
-    const int64_t cap = c->num_input_edges * ((c->flags & GP_CSR_SYMMETRIZE) ? 2 : 1);
-    // c->keys (raw packed input) is dead after the unique step: reuse it for the transposed keys.
-    GP_LAUNCH(transpose_keys_kernel, launch_blocks(cap, 256), 256, 0, stream, c->ukeys, c->meta, nb, cap, c->keys);
-    u64 *tsorted = c->keys;
-    // distinct keys are (src,dst)-sorted, so a stable sort on the dst half alone yields (dst,src) order
-    GP_TRY(gp_radix_sort(&c->sort_ws, c->keys, nullptr, (const u32 *)&c->meta[GP_META_NUM_EDGES], cap, nb,
-                         2 * nb, stream, &tsorted, nullptr));
+    if (c->rowptr_in == nullptr) {  // the transposed arrays are allocated on first use
+        GP_REQUIRE(!gp_is_capturing(), GP_ERR_INVALID, "in-edge CSR cannot be allocated inside a graph capture");
+        const size_t kc = (size_t)(c->key_capacity > 0 ? c->key_capacity : 1);
+        GP_CUDA_CHECK(cudaMalloc((void **)&c->rowptr_in, (size_t)(n + 1) * sizeof(int)));
+        GP_CUDA_CHECK(cudaMalloc((void **)&c->col_in, kc * sizeof(int)));
+        GP_CUDA_CHECK(cudaMalloc((void **)&c->deg_in, (size_t)(n + 1) * sizeof(int)));
+    }
     GP_LAUNCH(set_meta_kernel, 1, 1, 0, stream, c->meta, GP_META_IS_SYMMETRIC, 1);
-    GP_LAUNCH(symmetric_check_kernel, launch_blocks(cap, 256), 256, 0, stream, c->ukeys, tsorted, cap, c->meta);
-    const int64_t work = cap > n + 1 ? cap : n + 1;
-    GP_LAUNCH(unpack_csr_kernel, launch_blocks(work, 256), 256, 0, stream, tsorted, c->meta, n, nb, cap, c->rowptr_in,
-                                                                    c->col_in);
+    if (n > 0) {
+        // cursor / scan_status are free again once the out-edge CSR is finished... except that cursor
+        // holds the class ranks only until desc_kernel has run, which it has
+        int *ticket = c->scan_status + c->scan_status_words - 8;
+        GP_CUDA_CHECK(cudaMemsetAsync(c->deg_in, 0, (size_t)(n + 1) * sizeof(int), stream));
+        GP_CUDA_CHECK(cudaMemsetAsync(c->scan_status, 0, c->scan_status_words * sizeof(int), stream));
+        GP_LAUNCH(count_in_kernel, row_blocks(n), 256, 0, stream, c->row_start, c->deg, c->col, n, c->deg_in);
+        PtrScanIo pio{c->deg_in, c->rowptr_in, c->cursor, n};
+        gp_count_launch();
+        chained_scan_kernel<1, PtrScanIo><<<scan_tiles(n + 1), SCAN_THREADS, 0, stream>>>(pio, n + 1, c->scan_status,
+                                                                                        ticket);
+        GP_LAUNCH(scatter_in_kernel, row_blocks(n), 256, 0, stream, c->row_start, c->deg, c->col, n, c->cursor,
+                  c->col_in);
+        // the transposed rows hold no duplicates: sorting them in place restores ascending order
+        GP_TRY(sort_rows(c, c->rowptr_in, c->deg_in, c->col_in, GP_META_SCRATCH, stream));
+        GP_LAUNCH(compare_csr_kernel, row_blocks(n), 256, 0, stream, c->row_start, c->deg, c->col, c->rowptr_in,
+                  c->col_in, n, c->meta);
+    }
     GP_LAUNCH(set_meta_kernel, 1, 1, 0, stream, c->meta, GP_META_IN_BUILT, 1);
     GP_CUDA_CHECK(cudaGetLastError());
     c->in_built = true;
@@ -365,15 +846,33 @@ extern "C" int gp_csr_export(gp_csr_t *c, int which, int32_t *d_rowptr, int32_t 
                "gp_csr_export: NULL argument");
     GP_REQUIRE(c->built, GP_ERR_INVALID, "gp_csr_export: gp_csr_build has not been called");
     GP_REQUIRE(which == 0 || which == 1, GP_ERR_INVALID, "gp_csr_export: which must be 0 (out) or 1 (in)");
-    if (which == 1) GP_TRY(gp_csr_ensure_in(c, stream));
-    int m = 0;
-    GP_CUDA_CHECK(cudaMemcpyAsync(&m, &c->meta[GP_META_NUM_EDGES], sizeof(int), cudaMemcpyDeviceToHost, stream));
-    GP_CUDA_CHECK(cudaStreamSynchronize(stream));
-    GP_CUDA_CHECK(cudaMemcpyAsync(d_rowptr, which ? c->rowptr_in : c->rowptr_out,
-                                  (size_t)(c->num_nodes + 1) * sizeof(int), cudaMemcpyDeviceToDevice, stream));
-    if (m > 0)
-        GP_CUDA_CHECK(cudaMemcpyAsync(d_col, which ? c->col_in : c->col_out, (size_t)(u32)m * sizeof(int),
-                                      cudaMemcpyDeviceToDevice, stream));
+    const int64_t n = c->num_nodes;
+    if (n == 0) {
+        GP_CUDA_CHECK(cudaMemsetAsync(d_rowptr, 0, sizeof(int), stream));
+        GP_CUDA_CHECK(cudaStreamSynchronize(stream));
+        return GP_OK;
+    }
+    if (which == 1) {
+        GP_TRY(gp_csr_ensure_in(c, stream));
+        int m = 0;
+        GP_CUDA_CHECK(cudaMemcpyAsync(&m, &c->meta[GP_META_NUM_EDGES], sizeof(int), cudaMemcpyDeviceToHost, stream));
+        GP_CUDA_CHECK(cudaStreamSynchronize(stream));
+        GP_CUDA_CHECK(cudaMemcpyAsync(d_rowptr, c->rowptr_in, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToDevice,
+                                      stream));
+        if (m > 0)
+            GP_CUDA_CHECK(cudaMemcpyAsync(d_col, c->col_in, (size_t)(u32)m * sizeof(int), cudaMemcpyDeviceToDevice,
+                                          stream));
+    } else {
+        // squeeze the slack out: rowptr = exclusive prefix of deg, then a row-wise gather
+        int *ticket = c->scan_status + c->scan_status_words - 8;
+        GP_CUDA_CHECK(cudaMemsetAsync(c->scan_status, 0, c->scan_status_words * sizeof(int), stream));
+        PtrScanIo pio{c->deg, d_rowptr, c->cursor, n};
+        gp_count_launch();
+        chained_scan_kernel<1, PtrScanIo><<<scan_tiles(n + 1), SCAN_THREADS, 0, stream>>>(pio, n + 1, c->scan_status,
+                                                                                        ticket);
+        GP_LAUNCH(gather_rows_kernel, row_blocks(n), 256, 0, stream, c->row_start, c->deg, c->col, d_rowptr, n, d_col);
+        GP_CUDA_CHECK(cudaGetLastError());
+    }
     GP_CUDA_CHECK(cudaStreamSynchronize(stream));
     return GP_OK;
 }

@@ -771,7 +771,7 @@ extern "C" int gp_msbfs_run(gp_msbfs_t *h, const int64_t *d_anchors, int64_t num
     p.nzwords = (int)h->nzwords;
     p.map_stride = (int)(((int64_t)batches * h->nzwords + 3) / 4 * 4);
     p.map_smem_words = 0;  // decided per launch configuration (launch_bfs_cfg)
-    p.col = h->csr->col_out;
+    p.col = h->csr->col;
     p.meta = h->csr->meta;
     p.anchors = (const long long *)d_anchors;
     p.result = h->seen;

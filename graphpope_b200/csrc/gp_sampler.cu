@@ -9,40 +9,41 @@
 // FMA contraction; the dangling mass is a left-to-right sum (Python's sum()); then
 //     x = alpha * (y + dsum * p) + (1 - alpha) * p,   stop when sum|x - xlast| < N * tol.
 #include "gp_internal.h"
+#include "gp_sort.cuh"
 
 #include <vector>
 
 namespace {
 
-__global__ void degree_kernel(const int *__restrict__ rp_out, const int *__restrict__ rp_in, long long n,
+__global__ void degree_kernel(const int *__restrict__ deg_out, const int *__restrict__ rp_in, long long n,
                               int *__restrict__ deg)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < n; u += stride)
-        deg[u] = (rp_out[u + 1] - rp_out[u]) + (rp_in[u + 1] - rp_in[u]);
+        deg[u] = deg_out[u] + (rp_in[u + 1] - rp_in[u]);
 }
 
-__global__ void pr_init_kernel(const int *__restrict__ rp_out, long long n, double *__restrict__ x,
+__global__ void pr_init_kernel(const int *__restrict__ deg_out, long long n, double *__restrict__ x,
                                double *__restrict__ inv_out)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const double x0 = 1.0 / (double)n;
     for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < n; u += stride) {
-        const int d = rp_out[u + 1] - rp_out[u];
+        const int d = deg_out[u];
         inv_out[u] = d > 0 ? 1.0 / (double)d : 0.0;
         x[u] = x0;
     }
 }
 
 // Ascending list of nodes without out-edges (one warp, ballot compaction keeps the order).
-__global__ void dangling_list_kernel(const int *__restrict__ rp_out, long long n, int *__restrict__ list,
+__global__ void dangling_list_kernel(const int *__restrict__ deg_out, long long n, int *__restrict__ list,
                                      int *count)
 {
     const int lane = threadIdx.x;
     int base = 0;
     for (long long u0 = 0; u0 < n; u0 += 32) {
         const long long u = u0 + lane;
-        const bool d = u < n && rp_out[u + 1] == rp_out[u];
+        const bool d = u < n && deg_out[u] == 0;
         const u32 m = __ballot_sync(FULL_MASK, d);
         if (d) list[base + __popc(m & ((1u << lane) - 1u))] = (int)u;
         base += __popc(m);
@@ -181,7 +182,7 @@ extern "C" int gp_degree(const gp_csr_t *csr_, int32_t *d_degree, gp_stream_t st
     GP_REQUIRE(csr->built, GP_ERR_INVALID, "gp_degree: the CSR has not been built");
     GP_TRY(gp_csr_ensure_in(csr, stream));
     if (csr->num_nodes == 0) return GP_OK;
-    GP_LAUNCH(degree_kernel, blocks_for(csr->num_nodes), 256, 0, stream, csr->rowptr_out, csr->rowptr_in,
+    GP_LAUNCH(degree_kernel, blocks_for(csr->num_nodes), 256, 0, stream, csr->deg, csr->rowptr_in,
                                                                   csr->num_nodes, d_degree);
     GP_CUDA_CHECK(cudaGetLastError());
     return GP_OK;
@@ -211,8 +212,8 @@ extern "C" int gp_pagerank(const gp_csr_t *csr_, double alpha, double tol, int32
     int *dang = (int *)b_dang.p;
     double *dsum = (double *)b_small.p, *err = dsum + 1;
     int *n_dang = (int *)(dsum + 2);
-    GP_LAUNCH(pr_init_kernel, nblocks, 256, 0, stream, csr->rowptr_out, n, xa, inv_out);
-    GP_LAUNCH(dangling_list_kernel, 1, 32, 0, stream, csr->rowptr_out, n, dang, n_dang);
+    GP_LAUNCH(pr_init_kernel, nblocks, 256, 0, stream, csr->deg, n, xa, inv_out);
+    GP_LAUNCH(dangling_list_kernel, 1, 32, 0, stream, csr->deg, n, dang, n_dang);
     const double one_minus_alpha = 1 - alpha;
     bool converged = false;
     int it = 0;

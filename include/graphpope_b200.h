@@ -94,8 +94,8 @@ int64_t gp_launch_count(void);
 /* ------------------------------------------------------------------ CSR build
  * Replaces torch_geometric.utils.to_networkx(data) as called at utils.py:121
  * (and :27,33,39,45,51,57): nodes 0..N-1, parallel edges collapse, self-loops
- * kept, no symmetrisation unless GP_CSR_SYMMETRIZE.  Built on the device with a
- * radix sort of packed (src,dst) keys + unique + row-pointer search.            */
+ * kept, no symmetrisation unless GP_CSR_SYMMETRIZE.  Built on the device as a
+ * counting sort by source row + a sort/unique inside every row (gp_csr.cu).     */
 int gp_csr_create(int64_t num_nodes, int64_t edge_capacity, uint32_t flags, gp_csr_t **out);
 /* async.  d_edge_index: int64 [2, num_edges] row-major (row 0 = src, row 1 = dst). */
 int gp_csr_build(gp_csr_t *csr, const int64_t *d_edge_index, int64_t num_edges, gp_stream_t stream);

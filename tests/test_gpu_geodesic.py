@@ -63,6 +63,43 @@ def test_csr_matches_oracle(dev, n, e, seed, symmetrize):
     assert bool(info["is_symmetric"]) == sym
 
 
+@pytest.mark.parametrize("n", [20000, 1_000_000])
+def test_csr_row_sort_paths(dev, n):
+    """Rows of every length class with repeated edges: the warp register sort (<= 32 / 64 / 128 edges),
+    the CTA bitmap sort (graphs whose node bitmap fits in shared memory), the shared-memory sorting
+    network and the in-place one (rows above 8192 edges when the bitmap does not fit)."""
+    from oracle import geodesic as g
+    rng = np.random.default_rng(n)
+    lens = [0, 1, 2, 31, 32, 33, 40, 63, 64, 65, 100, 127, 128, 129, 200, 511, 1000, 4097, 8192, 8193, 9000]
+    src, dst = [], []
+    for r, ln in enumerate(lens):
+        row = r * 7 + 3
+        cols = rng.choice(n, size=ln, replace=False) if ln else np.zeros(0, dtype=np.int64)
+        rep = rng.integers(1, 4, size=ln)  # every edge 1..3 times
+        cols = np.repeat(cols, rep)
+        src.append(np.full(cols.size, row, dtype=np.int64))
+        dst.append(cols.astype(np.int64))
+    # background edges, some of them into the heavy rows
+    bg = synth.random_digraph(n, 5000, seed=n + 1)
+    src.append(bg[0]); dst.append(bg[1])
+    ei = np.stack([np.concatenate(src), np.concatenate(dst)])
+    ei = np.ascontiguousarray(ei[:, rng.permutation(ei.shape[1])])
+    csr = dev.DeviceCsr(n, ei.shape[1]).build(torch.as_tensor(ei).cuda())
+    for which, fn in (("out", g.out_csr), ("in", g.in_csr)):
+        rp_want, col_want = fn(ei, n, False)
+        rp, col = csr.export(which)
+        assert np.array_equal(rp.cpu().numpy(), rp_want), which
+        assert np.array_equal(col.cpu().numpy(), col_want), which
+    info = csr.info()
+    s_, d_ = g.dedup_edges(ei, n, False)
+    assert info["num_edges"] == s_.size
+    assert info["max_out_degree"] == np.bincount(s_, minlength=n).max()
+    # and the traversal over that CSR (hub chunks, every slot class) stays bit-exact
+    anchors = rng.integers(0, n, 64)
+    hops, _, _ = _gpu_hops_and_features(dev, ei, n, anchors)
+    assert np.array_equal(hops, _oracle_hops(ei, n, anchors))
+
+
 def test_csr_rejects_out_of_range_index(dev):
     ei = torch.tensor([[0, 1, 9], [1, 2, 0]], dtype=torch.int64).cuda()
     csr = dev.DeviceCsr(5, 3).build(ei)
