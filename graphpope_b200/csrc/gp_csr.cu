@@ -413,28 +413,80 @@ __device__ __forceinline__ int warp_row_sort_unique(int *colbuf, int s, int len,
     return base;
 }
 
-// Rows of <= 128 edges: one warp, registers only.  Longer rows are queued for rowsort_big_kernel.
-__global__ void rowsort_small_kernel(const int *__restrict__ ptr, const int *len_in, int *__restrict__ colbuf,
-                                     long long n, int *deg, int *__restrict__ biglist, int *meta, int max_word)
+// Sort + unique of one row of <= 8 edges by ONE thread (19-comparator network in registers).  Most rows
+// of the named graphs are this short, and a warp of such rows reads one contiguous stretch of colbuf.
+__device__ __forceinline__ int thread_row_sort_unique(int *colbuf, int s, int len)
 {
-    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const int lane = lane_id();
-    int mx = 0;
-    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
-        const int s = ptr[r], len = len_in[r];
-        if (len > 128) {
-            if (lane == 0) biglist[atomicAdd(&meta[GP_META_NUM_BIG_ROWS], 1)] = (int)r;
-            continue;
+    int v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = i < len ? colbuf[s + i] : 0x7FFFFFFF;
+#define GP_CE(a, b)                              \
+    {                                            \
+        const int lo = min(v[a], v[b]);          \
+        v[b] = max(v[a], v[b]);                  \
+        v[a] = lo;                               \
+    }
+    GP_CE(0, 1) GP_CE(2, 3) GP_CE(4, 5) GP_CE(6, 7)
+    GP_CE(0, 2) GP_CE(1, 3) GP_CE(4, 6) GP_CE(5, 7)
+    GP_CE(1, 2) GP_CE(5, 6) GP_CE(0, 4) GP_CE(3, 7)
+    GP_CE(1, 5) GP_CE(2, 6)
+    GP_CE(1, 4) GP_CE(3, 6)
+    GP_CE(2, 4) GP_CE(3, 5)
+    GP_CE(3, 4)
+#undef GP_CE
+    int d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i < len && (i == 0 || v[i] != v[i - 1])) {
+            colbuf[s + d] = v[i];
+            ++d;
         }
-        if (len == 0) continue;  // deg[r] already holds 0
-        int d;
-        if (len <= 32) d = warp_row_sort_unique<1>(colbuf, s, len, lane);
-        else if (len <= 64) d = warp_row_sort_unique<2>(colbuf, s, len, lane);
-        else d = warp_row_sort_unique<4>(colbuf, s, len, lane);
-        if (lane == 0 && d != len) deg[r] = d;
-        mx = max(mx, d);
+    }
+    return d;
+}
+
+// Rows of <= 128 edges.  Pass 1: a thread per row for rows of <= 8 edges.  Pass 2: every warp walks the
+// longer rows among its own 32 (registers only: 1, 2 or 4 keys per lane).  Rows above 128 edges are
+// queued for rowsort_big_kernel.
+__global__ void __launch_bounds__(256)
+rowsort_small_kernel(const int *__restrict__ ptr, const int *len_in, int *__restrict__ colbuf, long long n, int *deg,
+                     int *__restrict__ biglist, int *meta, int max_word)
+{
+    const int lane = lane_id();
+    const long long nblk = (n + 255) / 256;
+    int mx = 0;
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const long long r = blk * 256 + threadIdx.x;
+        int s = 0, len = 0;
+        if (r < n) {
+            s = ptr[r];
+            len = len_in[r];
+        }
+        if (len > 0 && len <= 8) {
+            const int d = thread_row_sort_unique(colbuf, s, len);
+            if (d != len) deg[r] = d;
+            mx = max(mx, d);
+        }
+        u32 longer = __ballot_sync(FULL_MASK, len > 8);
+        while (longer) {
+            const int src = __ffs(longer) - 1;
+            longer &= longer - 1;
+            const int rs = __shfl_sync(FULL_MASK, s, src), rlen = __shfl_sync(FULL_MASK, len, src);
+            const long long rr = r - lane + src;
+            if (rlen > 128) {
+                if (lane == 0) biglist[atomicAdd(&meta[GP_META_NUM_BIG_ROWS], 1)] = (int)rr;
+                continue;
+            }
+            int d;
+            if (rlen <= 32) d = warp_row_sort_unique<1>(colbuf, rs, rlen, lane);
+            else if (rlen <= 64) d = warp_row_sort_unique<2>(colbuf, rs, rlen, lane);
+            else d = warp_row_sort_unique<4>(colbuf, rs, rlen, lane);
+            if (lane == 0 && d != rlen) deg[rr] = d;
+            mx = max(mx, d);
+        }
     }
     // one same-address atomic per warp would serialise in L2: only warps that raise the maximum issue one
+    mx = __reduce_max_sync(FULL_MASK, mx);
     if (lane == 0 && mx > 0 && mx > *(volatile int *)&meta[max_word]) atomicMax(&meta[max_word], mx);
 }
 
@@ -649,12 +701,12 @@ int scan_tiles(int64_t count) { return (int)gp_ceil_div(count > 0 ? count : 1, S
 
 // Sorts (and de-duplicates) the row segments [ptr[r], ptr[r] + len[r]) of colbuf in place; len[r] is
 // overwritten with the distinct count where it shrinks; meta[max_word] = max distinct count.
-int sort_rows(gp_csr *c, const int *ptr, int *len, int *colbuf, int max_word, cudaStream_t stream)
+int sort_rows(gp_csr *c, const int *ptr, int *len, int *colbuf, int max_word, bool reset_queue, cudaStream_t stream)
 {
     const int64_t n = c->num_nodes;
-    GP_LAUNCH(set_meta_kernel, 1, 1, 0, stream, c->meta, GP_META_NUM_BIG_ROWS, 0);
-    GP_LAUNCH(rowsort_small_kernel, row_blocks(n), 256, 0, stream, ptr, len, colbuf, n, len, c->biglist, c->meta,
-              max_word);
+    if (reset_queue) GP_LAUNCH(set_meta_kernel, 1, 1, 0, stream, c->meta, GP_META_NUM_BIG_ROWS, 0);
+    GP_LAUNCH(rowsort_small_kernel, launch_blocks(n, 256), 256, 0, stream, ptr, len, colbuf, n, len, c->biglist,
+              c->meta, max_word);
     GP_LAUNCH(rowsort_big_kernel, gp_sm_count() * 4, BIG_THREADS, c->big_smem_bytes, stream, ptr, len, colbuf, len,
               c->biglist, c->meta, max_word, c->bitmap_words);
     return GP_OK;
@@ -707,9 +759,12 @@ extern "C" int gp_csr_create(int64_t num_nodes, int64_t edge_capacity, uint32_t 
     alloc((void **)&c->hubidx, (nn + 1) * sizeof(int));
     alloc((void **)&c->biglist, (size_t)c->big_capacity * sizeof(int));
     alloc((void **)&c->desc, (size_t)c->desc_capacity * sizeof(int4));
-    alloc((void **)&c->meta, GP_META_WORDS * sizeof(int));
-    c->scan_status_words = (size_t)scan_tiles(num_nodes + 1) * ScanStatus<ROW_CH>::STRIDE + 8;
-    alloc((void **)&c->scan_status, c->scan_status_words * sizeof(int));
+    // meta words, then the look-back words of the two scans of a build (separate regions, so one
+    // memset per build clears everything), then the ticket counters
+    c->scan_b_offset = (size_t)scan_tiles(num_nodes + 1) * ScanStatus<1>::STRIDE;
+    c->scan_status_words = c->scan_b_offset + (size_t)scan_tiles(num_nodes + 1) * ScanStatus<ROW_CH>::STRIDE + 8;
+    alloc((void **)&c->meta, (GP_META_WORDS + c->scan_status_words) * sizeof(int));
+    c->scan_status = c->meta != nullptr ? c->meta + GP_META_WORDS : nullptr;
     if (rc != GP_OK) {
         gp_csr_free(c);
         return rc;
@@ -733,7 +788,6 @@ extern "C" int gp_csr_free(gp_csr_t *c)
     cudaFree(c->biglist);
     cudaFree(c->desc);
     cudaFree(c->meta);
-    cudaFree(c->scan_status);
     delete c;
     return GP_OK;
 }
@@ -751,13 +805,12 @@ extern "C" int gp_csr_build(gp_csr_t *c, const int64_t *d_edge_index, int64_t nu
     c->num_input_edges = num_edges;
     c->built = false;
     c->in_built = false;
-    GP_CUDA_CHECK(cudaMemsetAsync(c->meta, 0, GP_META_WORDS * sizeof(int), stream));
+    GP_CUDA_CHECK(cudaMemsetAsync(c->meta, 0, (GP_META_WORDS + c->scan_status_words) * sizeof(int), stream));
     if (n > 0) {
         const long long *ei = (const long long *)d_edge_index;
         const int tiles = scan_tiles(n + 1);
         int *ticket_a = c->scan_status + c->scan_status_words - 8, *ticket_b = ticket_a + 1;
         GP_CUDA_CHECK(cudaMemsetAsync(c->deg, 0, (size_t)(n + 1) * sizeof(int), stream));
-        GP_CUDA_CHECK(cudaMemsetAsync(c->scan_status, 0, c->scan_status_words * sizeof(int), stream));
         if (num_edges > 0)
             GP_LAUNCH(count_edges_kernel, launch_blocks(num_edges, 256), 256, 0, stream, ei, num_edges, n, sym, c->deg,
                       c->meta);
@@ -767,13 +820,11 @@ extern "C" int gp_csr_build(gp_csr_t *c, const int64_t *d_edge_index, int64_t nu
         if (num_edges > 0)
             GP_LAUNCH(scatter_edges_kernel, launch_blocks(num_edges, 256), 256, 0, stream, ei, num_edges, n, sym,
                       c->cursor, c->col);
-        GP_TRY(sort_rows(c, c->row_start, c->deg, c->col, GP_META_MAX_DEGREE, stream));  // deg := distinct degree
-        // the first scan used the leading status words: clear them again for the row scan
-        GP_CUDA_CHECK(cudaMemsetAsync(c->scan_status, 0, (size_t)tiles * ScanStatus<1>::STRIDE * sizeof(int), stream));
+        GP_TRY(sort_rows(c, c->row_start, c->deg, c->col, GP_META_MAX_DEGREE, false, stream));  // deg := distinct degree
         RowScanIo rio{c->deg, c->cursor, c->hubidx, c->meta, n};  // cursor := rank of the row inside its class
         gp_count_launch();
-        chained_scan_kernel<ROW_CH, RowScanIo><<<scan_tiles(n), SCAN_THREADS, 0, stream>>>(rio, n, c->scan_status,
-                                                                                         ticket_b);
+        chained_scan_kernel<ROW_CH, RowScanIo><<<scan_tiles(n), SCAN_THREADS, 0, stream>>>(
+            rio, n, c->scan_status + c->scan_b_offset, ticket_b);
         GP_LAUNCH(desc_kernel, launch_blocks(n, 256), 256, 0, stream, c->row_start, c->deg, c->cursor, c->hubidx, c->meta,
                   n, c->desc);
     }
@@ -809,7 +860,7 @@ int gp_csr_ensure_in(gp_csr *c, cudaStream_t stream)
         GP_LAUNCH(scatter_in_kernel, row_blocks(n), 256, 0, stream, c->row_start, c->deg, c->col, n, c->cursor,
                   c->col_in);
         // the transposed rows hold no duplicates: sorting them in place restores ascending order
-        GP_TRY(sort_rows(c, c->rowptr_in, c->deg_in, c->col_in, GP_META_SCRATCH, stream));
+        GP_TRY(sort_rows(c, c->rowptr_in, c->deg_in, c->col_in, GP_META_SCRATCH, true, stream));
         GP_LAUNCH(compare_csr_kernel, row_blocks(n), 256, 0, stream, c->row_start, c->deg, c->col, c->rowptr_in,
                   c->col_in, n, c->meta);
     }

@@ -53,9 +53,10 @@ struct gp_csr {
     int *hubidx = nullptr;      // [N + 1] index among the hub rows (hub rows only)
     int *biglist = nullptr;     // [big_capacity] rows queued for the CTA-wide row sort
     int4 *desc = nullptr;       // [desc_capacity] {row, first edge, count | chunks << 8, hub index or -1}
-    int *meta = nullptr;        // [GP_META_WORDS]
+    int *meta = nullptr;        // [GP_META_WORDS], followed in the same allocation by scan_status
     int *scan_status = nullptr; // look-back words of the chained scans + ticket counters in the last 8 words
     size_t scan_status_words = 0;
+    size_t scan_b_offset = 0;   // first status word of the second scan of a build
     int bitmap_words = 0;       // ceil(N / 32) if the long-row sort may use a node bitmap in shared memory, else 0
     int big_smem_bytes = 0;     // dynamic shared memory of rowsort_big_kernel
 };

@@ -143,7 +143,7 @@ __device__ __forceinline__ u64 grid_barrier_flags(u64 *bar_word, u32 nblocks, bo
         do {
             v = ld_relaxed_u64(bar_word);  // relaxed polling: an acquire load would flush this SM's L1 each time
         } while ((u32)(v & GP_BAR_FIELD) < nblocks);
-        u32 dummy;
+        u32 dummy;  // one acquire load after the relaxed polling (measured faster than fence.acq_rel here)
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dummy) : "l"(bar_word) : "memory");
         *s_bcast = v;
     }
@@ -673,19 +673,26 @@ extern "C" int gp_msbfs_create(const gp_csr_t *csr, int64_t max_anchors, gp_msbf
             rc = (e == cudaErrorMemoryAllocation) ? GP_ERR_OOM : GP_ERR_CUDA;
         }
     };
-    // result block R[0..31] (reached mask, 15 first-reached-at-hop arrays, 16 deep-hop bit planes),
-    // then the seed frontier and the ping-pong pair
-    alloc((void **)&h->seen, (size_t)GP_BFS_RESULT_ARRAYS * words * sizeof(u64));
-    alloc((void **)&h->fr_a, 3 * words * sizeof(u64));
-    alloc((void **)&h->live, 3 * GP_BFS_MAX_LANE_WORDS * sizeof(u64));
+    // lane state, one allocation: seed frontier, then the result block R[0..31] (reached mask, 15
+    // first-reached-at-hop arrays, 16 deep-hop bit planes), then the ping-pong pair.  The seed frontier
+    // sits right before R[0] so one memset clears both.
+    alloc((void **)&h->lane_buf, (size_t)(1 + GP_BFS_RESULT_ARRAYS + 2) * words * sizeof(u64));
     h->hub_capacity = csr->hub_capacity;
     alloc((void **)&h->hub_acc, (size_t)h->hub_capacity * (size_t)h->cap_words_per_node * sizeof(u64));
     alloc((void **)&h->hub_cnt, (size_t)h->hub_capacity * (size_t)h->cap_words_per_node * sizeof(u32));
-    alloc((void **)&h->bar, 8 * sizeof(u64));
+    // small per-run state, one allocation cleared by one memset:
+    //   live [3][MAX_LANE_WORDS] u64 | bar [8] u64 | counters [4] u64 | status [ST_WORDS] int | nzmap
     h->nzwords = (h->num_nodes + 31) / 32;
-    alloc((void **)&h->nzmap, 3 * ((size_t)batches * (size_t)h->nzwords + 4) * sizeof(u32));
-    alloc((void **)&h->status, GP_BFS_ST_WORDS * sizeof(int));
-    alloc((void **)&h->counters, 4 * sizeof(u64));
+    h->scratch_bytes = (size_t)(3 * GP_BFS_MAX_LANE_WORDS + 8 + 4) * sizeof(u64) + 16 * sizeof(int) +
+                       3 * ((size_t)batches * (size_t)h->nzwords + 4) * sizeof(u32);
+    alloc((void **)&h->scratch, h->scratch_bytes);
+    if (rc == GP_OK) {
+        h->live = reinterpret_cast<u64 *>(h->scratch);
+        h->bar = h->live + 3 * GP_BFS_MAX_LANE_WORDS;
+        h->counters = h->bar + 8;
+        h->status = reinterpret_cast<int *>(h->counters + 4);
+        h->nzmap = reinterpret_cast<u32 *>(h->status + 16);
+    }
     if (getenv("GP_BFS_TRACE")) alloc((void **)&h->trace, GP_BFS_TRACE_WORDS * sizeof(u64));
     if (rc == GP_OK && (cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess)) {
         gp_set_error("gp_msbfs_create: cudaEventCreate failed");
@@ -703,17 +710,12 @@ extern "C" int gp_msbfs_free(gp_msbfs_t *h)
 {
     if (!h) return GP_OK;
     gp_drop_graphs(h);
-    cudaFree(h->seen);
-    cudaFree(h->fr_a);
-    cudaFree(h->live);
+    cudaFree(h->lane_buf);
+    cudaFree(h->scratch);
     cudaFree(h->hub_acc);
     cudaFree(h->hub_cnt);
-    cudaFree(h->bar);
-    cudaFree(h->nzmap);
     cudaFree(h->packed);
     cudaFree(h->deep_flag);
-    cudaFree(h->status);
-    cudaFree(h->counters);
     cudaFree(h->trace);
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     if (h->ev_stop) cudaEventDestroy(h->ev_stop);
@@ -739,19 +741,18 @@ extern "C" int gp_msbfs_run(gp_msbfs_t *h, const int64_t *d_anchors, int64_t num
     h->ran = false;
     const int64_t n = h->num_nodes;
     const size_t words = (size_t)wb * batches * (size_t)n;
+    h->seeds = h->lane_buf;
+    h->seen = h->lane_buf + words;  // R[0]; R[l] = seen + l * words
+    h->fr_a = h->seen + (size_t)GP_BFS_RESULT_ARRAYS * words;
     h->fr_b = h->fr_a + words;
-    h->seeds = h->fr_a + 2 * words;
-    GP_CUDA_CHECK(cudaMemsetAsync(h->status, 0, GP_BFS_ST_WORDS * sizeof(int), stream));
-    GP_CUDA_CHECK(cudaMemsetAsync(h->counters, 0, 4 * sizeof(u64), stream));
+    const int map_stride = (int)(((int64_t)batches * h->nzwords + 3) / 4 * 4);
+    const size_t run_scratch = (size_t)((char *)h->nzmap - (char *)h->scratch) + 3 * (size_t)map_stride * sizeof(u32);
+    GP_CUDA_CHECK(cudaMemsetAsync(h->scratch, 0, run_scratch, stream));  // live, bar, counters, status, maps
     if (n == 0 || num_anchors == 0) {
         h->ran = true;
         return GP_OK;
     }
-    GP_CUDA_CHECK(cudaMemsetAsync(h->seen, 0, words * sizeof(u64), stream));
-    GP_CUDA_CHECK(cudaMemsetAsync(h->seeds, 0, words * sizeof(u64), stream));
-    GP_CUDA_CHECK(cudaMemsetAsync(h->live, 0, 3 * GP_BFS_MAX_LANE_WORDS * sizeof(u64), stream));
-    GP_CUDA_CHECK(cudaMemsetAsync(h->bar, 0, 8 * sizeof(u64), stream));
-    GP_CUDA_CHECK(cudaMemsetAsync(h->nzmap, 0, 3 * (((size_t)batches * (size_t)h->nzwords + 3) / 4 * 4) * sizeof(u32), stream));
+    GP_CUDA_CHECK(cudaMemsetAsync(h->lane_buf, 0, 2 * words * sizeof(u64), stream));  // seeds + reached mask
     if (!h->hub_zeroed) {
         // the kernel leaves these zeroed again (the finalising chunk resets its row's words)
         GP_CUDA_CHECK(cudaMemsetAsync(h->hub_acc, 0, (size_t)h->hub_capacity * h->cap_words_per_node * sizeof(u64), stream));
@@ -769,7 +770,7 @@ extern "C" int gp_msbfs_run(gp_msbfs_t *h, const int64_t *d_anchors, int64_t num
     p.bar = h->bar;
     p.nzmap = h->nzmap;
     p.nzwords = (int)h->nzwords;
-    p.map_stride = (int)(((int64_t)batches * h->nzwords + 3) / 4 * 4);
+    p.map_stride = map_stride;
     p.map_smem_words = 0;  // decided per launch configuration (launch_bfs_cfg)
     p.col = h->csr->col;
     p.meta = h->csr->meta;

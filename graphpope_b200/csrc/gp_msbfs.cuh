@@ -34,6 +34,9 @@ struct gp_msbfs {
     int batches = 0;   // independent 64*wb-anchor batches
     bool ran = false;
 
+    u64 *lane_buf = nullptr; // one allocation: seeds | R[0..31] | ping | pong (pointers below are set per run)
+    void *scratch = nullptr; // one allocation: live | bar | counters | status | nzmap (cleared by one memset per run)
+    size_t scratch_bytes = 0;
     u64 *seen = nullptr;     // result block R[0..31], each [batches][N][wb]; R[0] = reached mask (gp_msbfs.cu)
     u64 *fr_a = nullptr;     // frontier ping (hops >= 16)
     u64 *fr_b = nullptr;     // frontier pong
