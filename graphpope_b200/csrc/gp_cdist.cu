@@ -11,10 +11,13 @@
 // (a node coinciding with a stochastic anchor, true distance 0) the entry is recomputed from the
 // difference form in fp32.
 //
-// Tiling: one CTA = 128 nodes x (<= 256 anchors); the anchor operand (hi and lo, K-major,
-// 128-byte swizzle) stays resident in shared memory for the CTA's lifetime, node tiles are staged
-// tile by tile; accumulators are 128 TMEM lanes x 256 columns.  The kernel is HBM bound by
-// construction (AI ~ 43 flop/B at D = 128): 4*N*D bytes in, 4*N*K bytes out.
+// Tiling: one persistent CTA per SM; a tile = 128 nodes x (<= 256 anchors).  The anchor operand (hi
+// and lo, K-major, 128-byte swizzle) stays resident in shared memory, node tiles are staged by four
+// producer warps, one thread issues the MMAs into one of two 256-column TMEM accumulators, and four
+// epilogue warps drain the other one: thread = node row out of TMEM, a 32 x 32 shared-memory
+// transpose, then thread = anchor column for the per-column min / max and for 128-byte coalesced row
+// stores.  The kernel is HBM bound by construction (AI ~ 43 flop/B at D = 128): 4*N*D bytes in,
+// 4*N*K bytes out; the MinMaxScaler costs a second pass over the inputs, not over the outputs.
 #include "gp_internal.h"
 
 #include <cuda_bf16.h>
@@ -77,7 +80,7 @@ __device__ __forceinline__ void umma_bf16(u32 tmem_d, u64 desc_a, u64 desc_b, u3
 __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity)
 {
     u32 done;
-    do {
+    while (true) {
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
@@ -87,7 +90,9 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity)
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-    } while (!done);
+        if (done) break;
+        __nanosleep(40);  // waiting warps share their scheduler with the warps they wait for
+    }
 }
 
 // Orderable-int encoding so float min/max can use integer atomics for any sign.
@@ -98,200 +103,329 @@ __device__ __forceinline__ int f2ord(float f)
 }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
 
-// Stage `rows` fp32 rows of length D (row-major, leading dim D) as bf16 hi / lo operands in the
-// canonical K-major SWIZZLE_128B layout: [D/64 chunks][rows_pad][128 B], 16-byte column c of row r
-// stored at column c ^ (r & 7).  Rows >= valid are zero.  Also writes the exact fp32 row norms.
-template <int D>
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u32 bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit(u32 bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 8 fp32 values -> one 16-byte group of bf16 "hi" and one of bf16 "lo" (x = hi + lo + O(2^-17 x)),
+// stored at 16-byte column c ^ (row & 7) of the row's 128-byte swizzle line; returns the sum of squares.
+__device__ __forceinline__ float split_store8(const float4 a, const float4 b, unsigned char *s_hi, unsigned char *s_lo,
+                                              size_t off)
+{
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    u32 hi[4], lo[4];
+    float ss = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float x0 = x[2 * i], x1 = x[2 * i + 1];
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+        hi[i] = (u32)__bfloat16_as_ushort(h0) | ((u32)__bfloat16_as_ushort(h1) << 16);
+        lo[i] = (u32)__bfloat16_as_ushort(l0) | ((u32)__bfloat16_as_ushort(l1) << 16);
+        ss = fmaf(x0, x0, ss);
+        ss = fmaf(x1, x1, ss);
+    }
+    *reinterpret_cast<uint4 *>(s_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4 *>(s_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    return ss;
+}
+
+// Stage `rows_pad` fp32 rows of length D (row-major, leading dim D) as bf16 hi / lo operands in the
+// canonical K-major SWIZZLE_128B layout: [D/64 chunks][rows_pad][128 B].  Rows >= valid are zero.
+// Also writes the exact fp32 row norms.  `nthreads` consecutive threads starting at `t0` take part;
+// a warp reads whole rows (32 bytes per lane), UNROLL row groups in flight per thread.
+template <int D, int UNROLL>
 __device__ __forceinline__ void stage_operand(const float *__restrict__ src, long long first_row, long long valid,
-                                              int rows_pad, unsigned char *s_hi, unsigned char *s_lo,
-                                              float *s_norm)
+                                              int rows_pad, unsigned char *s_hi, unsigned char *s_lo, float *s_norm,
+                                              int t, int nthreads)
 {
     constexpr int GROUPS = D / 8;  // 8-element (16-byte bf16) groups per row
     const int total = rows_pad * GROUPS;
-    for (int g = threadIdx.x; g < total; g += CD_THREADS) {
-        const int row = g / GROUPS, kg = g % GROUPS;
-        float x[8];
-        if ((long long)row < valid) {
-            const float4 *p = reinterpret_cast<const float4 *>(src + (size_t)(first_row + row) * D + kg * 8);
-            const float4 a = __ldg(p), b = __ldg(p + 1);
-            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
-            x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-        } else {
+    for (int g0 = t; g0 < total; g0 += nthreads * UNROLL) {
+        float4 a[UNROLL], b[UNROLL];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = 0.0f;
+        for (int u = 0; u < UNROLL; ++u) {
+            const int g = g0 + u * nthreads;
+            const int row = g / GROUPS, kg = g % GROUPS;
+            a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            b[u] = a[u];
+            if (g < total && (long long)row < valid) {
+                const float4 *q = reinterpret_cast<const float4 *>(src + (size_t)(first_row + row) * D + kg * 8);
+                a[u] = __ldg(q);
+                b[u] = __ldg(q + 1);
+            }
         }
-        u32 hi[4], lo[4];
-        float ss = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float x0 = x[2 * i], x1 = x[2 * i + 1];
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-            hi[i] = (u32)__bfloat16_as_ushort(h0) | ((u32)__bfloat16_as_ushort(h1) << 16);
-            lo[i] = (u32)__bfloat16_as_ushort(l0) | ((u32)__bfloat16_as_ushort(l1) << 16);
-            ss = fmaf(x0, x0, ss);
-            ss = fmaf(x1, x1, ss);
+        for (int u = 0; u < UNROLL; ++u) {
+            const int g = g0 + u * nthreads;
+            const int row = g / GROUPS, kg = g % GROUPS;
+            const int chunk = kg / 8, c = kg % 8;
+            const size_t off = (size_t)chunk * rows_pad * 128 + (size_t)row * 128 + (size_t)((c ^ (row & 7)) * 16);
+            float ss = 0.0f;
+            if (g < total) ss = split_store8(a[u], b[u], s_hi, s_lo, off);
+            // row norm: the GROUPS threads of a row are consecutive lanes (GROUPS = 8 or 16 divides 32)
+#pragma unroll
+            for (int m = GROUPS / 2; m; m >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, m);
+            if (g < total && kg == 0) s_norm[row] = ss;
         }
-        const int chunk = kg / 8, c = kg % 8;
-        const size_t off = (size_t)chunk * rows_pad * 128 + (size_t)row * 128 + (size_t)((c ^ (row & 7)) * 16);
-        *reinterpret_cast<uint4 *>(s_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4 *>(s_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        // row norm: the GROUPS threads of a row are consecutive lanes (GROUPS = 8 or 16 divides 32)
-#pragma unroll
-        for (int m = GROUPS / 2; m; m >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, m);
-        if (kg == 0) s_norm[row] = ss;
     }
 }
 
+// Euclidean entries where xx - 2 dot + aa cancels (a node coinciding with an anchor): recomputed from the
+// differences in fp32.  Kept out of line: it is rare, and the epilogue loop must stay small enough
+// for the instruction cache (the first version of this kernel was 160 KB of SASS and spent most of
+// its time waiting for instruction fetches).
 template <int D>
-__global__ void __launch_bounds__(CD_THREADS, 1) cdist_kernel(CdistParams p, int n_pad)
+__device__ __noinline__ float diff_form_d2(const float *__restrict__ xr, const float *__restrict__ ar)
+{
+    float s = 0.0f;
+    for (int t = 0; t < D; ++t) {
+        const float df = __ldg(xr + t) - __ldg(ar + t);
+        s = fmaf(df, df, s);
+    }
+    return s;
+}
+
+// Warp roles: warps 0-7 epilogue (TMEM lane quadrant = warp id % 4, column half = warp id / 4: a lone
+// warp per scheduler cannot hide its own ALU latency), warps 8-11 operand producers, warp 12 issues
+// the MMAs.  Per 128-row tile: producers stage A (hi, lo) once the previous tile's
+// MMAs have released the buffer; the MMA warp accumulates hi*hi + hi*lo + lo*hi into one of two
+// TMEM accumulators; the epilogue of tile i overlaps the staging and MMAs of tile i + 1.
+constexpr int CD_EPI_WARPS = 8;
+constexpr int CD_PROD_WARPS = 4;
+constexpr int CD_THREADS2 = 32 * (CD_EPI_WARPS + CD_PROD_WARPS + 1);
+constexpr int CD_TR_LD = 17;  // padded leading dimension of the 32 x 16 transpose tiles
+
+template <int D>
+__global__ void __launch_bounds__(CD_THREADS2, 1) cdist_kernel(CdistParams p, int n_pad, int write_out, int apply_scale,
+                                                               int track_minmax)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // carve: B hi | B lo | A hi | A lo (each 1024-aligned), then norms + barrier + tmem address
+    // carve: B hi | B lo | A hi | A lo (each 1024-aligned), then transpose tiles, norms, scales, barriers
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const size_t b_bytes = (size_t)(D / CD_KCHUNK) * n_pad * 128;
     const size_t a_bytes = (size_t)(D / CD_KCHUNK) * CD_TILE_M * 128;
     unsigned char *sB_hi = smem, *sB_lo = sB_hi + b_bytes;
     unsigned char *sA_hi = sB_lo + b_bytes, *sA_lo = sA_hi + a_bytes;
-    float *s_an = reinterpret_cast<float *>(sA_lo + a_bytes);
-    float *s_xn = s_an + CD_MAX_N;
-    u64 *s_bar = reinterpret_cast<u64 *>(s_xn + CD_TILE_M);
-    u32 *s_tmem = reinterpret_cast<u32 *>(s_bar + 1);
+    float *s_tr = reinterpret_cast<float *>(sA_lo + a_bytes);       // [8 warps][32][CD_TR_LD]
+    float *s_an = s_tr + CD_EPI_WARPS * 32 * CD_TR_LD;              // [CD_MAX_N] anchor norms
+    float *s_xn = s_an + CD_MAX_N;                                  // [3][CD_TILE_M] node norms, by tile % 3
+    float *s_scale = s_xn + 3 * CD_TILE_M;                          // [CD_MAX_N]
+    float *s_shift = s_scale + CD_MAX_N;                            // [CD_MAX_N]
+    float *s_ian = s_shift + CD_MAX_N;                              // [CD_MAX_N] 1 / |anchor| (0 for a zero row)
+    float *s_cmm = s_ian + CD_MAX_N;                                // [8 warps][2][CD_MAX_N / 2] running column min / max
+    u64 *s_bar = reinterpret_cast<u64 *>(s_cmm + CD_EPI_WARPS * CD_MAX_N);  // a_full, a_empty, acc_full[2], acc_empty[2]
+    u32 *s_tmem = reinterpret_cast<u32 *>(s_bar + 6);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long col_tile = blockIdx.y;
     const long long k0 = col_tile * CD_MAX_N;
     const long long kvalid = min((long long)CD_MAX_N, p.k - k0);
+    const u32 bar_a_full = smem_u32(s_bar + 0), bar_a_empty = smem_u32(s_bar + 1);
+    const u32 bar_acc_full = smem_u32(s_bar + 2), bar_acc_empty = smem_u32(s_bar + 4);  // [2] each, 8 bytes apart
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
-                     "r"(256u)
+                     "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(s_bar)), "r"(1u) : "memory");
+        mbar_init(bar_a_full, CD_PROD_WARPS * 32);
+        mbar_init(bar_a_empty, 1);
+        mbar_init(bar_acc_full, 1);
+        mbar_init(bar_acc_full + 8, 1);
+        mbar_init(bar_acc_empty, CD_EPI_WARPS * 32);
+        mbar_init(bar_acc_empty + 8, CD_EPI_WARPS * 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // anchors of this column tile: resident for the CTA's lifetime
-    stage_operand<D>(p.anc, k0, kvalid, n_pad, sB_hi, sB_lo, s_an);
+    // anchors of this column tile: resident for the CTA's lifetime (all threads help)
+    stage_operand<D, 2>(p.anc, k0, kvalid, n_pad, sB_hi, sB_lo, s_an, tid, CD_THREADS2 / 32 * 32);
+    for (int c = tid; c < n_pad; c += CD_THREADS2) {
+        float scale = 1.0f, shift = 0.0f;
+        if (apply_scale && c < kvalid) {
+            // MinMaxScaler.transform (utils.py:176): X * scale + min_, scale = 1/range (range < 10 eps -> 1)
+            const float dmin = ord2f(reinterpret_cast<const int *>(p.colmin)[k0 + c]);
+            const float dmax = ord2f(reinterpret_cast<const int *>(p.colmax)[k0 + c]);
+            float range = dmax - dmin;
+            if (range < 10.0f * 1.1920929e-07f) range = 1.0f;  // sklearn _handle_zeros_in_scale
+            scale = __fdiv_rn(1.0f, range);
+            shift = __fsub_rn(0.0f, __fmul_rn(dmin, scale));
+        }
+        s_scale[c] = scale;
+        s_shift[c] = shift;
+    }
+    __syncthreads();  // s_an complete
+    for (int c = tid; c < n_pad; c += CD_THREADS2) s_ian[c] = s_an[c] > 0.0f ? rsqrtf(s_an[c]) : 0.0f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const u32 tmem_base = *s_tmem;
-    const u32 idesc = make_idesc(CD_TILE_M, n_pad);
-    const u32 bar = smem_u32(s_bar);
-    u32 parity = 0;
-
     const long long row_tiles = (p.n + CD_TILE_M - 1) / CD_TILE_M;
-    for (long long tile = blockIdx.x; tile < row_tiles; tile += gridDim.x) {
-        const long long r0 = tile * CD_TILE_M;
-        const long long rvalid = min((long long)CD_TILE_M, p.n - r0);
-        stage_operand<D>(p.emb, r0, rvalid, CD_TILE_M, sA_hi, sA_lo, s_xn);
-        // generic-proxy smem writes -> visible to the tensor core's async proxy
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            u32 acc = 0;
-#pragma unroll
-            for (int term = 0; term < 3; ++term) {
-                const unsigned char *a_src = term == 2 ? sA_lo : sA_hi;  // hi*hi, hi*lo, lo*hi
-                const unsigned char *b_src = term == 1 ? sB_lo : sB_hi;
-#pragma unroll
-                for (int kc = 0; kc < D / CD_KCHUNK; ++kc) {
-#pragma unroll
-                    for (int ks = 0; ks < CD_KCHUNK / 16; ++ks) {
-                        const u64 da = make_sw128_desc(smem_u32(a_src + (size_t)kc * CD_TILE_M * 128 + ks * 32));
-                        const u64 db = make_sw128_desc(smem_u32(b_src + (size_t)kc * n_pad * 128 + ks * 32));
-                        umma_bf16(tmem_base, da, db, idesc, acc);
-                        acc = 1;
-                    }
-                }
-            }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-                         : "memory");
-        }
-        mbar_wait(bar, parity);
-        parity ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-        // epilogue: thread = one node row (TMEM lane), 16 anchor columns per tcgen05.ld
-        const int rloc = warp * 32 + lane;
-        const long long row = r0 + rloc;
-        const float xx = s_xn[rloc];
-        const float inv_xn = xx > 0.0f ? rsqrtf(xx) : 0.0f;
-        for (int c0 = 0; c0 < n_pad; c0 += 16) {
-            u32 v[16];
-            const u32 taddr = tmem_base + ((u32)(warp * 32) << 16) + (u32)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
-                "%14, %15}, [%16];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                : "r"(taddr)
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < p.n) {
-                float res[16];
+    if (warp >= CD_EPI_WARPS && warp < CD_EPI_WARPS + CD_PROD_WARPS) {
+        // ------------------------------------------------------------ producers
+        const int pt = tid - CD_EPI_WARPS * 32;
+        long long it = 0;
+        for (long long tile = blockIdx.x; tile < row_tiles; tile += gridDim.x, ++it) {
+            const long long r0 = tile * CD_TILE_M;
+            const long long rvalid = min((long long)CD_TILE_M, p.n - r0);
+            if (it > 0) mbar_wait(bar_a_empty, (u32)((it - 1) & 1));  // the MMAs of the previous tile have read A
+            stage_operand<D, 8>(p.emb, r0, rvalid, CD_TILE_M, sA_hi, sA_lo, s_xn + (it % 3) * CD_TILE_M, pt,
+                                CD_PROD_WARPS * 32);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core reads
+            mbar_arrive(bar_a_full);
+        }
+    } else if (warp == CD_EPI_WARPS + CD_PROD_WARPS) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const u32 idesc = make_idesc(CD_TILE_M, n_pad);
+            long long it = 0;
+            for (long long tile = blockIdx.x; tile < row_tiles; tile += gridDim.x, ++it) {
+                const int st = (int)(it & 1);
+                const long long use = it >> 1;  // earlier uses of this accumulator
+                mbar_wait(bar_a_full, (u32)(it & 1));
+                if (use > 0) mbar_wait(bar_acc_empty + 8 * st, (u32)((use - 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const u32 tmem_d = tmem_base + (u32)(st * CD_MAX_N);
+                u32 acc = 0;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int c = c0 + j;
-                    const float dot = __uint_as_float(v[j]);
-                    const float aa = s_an[c];
-                    float r;
-                    if (p.mode == GP_CDIST_EUCLIDEAN) {
-                        float d2 = xx - 2.0f * dot + aa;
-                        if (d2 < 1.0e-3f * (xx + aa) && c < kvalid) {
-                            // cancellation zone: recompute from differences (exact 0 for identical rows)
-                            const float *xr = p.emb + (size_t)row * D, *ar = p.anc + (size_t)(k0 + c) * D;
-                            float s = 0.0f;
-                            for (int t = 0; t < D; ++t) {
-                                const float df = __ldg(xr + t) - __ldg(ar + t);
-                                s = fmaf(df, df, s);
-                            }
-                            d2 = s;
+                for (int term = 0; term < 3; ++term) {
+                    const unsigned char *a_src = term == 2 ? sA_lo : sA_hi;  // hi*hi, hi*lo, lo*hi
+                    const unsigned char *b_src = term == 1 ? sB_lo : sB_hi;
+#pragma unroll
+                    for (int kc = 0; kc < D / CD_KCHUNK; ++kc) {
+#pragma unroll
+                        for (int ks = 0; ks < CD_KCHUNK / 16; ++ks) {
+                            const u64 da = make_sw128_desc(smem_u32(a_src + (size_t)kc * CD_TILE_M * 128 + ks * 32));
+                            const u64 db = make_sw128_desc(smem_u32(b_src + (size_t)kc * n_pad * 128 + ks * 32));
+                            umma_bf16(tmem_d, da, db, idesc, acc);
+                            acc = 1;
                         }
-                        r = sqrtf(fmaxf(d2, 0.0f));
-                    } else {
-                        const float inv_an = aa > 0.0f ? rsqrtf(aa) : 0.0f;
-                        const float sim = dot * inv_xn * inv_an;
-                        r = p.mode == GP_CDIST_COSINE_SIMILARITY ? sim : fminf(fmaxf(1.0f - sim, 0.0f), 2.0f);
                     }
-                    res[j] = r;
                 }
-                float *orow = p.out + (size_t)row * p.ld_out + p.col_offset + k0 + c0;
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c0 + j < kvalid) orow[j] = res[j];
+                umma_commit(bar_a_empty);            // A may be overwritten
+                umma_commit(bar_acc_full + 8 * st);  // accumulator ready
             }
         }
-        // all warps have drained TMEM and sA before the next tile overwrites them
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+    } else {
+        // ------------------------------------------------------------ epilogue
+        const int quad = warp & 3, half = warp >> 2;         // TMEM lane quadrant, column half
+        const int ncols = n_pad >> 1, cbase = half * ncols;  // this warp's columns [cbase, cbase + ncols)
+        float *tr = s_tr + warp * 32 * CD_TR_LD;
+        float *wmin = s_cmm + warp * CD_MAX_N, *wmax = wmin + CD_MAX_N / 2;  // running min / max of its columns
+        for (int c = lane; c < CD_MAX_N / 2; c += 32) {
+            wmin[c] = INFINITY;
+            wmax[c] = -INFINITY;
+        }
+        __syncwarp();
+        const int mode = p.mode;
+        const int rsel = lane >> 4, cl = lane & 15;  // transposed phase: two rows x 16 columns per step
+        long long it = 0;
+        for (long long tile = blockIdx.x; tile < row_tiles; tile += gridDim.x, ++it) {
+            const int st = (int)(it & 1);
+            const long long use = it >> 1;
+            const long long r0 = tile * CD_TILE_M + quad * 32;
+            mbar_wait(bar_acc_full + 8 * st, (u32)(use & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long row = r0 + lane;
+            const float xx = s_xn[(it % 3) * CD_TILE_M + quad * 32 + lane];
+            const float inv_xn = xx > 0.0f ? rsqrtf(xx) : 0.0f;
+            const int rows_here = (int)min(32ll, max(0ll, p.n - r0));
+#pragma unroll 1
+            for (int c0 = cbase; c0 < cbase + ncols; c0 += 16) {
+                u32 v[16];
+                const u32 taddr = tmem_base + ((u32)(quad * 32) << 16) + (u32)(st * CD_MAX_N + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+                    "%14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // thread = node row: finish the 16 entries of this row, park them in the transpose tile
+                if (mode == GP_CDIST_EUCLIDEAN) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float aa = s_an[c0 + j];
+                        float d2 = fmaf(-2.0f, __uint_as_float(v[j]), xx + aa);
+                        if (d2 < 1.0e-3f * (xx + aa) && c0 + j < kvalid && row < p.n)
+                            d2 = diff_form_d2<D>(p.emb + (size_t)row * D, p.anc + (size_t)(k0 + c0 + j) * D);
+                        float r;
+                        asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(d2, 0.0f)));
+                        tr[lane * CD_TR_LD + j] = r;
+                    }
+                } else {
+                    const bool sim_mode = mode == GP_CDIST_COSINE_SIMILARITY;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float sim = __uint_as_float(v[j]) * inv_xn * s_ian[c0 + j];
+                        tr[lane * CD_TR_LD + j] = sim_mode ? sim : fminf(fmaxf(1.0f - sim, 0.0f), 2.0f);
+                    }
+                }
+                __syncwarp();
+                // lanes 0-15 / 16-31 = the 16 anchor columns of an even / odd row: running min / max,
+                // scaling, and row stores of 64 contiguous bytes
+                const int c = c0 + cl;
+                const bool cvalid = c < kvalid;
+                const float sc = s_scale[c], sh = s_shift[c];
+                float *ocol = p.out + (size_t)(r0 + rsel) * p.ld_out + p.col_offset + k0 + c;
+                float mn = INFINITY, mx = -INFINITY;
+                if (write_out && cvalid) {
+                    if (apply_scale) {
+#pragma unroll 4
+                        for (int rr = rsel; rr < rows_here; rr += 2)
+                            ocol[(size_t)(rr - rsel) * p.ld_out] = __fadd_rn(__fmul_rn(tr[rr * CD_TR_LD + cl], sc), sh);
+                    } else {
+#pragma unroll 4
+                        for (int rr = rsel; rr < rows_here; rr += 2) ocol[(size_t)(rr - rsel) * p.ld_out] = tr[rr * CD_TR_LD + cl];
+                    }
+                }
+                if (track_minmax) {
+#pragma unroll 4
+                    for (int rr = rsel; rr < rows_here; rr += 2) {
+                        const float val = tr[rr * CD_TR_LD + cl];
+                        mn = fminf(mn, val);
+                        mx = fmaxf(mx, val);
+                    }
+                    mn = fminf(mn, __shfl_xor_sync(FULL_MASK, mn, 16));
+                    mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, 16));
+                    if (lane < 16) {
+                        wmin[c - cbase] = fminf(wmin[c - cbase], mn);
+                        wmax[c - cbase] = fmaxf(wmax[c - cbase], mx);
+                    }
+                }
+                __syncwarp();
+            }
+            // this warp has drained its part of the accumulator
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(bar_acc_empty + 8 * st);
+        }
+        if (track_minmax) {
+            for (int c = lane; c < ncols; c += 32) {
+                if (cbase + c < kvalid && wmin[c] <= wmax[c]) {
+                    atomicMin(reinterpret_cast<int *>(p.colmin) + k0 + cbase + c, f2ord(wmin[c]));
+                    atomicMax(reinterpret_cast<int *>(p.colmax) + k0 + cbase + c, f2ord(wmax[c]));
+                }
+            }
+        }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
-}
-
-// Column min / max of out[:, col_offset : col_offset + k] (MinMaxScaler.fit, utils.py:175).
-__global__ void __launch_bounds__(256) col_minmax_kernel(const float *__restrict__ out, long long n, long long k,
-                                                         long long ld, long long col_offset, int *cmin, int *cmax)
-{
-    const long long rows_per_block = (n + gridDim.y - 1) / gridDim.y;
-    const long long r_begin = (long long)blockIdx.y * rows_per_block;
-    const long long r_end = min(n, r_begin + rows_per_block);
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= k || r_begin >= r_end) return;
-    float mn = INFINITY, mx = -INFINITY;
-    for (long long r = r_begin; r < r_end; ++r) {
-        const float v = out[(size_t)r * ld + col_offset + c];
-        mn = fminf(mn, v);
-        mx = fmaxf(mx, v);
-    }
-    atomicMin(cmin + c, f2ord(mn));
-    atomicMax(cmax + c, f2ord(mx));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
 __global__ void minmax_init_kernel(int *cmin, int *cmax, long long k)
@@ -303,29 +437,10 @@ __global__ void minmax_init_kernel(int *cmin, int *cmax, long long k)
     }
 }
 
-// MinMaxScaler.transform (utils.py:176): X * scale + min_, scale = 1/range (range < 10 eps -> 1).
-__global__ void __launch_bounds__(256) col_scale_kernel(float *__restrict__ out, long long n, long long k,
-                                                        long long ld, long long col_offset,
-                                                        const int *__restrict__ cmin, const int *__restrict__ cmax)
-{
-    const long long total = n * k;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const long long r = i / k, c = i - r * k;
-        const float dmin = ord2f(cmin[c]), dmax = ord2f(cmax[c]);
-        float range = dmax - dmin;
-        if (range < 10.0f * 1.1920929e-07f) range = 1.0f;  // sklearn _handle_zeros_in_scale
-        const float scale = __fdiv_rn(1.0f, range);
-        const float mn = __fsub_rn(0.0f, __fmul_rn(dmin, scale));
-        float *q = out + (size_t)r * ld + col_offset + c;
-        *q = __fadd_rn(__fmul_rn(*q, scale), mn);
-    }
-}
-
 size_t cdist_smem_bytes(int d, int n_pad)
 {
     const size_t b = (size_t)(d / CD_KCHUNK) * n_pad * 128, a = (size_t)(d / CD_KCHUNK) * CD_TILE_M * 128;
-    return 1024 + 2 * b + 2 * a + sizeof(float) * (CD_MAX_N + CD_TILE_M) + 64;
+    return 1024 + 2 * b + 2 * a + sizeof(float) * (CD_EPI_WARPS * 32 * CD_TR_LD + 4 * CD_MAX_N + 3 * CD_TILE_M + CD_EPI_WARPS * CD_MAX_N) + 128;
 }
 
 }  // namespace
@@ -360,34 +475,54 @@ extern "C" int gp_cdist_minmax(const float *d_emb, const float *d_anchor_emb, in
     p.colmin = p.colmax = nullptr;
     const int64_t col_tiles = gp_ceil_div(num_anchors, CD_MAX_N);
     const int64_t ktile = num_anchors < CD_MAX_N ? num_anchors : CD_MAX_N;
-    const int n_pad = (int)(gp_ceil_div(ktile, 16) * 16);  // UMMA N: multiple of 16 at M = 128
+    const int n_pad = (int)(gp_ceil_div(ktile, 32) * 32);  // UMMA N (multiple of 16 at M = 128); the epilogue works in 32s
     const size_t smem = cdist_smem_bytes((int)dim, n_pad);
     const int64_t row_tiles = gp_ceil_div(num_nodes, CD_TILE_M);
     int grid_x = gp_sm_count();
     if (row_tiles < grid_x) grid_x = (int)row_tiles;
-    gp_count_launch();
-    if (dim == 128) {
-        GP_CUDA_CHECK(cudaFuncSetAttribute(cdist_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cdist_kernel<128><<<dim3(grid_x, (unsigned)col_tiles), CD_THREADS, smem, stream>>>(p, n_pad);
-    } else {
-        GP_CUDA_CHECK(cudaFuncSetAttribute(cdist_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cdist_kernel<64><<<dim3(grid_x, (unsigned)col_tiles), CD_THREADS, smem, stream>>>(p, n_pad);
-    }
-    GP_CUDA_CHECK(cudaGetLastError());
-    if (apply_minmax) {
-        int *mm = nullptr;
-        GP_CUDA_CHECK(cudaMallocAsync((void **)&mm, sizeof(int) * 2 * (size_t)num_anchors, stream));
-        int *cmin = mm, *cmax = mm + num_anchors;
-        GP_LAUNCH(minmax_init_kernel, (unsigned)gp_ceil_div(num_anchors, 256), 256, 0, stream, cmin, cmax, num_anchors);
-        const int ysplit = (int)std::min<int64_t>(std::max<int64_t>(1, num_nodes / 256), (int64_t)gp_sm_count() * 2);
-        GP_LAUNCH(col_minmax_kernel, dim3((unsigned)gp_ceil_div(num_anchors, 256), ysplit), 256, 0, stream, d_out,
-                  num_nodes, num_anchors, ld_out, col_offset, cmin, cmax);
-        int64_t blocks = gp_ceil_div(num_nodes * num_anchors, 256);
-        if (blocks > (int64_t)gp_sm_count() * 16) blocks = (int64_t)gp_sm_count() * 16;
-        GP_LAUNCH(col_scale_kernel, (unsigned)blocks, 256, 0, stream, d_out, num_nodes, num_anchors, ld_out,
-                  col_offset, cmin, cmax);
-        GP_CUDA_CHECK(cudaFreeAsync(mm, stream));
+    const dim3 grid(grid_x, (unsigned)col_tiles);
+    auto launch = [&](int write_out, int apply_scale, int track) -> int {
+        gp_count_launch();
+        if (dim == 128) {
+            GP_CUDA_CHECK(cudaFuncSetAttribute(cdist_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cdist_kernel<128><<<grid, CD_THREADS2, smem, stream>>>(p, n_pad, write_out, apply_scale, track);
+        } else {
+            GP_CUDA_CHECK(cudaFuncSetAttribute(cdist_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cdist_kernel<64><<<grid, CD_THREADS2, smem, stream>>>(p, n_pad, write_out, apply_scale, track);
+        }
         GP_CUDA_CHECK(cudaGetLastError());
+        return GP_OK;
+    };
+    if (!apply_minmax) {
+        GP_TRY(launch(1, 0, 0));
+    } else {
+        // MinMaxScaler (utils.py:175-176) without a second trip of the N x K block through HBM: pass 1
+        // computes the block and keeps only the per-column min / max, pass 2 recomputes it (the node
+        // table is L2 resident by then) and writes the scaled values.
+        // stream-ordered scratch from a pool of our own that keeps its memory across synchronisations
+        // (the default pool hands it back to the driver at every sync, ~100 us per call)
+        static cudaMemPool_t pool = nullptr;
+        if (pool == nullptr) {
+            int dev = 0;
+            GP_CUDA_CHECK(cudaGetDevice(&dev));
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            GP_CUDA_CHECK(cudaMemPoolCreate(&pool, &props));
+            uint64_t keep = ~0ull;
+            GP_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
+        int *mm = nullptr;
+        GP_CUDA_CHECK(cudaMallocFromPoolAsync((void **)&mm, sizeof(int) * 2 * (size_t)num_anchors, pool, stream));
+        p.colmin = reinterpret_cast<float *>(mm);
+        p.colmax = reinterpret_cast<float *>(mm + num_anchors);
+        GP_LAUNCH(minmax_init_kernel, (unsigned)gp_ceil_div(num_anchors, 256), 256, 0, stream, mm, mm + num_anchors,
+                  num_anchors);
+        int rc = launch(0, 0, 1);
+        if (rc == GP_OK) rc = launch(1, 1, 0);
+        GP_CUDA_CHECK(cudaFreeAsync(mm, stream));
+        GP_TRY(rc);
     }
     return GP_OK;
 }
