@@ -212,7 +212,9 @@ __global__ void __launch_bounds__(CD_THREADS2, 1) cdist_kernel(CdistParams p, in
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve: B hi | B lo | A hi | A lo (each 1024-aligned), then transpose tiles, norms, scales, barriers
-    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // (an offset, not an integer round trip of the pointer: the compiler must keep seeing shared memory,
+    // or every access below turns into a generic LD / ST)
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const size_t b_bytes = (size_t)(D / CD_KCHUNK) * n_pad * 128;
     const size_t a_bytes = (size_t)(D / CD_KCHUNK) * CD_TILE_M * 128;
     unsigned char *sB_hi = smem, *sB_lo = sB_hi + b_bytes;
@@ -331,6 +333,7 @@ __global__ void __launch_bounds__(CD_THREADS2, 1) cdist_kernel(CdistParams p, in
         }
         __syncwarp();
         const int mode = p.mode;
+        const int kv = (int)kvalid;
         const int rsel = lane >> 4, cl = lane & 15;  // transposed phase: two rows x 16 columns per step
         long long it = 0;
         for (long long tile = blockIdx.x; tile < row_tiles; tile += gridDim.x, ++it) {
@@ -340,6 +343,7 @@ __global__ void __launch_bounds__(CD_THREADS2, 1) cdist_kernel(CdistParams p, in
             mbar_wait(bar_acc_full + 8 * st, (u32)(use & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long long row = r0 + lane;
+            const bool row_ok = row < p.n;
             const float xx = s_xn[(it % 3) * CD_TILE_M + quad * 32 + lane];
             const float inv_xn = xx > 0.0f ? rsqrtf(xx) : 0.0f;
             const int rows_here = (int)min(32ll, max(0ll, p.n - r0));
@@ -357,14 +361,29 @@ __global__ void __launch_bounds__(CD_THREADS2, 1) cdist_kernel(CdistParams p, in
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 // thread = node row: finish the 16 entries of this row, park them in the transpose tile
                 if (mode == GP_CDIST_EUCLIDEAN) {
+                    float d2[16];
+                    u32 fix = 0;  // entries in the cancellation zone (rare): recomputed below, out of the main loop
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float aa = s_an[c0 + j];
-                        float d2 = fmaf(-2.0f, __uint_as_float(v[j]), xx + aa);
-                        if (d2 < 1.0e-3f * (xx + aa) && c0 + j < kvalid && row < p.n)
-                            d2 = diff_form_d2<D>(p.emb + (size_t)row * D, p.anc + (size_t)(k0 + c0 + j) * D);
+                        const float sum = xx + s_an[c0 + j];
+                        d2[j] = fmaf(-2.0f, __uint_as_float(v[j]), sum);
+                        fix |= (d2[j] < 1.0e-3f * sum ? 1u : 0u) << j;
+                    }
+                    if (!row_ok) fix = 0;
+                    while (fix) {
+                        const int j = __ffs(fix) - 1;
+                        fix &= fix - 1;
+                        if (c0 + j < kv) {
+                            const float e = diff_form_d2<D>(p.emb + (size_t)row * D, p.anc + (size_t)(k0 + c0 + j) * D);
+#pragma unroll
+                            for (int t = 0; t < 16; ++t)
+                                if (t == j) d2[t] = e;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
                         float r;
-                        asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(d2, 0.0f)));
+                        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(d2[j], 0.0f)));
                         tr[lane * CD_TR_LD + j] = r;
                     }
                 } else {
@@ -379,7 +398,7 @@ __global__ void __launch_bounds__(CD_THREADS2, 1) cdist_kernel(CdistParams p, in
                 // lanes 0-15 / 16-31 = the 16 anchor columns of an even / odd row: running min / max,
                 // scaling, and row stores of 64 contiguous bytes
                 const int c = c0 + cl;
-                const bool cvalid = c < kvalid;
+                const bool cvalid = c < kv;
                 const float sc = s_scale[c], sh = s_shift[c];
                 float *ocol = p.out + (size_t)(r0 + rsel) * p.ld_out + p.col_offset + k0 + c;
                 float mn = INFINITY, mx = -INFINITY;
