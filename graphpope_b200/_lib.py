@@ -90,6 +90,7 @@ SIGNATURES = {
     "gp_geodesic_embed_host": (c_int, [c_void_p, c_int64, c_int64, c_uint32, c_void_p, c_int64, c_void_p,
                                        c_int64, c_void_p, c_int64, c_int64, c_void_p, POINTER(MsbfsStats)]),
     "gp_host_concat": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64]),
+    "gp_block_to_host": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p]),
     "gp_degree": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gp_pagerank": (c_int, [c_void_p, c_double, c_double, c_int32, c_void_p, POINTER(c_int32), c_void_p]),
     "gp_topk_stable_i32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),

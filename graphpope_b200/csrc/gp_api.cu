@@ -427,6 +427,23 @@ extern "C" int gp_host_concat(const float *h_x, int64_t num_features, const floa
     return GP_OK;
 }
 
+extern "C" int gp_block_to_host(const float *d_block, int64_t num_nodes, int64_t block_cols, float *h_out,
+                                int64_t ld_out, int64_t col_offset, gp_stream_t stream_)
+{
+    GP_REQUIRE(num_nodes >= 0 && block_cols >= 0 && col_offset >= 0 && ld_out >= col_offset + block_cols, GP_ERR_INVALID,
+               "gp_block_to_host: inconsistent sizes");
+    if (num_nodes == 0 || block_cols == 0) return GP_OK;
+    GP_REQUIRE(d_block != nullptr && h_out != nullptr, GP_ERR_INVALID, "gp_block_to_host: NULL argument");
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, h_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    GP_REQUIRE(pinned, GP_ERR_INVALID, "gp_block_to_host: h_out must be pinned host memory");
+    GP_CUDA_CHECK(cudaMemcpy2DAsync(h_out + col_offset, sizeof(float) * (size_t)ld_out, d_block,
+                                    sizeof(float) * (size_t)block_cols, sizeof(float) * (size_t)block_cols,
+                                    (size_t)num_nodes, cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+    return GP_OK;
+}
+
 extern "C" int gp_geodesic_embed_host(const int64_t *h_edge_index, int64_t num_edges, int64_t num_nodes,
                                       uint32_t csr_flags, const int64_t *h_anchors, int64_t num_anchors,
                                       const float *h_x, int64_t num_features, float *h_out, int64_t ld_out,

@@ -177,21 +177,14 @@ __global__ void __launch_bounds__(256) decode_features_bytes_kernel(GpDecodePara
             }
         }
         for (int r = 0; r < p.num_ranks; ++r) {
-            const unsigned char *blk = reinterpret_cast<const unsigned char *>(
-                p.packed ? p.rank_ptr[r] : p.planes0 + (size_t)r * p.rank_stride);
+            const unsigned char *blk = reinterpret_cast<const unsigned char *>(p.planes0 + (size_t)r * p.rank_stride);
             for (int b = 0; b < batches; ++b) {
                 const int col0 = b * 64 * p.wb + lane * 8;  // first of this lane's 8 columns inside the rank
                 if (lane >= row_bytes || col0 >= kr) continue;
                 const unsigned char *rowp = blk + ((size_t)b * p.n + (size_t)u) * row_bytes + lane;
                 const u32 reach = rowp[0];
                 u32 m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-                if (reach && p.packed) {
-                    // hop index already bit-sliced by the owner rank; these loads cross NVLink for peers
-                    m0 = rowp[1 * plane_bytes];
-                    m1 = rowp[2 * plane_bytes];
-                    m2 = rowp[3 * plane_bytes];
-                    m3 = rowp[4 * plane_bytes];
-                } else if (reach) {
+                if (reach) {
 #pragma unroll
                     for (int l = 1; l <= GP_BFS_LEVEL_ARRAYS; ++l) {
                         if (l <= va.levels) {
@@ -210,7 +203,7 @@ __global__ void __launch_bounds__(256) decode_features_bytes_kernel(GpDecodePara
                                   (((m3 >> c) & 1u) << 3);
                     v[c] = ((reach >> c) & 1u) ? s_inv[d] : 0.0f;
                 }
-                if (va.deep && reach && !p.packed) {
+                if (va.deep && reach) {
                     const unsigned char *pl = rowp + (size_t)(1 + GP_BFS_LEVEL_ARRAYS) * plane_bytes;
                     u32 e[GP_BFS_PLANES];
 #pragma unroll
@@ -226,6 +219,69 @@ __global__ void __launch_bounds__(256) decode_features_bytes_kernel(GpDecodePara
                 float4 *dst = reinterpret_cast<float4 *>(orow + p.col_offset + (size_t)r * kr + col0);
                 dst[0] = make_float4(v[0], v[1], v[2], v[3]);
                 dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        }
+    }
+}
+
+// Peer assembly (packed exchange format, gp_decode_peers): same row / lane mapping as the kernel above,
+// but the five bytes of EVERY rank's shard are requested up front, so the NVLink round trips of all
+// peers overlap (one dependent round trip per row instead of two per peer).
+__global__ void __launch_bounds__(256) decode_features_peers_kernel(GpDecodeParams p, int vec_x)
+{
+    __shared__ float s_inv[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_inv[i] = inv_hops((u32)i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int row_bytes = p.wb * 8;
+    const int kr = (int)p.anchors_per_rank;
+    const int batches = (kr + 64 * p.wb - 1) / (64 * p.wb);
+    const size_t plane_bytes = (size_t)p.plane_stride * 8;
+    for (long long u = warp; u < p.n; u += nwarps) {
+        float *orow = p.out + (size_t)u * p.ld_out;
+        for (int b = 0; b < batches; ++b) {
+            const int col0 = b * 64 * p.wb + lane * 8;  // first of this lane's 8 columns inside the rank
+            if (lane >= row_bytes || col0 >= kr) continue;
+            const size_t roff = ((size_t)b * p.n + (size_t)u) * row_bytes + lane;
+            u32 m[GP_MAX_RANKS][GP_PACKED_ARRAYS];
+#pragma unroll
+            for (int r = 0; r < GP_MAX_RANKS; ++r) {
+                if (r < p.num_ranks) {
+                    const unsigned char *rowp = reinterpret_cast<const unsigned char *>(p.rank_ptr[r]) + roff;
+#pragma unroll
+                    for (int a = 0; a < GP_PACKED_ARRAYS; ++a) m[r][a] = rowp[(size_t)a * plane_bytes];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < GP_MAX_RANKS; ++r) {
+                if (r < p.num_ranks) {
+                    const u32 reach = m[r][0];
+                    float v[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const u32 d = ((m[r][1] >> c) & 1u) | (((m[r][2] >> c) & 1u) << 1) | (((m[r][3] >> c) & 1u) << 2) |
+                                      (((m[r][4] >> c) & 1u) << 3);
+                        v[c] = ((reach >> c) & 1u) ? s_inv[d] : 0.0f;
+                    }
+                    float4 *dst = reinterpret_cast<float4 *>(orow + p.col_offset + (size_t)r * kr + col0);
+                    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            }
+        }
+        // x is streamed into columns [0, F) while the peer loads are in flight
+        if (p.x != nullptr) {
+            const float *xrow = p.x + (size_t)u * p.ld_x;
+            if (vec_x) {
+                const float4 *x4 = reinterpret_cast<const float4 *>(xrow);
+                float4 *o4 = reinterpret_cast<float4 *>(orow);
+                const int q = (int)(p.num_features >> 2);
+                for (int i = lane; i < q; i += 32) o4[i] = __ldg(x4 + i);
+                for (int i = (q << 2) + lane; i < (int)p.num_features; i += 32) orow[i] = __ldg(xrow + i);
+            } else {
+                for (int i = lane; i < (int)p.num_features; i += 32) orow[i] = __ldg(xrow + i);
             }
         }
     }
@@ -307,7 +363,9 @@ int gp_launch_decode_features(const GpDecodeParams &p, cudaStream_t stream)
                       (p.ld_out % 4 == 0);
     const int vec_f = aligned16(p.out) && (p.ld_out % 4 == 0) && (p.col_offset % 4 == 0) &&
                       (p.anchors_per_rank % 4 == 0 || p.num_ranks == 1);
-    if (vec_f && p.anchors_per_rank % 8 == 0 && p.anchors_per_rank > 0)
+    if (vec_f && p.anchors_per_rank % 8 == 0 && p.anchors_per_rank > 0 && p.packed)
+        GP_LAUNCH(decode_features_peers_kernel, grid_for(p.n, 8), 256, 0, stream, p, vec_x);
+    else if (vec_f && p.anchors_per_rank % 8 == 0 && p.anchors_per_rank > 0)
         GP_LAUNCH(decode_features_bytes_kernel, grid_for(p.n, 8), 256, 0, stream, p, vec_x);
     else
         GP_LAUNCH(decode_features_kernel, grid_for(p.n, 8), 256, 0, stream, p, k_total, vec_x, vec_f);

@@ -114,18 +114,32 @@ def sharded_geodesic_embed_host(engine, edge_index: torch.Tensor, anchors, x: to
         staging["block_h"] = torch.empty((n, k), dtype=torch.float32).pin_memory()
     staging["ei"].copy_(edge_index, non_blocking=True)
     staging["anchors"].copy_(a, non_blocking=True)
+    lib = _lib.load()
+    direct = out.is_pinned() and out.stride(1) == 1  # strided DMA straight into columns [F, F + K) of `out`
+
+    def device_to_host():
+        if direct:
+            check(lib.gp_block_to_host(_ptr(staging["block_d"]), n, k, _ptr(out), out.stride(0), f,
+                                       c_void_p(torch.cuda.current_stream().cuda_stream)))
+        else:
+            staging["block_h"].copy_(staging["block_d"], non_blocking=True)  # one contiguous DMA, scattered below
+
     if peer is not None:
         _, deep = peer.run(staging["ei"], staging["anchors"], None, staging["block_d"])
     else:
         deep = None
         sharded_geodesic_features(engine, staging["ei"], staging["anchors"], None, staging["block_d"], group)
-    staging["block_h"].copy_(staging["block_d"], non_blocking=True)  # one contiguous DMA
+    device_to_host()
+    # concat_into_features (utils.py:129-135): x goes into columns [0, F) on the host while the GPU works
+    if x is not None:
+        check(lib.gp_host_concat(_ptr(x), f, None, 0, n, _ptr(out), out.stride(0)))
     torch.cuda.current_stream().synchronize()
     if deep is not None and int(deep.item()) != 0:  # hops > 15 somewhere: redo through the all-gather path
         sharded_geodesic_features(engine, staging["ei"], staging["anchors"], None, staging["block_d"], group)
-        staging["block_h"].copy_(staging["block_d"], non_blocking=True)
+        device_to_host()
         torch.cuda.current_stream().synchronize()
-    check(_lib.load().gp_host_concat(_ptr(x), f, _ptr(staging["block_h"]), k, n, _ptr(out), out.stride(0)))
+    if not direct:
+        check(lib.gp_host_concat(None, f, _ptr(staging["block_h"]), k, n, _ptr(out), out.stride(0)))
     return out
 
 

@@ -201,6 +201,12 @@ int gp_geodesic_embed_host(const int64_t *h_edge_index, int64_t num_edges, int64
  * [N, block_cols] block: out[:, 0:F] = x, out[:, F:F+block_cols] = block, threaded row copies.      */
 int gp_host_concat(const float *h_x, int64_t num_features, const float *h_block, int64_t block_cols,
                    int64_t num_nodes, float *h_out, int64_t ld_out);
+/* async.  Device block [N, block_cols] (contiguous) -> columns [col_offset, col_offset + block_cols) of
+ * the PINNED host matrix h_out (leading dimension ld_out) as one strided DMA, so the host only has to
+ * copy x (gp_host_concat with h_block = NULL) while the transfer runs.  GP_ERR_INVALID if h_out is
+ * pageable (a pageable 2-D copy degenerates into N small transfers: stage it instead).              */
+int gp_block_to_host(const float *d_block, int64_t num_nodes, int64_t block_cols, float *h_out, int64_t ld_out,
+                     int64_t col_offset, gp_stream_t stream);
 
 /* ------------------------------------------------------------------ samplers
  * degree_centrality (utils.py:38-42): in+out degree over de-duplicated edges

@@ -111,3 +111,33 @@ def test_device_entry_points_fail_loudly_without_a_gpu():
         utils.get_geodesic_distance_vector(d, 6)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         utils.sample_anchor_nodes(d, 1, "degree_centrality")
+
+
+def test_host_concat_matches_torch_cat():
+    """gp_host_concat (concat_into_features, utils.py:129-135, for host buffers) is pure host code: the
+    worker pool + streaming-store row copy must equal torch.cat for aligned and odd shapes."""
+    import ctypes
+
+    import numpy as np
+    import torch
+
+    from graphpope_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for n, f, k in ((1, 1, 1), (7, 3, 5), (1000, 500, 256), (40000, 37, 19), (3000, 500, 256)):
+        x = torch.as_tensor(rng.standard_normal((n, f)).astype(np.float32))
+        b = torch.as_tensor(rng.standard_normal((n, k)).astype(np.float32))
+        out = torch.full((n, f + k), float("nan"))
+        rc = lib.gp_host_concat(ctypes.c_void_p(x.data_ptr()), f, ctypes.c_void_p(b.data_ptr()), k, n,
+                                ctypes.c_void_p(out.data_ptr()), f + k)
+        assert rc == 0
+        assert torch.equal(out, torch.cat((x, b), 1))
+        # destination rows that start off a 16-byte boundary (a column slice of a wider buffer)
+        wide = torch.full((n, f + k + 3), float("nan"))
+        view = wide[:, 1:1 + f + k]
+        rc = lib.gp_host_concat(ctypes.c_void_p(x.data_ptr()), f, ctypes.c_void_p(b.data_ptr()), k, n,
+                                ctypes.c_void_p(view.data_ptr()), f + k + 3)
+        assert rc == 0
+        assert torch.equal(view, torch.cat((x, b), 1))
+        assert torch.isnan(wide[:, 0]).all() and torch.isnan(wide[:, -2:]).all()
