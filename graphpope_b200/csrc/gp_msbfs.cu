@@ -367,12 +367,6 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
         __syncthreads();
         GP_TRACE(0);
 
-        u32 tr_tiles = 0, tr_fast = 0;
-        u64 tr_pack = 0;
-        const long long tr_t0 = p.trace != nullptr ? clock64() : 0;
-        auto tr_mark = [&](int k) {  // diagnostics: 16-bit cycle stamps of the first tiles of the level
-            if (p.trace != nullptr && k < 4) tr_pack |= (u64)min(65535ll, clock64() - tr_t0) << (16 * k);
-        };
         int nzrows = 0;
         for (int b = 0; b < p.batches; ++b) {
             u64 lv[VW], live_acc[VW];
@@ -389,7 +383,6 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
             int j_next = 0;
             for (int j = warp; j < tiles_cta; j = __shfl_sync(FULL_MASK, j_next, 0)) {
                 if (lane == 0) j_next = atomicAdd(&s_queue[b], 1) + WARPS;
-                if (tr_tiles == 0) tr_mark(0);
 
             int4 lead, cols;
             unsigned char *dflag = nullptr;
@@ -414,14 +407,9 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
                 seenv[i] = ~0ull;
                 acc[i] = 0;
             }
-            ++tr_tiles;
             if (__all_sync(FULL_MASK, done)) {
-                ++tr_fast;
-                if (tr_tiles == 1) tr_mark(1);
                 // whole tile finished: only the empty next-frontier rows have to be written
                 if (leader && writes_empty) finalize_row<VW>(c, off, lead.x, acc, seenv, live_acc, lv, nzrows);
-                if (tr_tiles == 1) tr_mark(2);
-                if (tr_tiles == 2) tr_mark(3);
                 continue;
             }
             const int v[GP_SLOT_EDGES] = {cols.x, cols.y, cols.z, cols.w};
@@ -526,11 +514,6 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
         }
         nzrows = __reduce_add_sync(FULL_MASK, nzrows);
         if (lane == 0 && nzrows) atomicAdd(&s_nzrows, nzrows);
-        if (p.trace != nullptr && lane == 0 && level <= 32)
-        {
-            p.trace[(((size_t)(level - 1) * total_warps + gwarp) << 2) + 2] = ((u64)tr_fast << 32) | tr_tiles;
-            p.trace[(((size_t)(level - 1) * total_warps + gwarp) << 2) + 1] = tr_pack;
-        }
         GP_TRACE(3);
         __syncthreads();
         if (tid < lw) {

@@ -31,13 +31,6 @@ for l in range(L):
     d = t[l]
     tot = d[:, 3] - d[:, 0]
     print("%3d | %7d | %7d | %7d | %7d | warp %d (cta %d)" % (l + 1, tot.max(), np.median(tot), np.percentile(tot, 90), tot.min(), tot.argmax(), tot.argmax() // wpc))
-print("lvl | first tile done after (p50 cycles) | tiles per warp p50/max | fast-path tiles total / all tiles")
-for l in range(L):
-    d = t[l]
-    tiles = d[:, 2] & 0xFFFFFFFF; fast = d[:, 2] >> 32
-    st = [(d[:, 1] >> (16 * k)) & 0xFFFF for k in range(4)]
-    ok = st[3] > 0
-    print("%3d | stamps p50 (grab, vote, finalized, 2nd tile finalized): %s | %d / %d | %d / %d" % (l + 1, [int(np.median(x[ok])) if ok.any() else -1 for x in st], np.median(tiles), tiles.max(), fast.sum(), tiles.sum()))
 for l in range(L - 1):
     end = t[l, :, 3].reshape(-1, wpc).max(axis=1); start = t[l + 1, :, 0].reshape(-1, wpc).min(axis=1)
     w = start - end

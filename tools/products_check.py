@@ -22,21 +22,23 @@ for rep in range(3):
           f"hops decode {ev[2].elapsed_time(ev[3]):.2f} ms; {k * ei.shape[1] / ev[1].elapsed_time(ev[2]) / 1e6:.1f} GTEPS (BFS only); {st}", flush=True)
 info = eng.csr.info(); print("csr info", info, flush=True)
 assert info["num_edges"] == ei.shape[1] and info["is_symmetric"] == 1
-h = hops  # [N, k] uint16 on device
+h = hops.view(torch.int16)  # [N, k] on device; torch cannot index uint16, so reinterpret and mask below
+def as_i32(t):
+    return t.to(torch.int32) & 0xFFFF
 # (1) every anchor is at distance 0 from itself
 assert bool((h[a_d, torch.arange(k, device="cuda")] == 0).all())
 # (2) along every edge (u, v) of a symmetric graph hop counts differ by at most 1 (unreachable = 0xFFFF on both ends)
 src, dst = ei_d[0], ei_d[1]
 bad = 0
 for c0 in range(0, k, 64):
-    hu = h[:, c0:c0 + 64].to(torch.int32)
+    hu = as_i32(h[:, c0:c0 + 64])
     for e0 in range(0, ei.shape[1], 16_000_000):
         s_, d_ = src[e0:e0 + 16_000_000], dst[e0:e0 + 16_000_000]
         bad += int(((hu[s_] - hu[d_]).abs() > 1).sum().item())
 print("edges violating |hops(u) - hops(v)| <= 1:", bad); assert bad == 0
 # (3) every reached non-anchor (node, lane) has a neighbour one hop closer: checked through a scatter-min over edges
 for c0 in range(0, k, 64):
-    hu = h[:, c0:c0 + 64].to(torch.int32)
+    hu = as_i32(h[:, c0:c0 + 64])
     best = torch.full_like(hu, 1 << 20)
     for e0 in range(0, ei.shape[1], 16_000_000):
         s_, d_ = src[e0:e0 + 16_000_000], dst[e0:e0 + 16_000_000]
@@ -48,7 +50,7 @@ print("parent property holds for all reached (node, anchor) pairs")
 from oracle import cbfs
 cols = [0, k // 2, k - 1]
 want = cbfs.bfs_hops(cbfs.InCsr(ei, n), anchors[cols])
-got = h[:, cols].cpu().numpy()
+got = h[:, cols].cpu().numpy().view(np.uint16)
 assert np.array_equal(got, want), "hops differ from the oracle"
 print("columns", cols, "bit-equal to the oracle; max hop", int(want[want != 0xFFFF].max()))
 print("PRODUCTS CHECK PASSED")
