@@ -93,6 +93,7 @@ SIGNATURES = {
     "gp_block_to_host": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p]),
     "gp_degree": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gp_pagerank": (c_int, [c_void_p, c_double, c_double, c_int32, c_void_p, POINTER(c_int32), c_void_p]),
+    "gp_closeness": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gp_topk_stable_i32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "gp_topk_stable_f64": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "gp_cdist_minmax": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_void_p,

@@ -190,6 +190,7 @@ __device__ __forceinline__ bool finalize_row(const LevelCtx<VW> &c, size_t off, 
         u64 z[VW];
 #pragma unroll
         for (int i = 0; i < VW; ++i) z[i] = 0;
+#pragma unroll 1  // rare (hop 15 of a deep graph): keep it out of the way of the hot path's registers
         for (int q = c.zero_first; q < c.zero_first + c.zero_count; ++q)
             vstore<VW>(c.planes + (size_t)q * c.plane_stride + off, z);
     }
@@ -333,16 +334,10 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
         c.planes = p.result + (size_t)(1 + GP_BFS_LEVEL_ARRAYS) * p.plane_stride;
         c.plane_stride = p.plane_stride;
         c.level = level;
-        // planes are first needed at hop 16 = 2^4: clear planes 0..4 one level ahead, and every
-        // higher plane q one level before hop 2^q first sets it
+        // the deep-hop bit planes are first needed at hop 16: every row clears all of them one level ahead
+        // (deep graphs only; clearing them lazily left the high planes of a shallower run undefined)
         c.zero_first = 0;
-        c.zero_count = 0;
-        if (level == GP_BFS_LEVEL_ARRAYS) {
-            c.zero_count = 5;
-        } else if (level > GP_BFS_LEVEL_ARRAYS && ((level + 1) & level) == 0 && 31 - __clz(level + 1) < GP_BFS_PLANES) {
-            c.zero_first = 31 - __clz(level + 1);
-            c.zero_count = 1;
-        }
+        c.zero_count = level == GP_BFS_LEVEL_ARRAYS ? GP_BFS_PLANES : 0;
         const u64 *live_r = p.live + (level % 3) * GP_BFS_MAX_LANE_WORDS;
         u64 *live_w = p.live + ((level + 1) % 3) * GP_BFS_MAX_LANE_WORDS;
         u64 *live_z = p.live + ((level + 2) % 3) * GP_BFS_MAX_LANE_WORDS;

@@ -87,6 +87,12 @@ class DeviceCsr:
         check(self._lib.gp_pagerank(self._h, alpha, tol, max_iter, _ptr(x), byref(it), _stream()))
         return x, it.value
 
+    def closeness(self) -> torch.Tensor:
+        """networkx ``closeness_centrality`` defaults (utils.py:50-54): float64[N], bit-equal scores."""
+        x = torch.empty(self.num_nodes, dtype=torch.float64, device="cuda")
+        check(self._lib.gp_closeness(self._h, _ptr(x), _stream()))
+        return x
+
     def close(self):
         if self._h:
             self._lib.gp_csr_free(self._h)

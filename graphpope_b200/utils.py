@@ -21,9 +21,9 @@ the CPU process pool it sized (utils.py:98) is replaced by one multi-source BFS 
 What runs where
   * geodesic distances, 1/(d+1) normalisation, concat: device (libgraphpope_b200.so).
   * ``stochastic`` anchors: host numpy global RNG, exactly utils.py:22-24 (same seed, same anchors).
-  * ``degree_centrality`` / ``pagerank`` anchors: device (CSR row-pointer differences, float64 SpMV power
-    iteration, stable top-k).
-  * betweenness / eigenvector / closeness / clustering anchors and KMeans centres: the reference's own
+  * ``degree_centrality`` / ``pagerank`` / ``closeness_centrality`` anchors: device (degree array, float64
+    SpMV power iteration, MS-BFS from every node + bit-sliced column sums; stable top-k).
+  * betweenness / eigenvector / clustering anchors and KMeans centres: the reference's own
     networkx / scikit-learn calls on the host (stated scope of the port).
 There is no CPU fallback for the device parts: without the CUDA library or a GPU these functions raise.
 """
@@ -43,8 +43,7 @@ from . import _lib
 SYMMETRIZE = os.environ.get("GRAPHPOPE_SYMMETRIZE", "0") == "1"
 VERBOSE = os.environ.get("GRAPHPOPE_QUIET", "0") != "1"
 
-_HOST_CENTRALITIES = ("betweenness_centrality", "eigenvector_centrality", "closeness_centrality",
-                      "clustering_coefficient")
+_HOST_CENTRALITIES = ("betweenness_centrality", "eigenvector_centrality", "clustering_coefficient")
 
 last_stats: dict = {}  # stats of the most recent MS-BFS (levels, edges examined, ...)
 
@@ -95,6 +94,11 @@ def sample_anchor_nodes(data, num_anchor_nodes, sampling_method):
         score, _ = csr.pagerank()  # networkx pagerank_scipy defaults
         return _dev.topk_stable(score, num_anchor_nodes).cpu().tolist()
 
+    if sampling_method == 'closeness_centrality':
+        # every node as an anchor of the MS-BFS + bit-sliced column sums (gp_closeness.cu)
+        csr = _device_csr(data)
+        return _dev.topk_stable(csr.closeness(), num_anchor_nodes).cpu().tolist()
+
     if sampling_method in _HOST_CENTRALITIES:
         # Not re-implemented (north_star): the reference's own networkx call, same top-k rule.
         import networkx as nx
@@ -103,7 +107,6 @@ def sample_anchor_nodes(data, num_anchor_nodes, sampling_method):
         score = {
             'betweenness_centrality': nx.betweenness_centrality,
             'eigenvector_centrality': nx.eigenvector_centrality_numpy,
-            'closeness_centrality': nx.closeness_centrality,
             'clustering_coefficient': nx.clustering,
         }[sampling_method](G)
         ranked = sorted(score.items(), key=lambda item: item[1])  # stable, ascending

@@ -217,6 +217,11 @@ int gp_degree(const gp_csr_t *csr, int32_t *d_degree, gp_stream_t stream);
  * stop when the L1 change < N*tol.  syncs.  d_x float64[N].                     */
 int gp_pagerank(const gp_csr_t *csr, double alpha, double tol, int32_t max_iter,
                 double *d_x, int32_t *iterations, gp_stream_t stream);
+/* closeness_centrality (utils.py:50-54 -> nx.closeness_centrality defaults: incoming distance,
+ * Wasserman-Faust scaling): scores of ALL nodes from N/4096 passes of the MS-BFS with every node as an
+ * anchor plus bit-sliced column sums; float64 in networkx's operation order (bit-equal).  syncs.
+ * d_score float64[N].                                                                             */
+int gp_closeness(const gp_csr_t *csr, double *d_score, gp_stream_t stream);
 /* Stable top-k of utils.py:29-30 / 41-42: ascending stable sort by score, keep
  * the last k (ties keep ascending node id; output in ascending-score order).
  * async.  d_out int64[min(k, N)] (k == 0 returns all N: list[-0:] quirk).       */

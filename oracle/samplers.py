@@ -3,8 +3,9 @@
 TEST INFRASTRUCTURE — see oracle/__init__.py.
 
 Only the samplers the device path re-implements are restated here
-(stochastic, degree_centrality, pagerank).  The other four centralities stay
-on the reference's own networkx calls in the product (north_star).
+(stochastic, degree_centrality, pagerank, closeness_centrality).  The other three
+centralities stay on the reference's own networkx calls in the product
+(north_star).
 
 Third-party arithmetic restated: networkx (unpinned by the reference's
 requirements.txt; 3.6.1 installed) ``degree_centrality`` and
@@ -103,3 +104,37 @@ def pagerank_scores(edge_index, num_nodes: int, alpha: float = 0.85,
 def pagerank_anchors(edge_index, num_nodes: int, k: int) -> list:
     x, _ = pagerank_scores(edge_index, num_nodes)
     return stable_top_k(x, k)
+
+
+def closeness_scores(edge_index, num_nodes: int) -> np.ndarray:
+    """networkx ``closeness_centrality(G)`` defaults restated (utils.py:50-54 call site).
+
+    Incoming distance on the DiGraph, Wasserman-Faust scaling, float64 in networkx's
+    operation order: ``cc = (r - 1) / totsp; cc *= (r - 1) / (N - 1)`` with ``r`` the
+    number of nodes that can reach the node (itself included) and ``totsp`` the sum of
+    their hop counts; 0 when ``totsp == 0`` or ``N == 1``.
+    """
+    from . import cbfs
+
+    n = int(num_nodes)
+    out = np.zeros(n, dtype=np.float64)
+    if n == 0:
+        return out
+    csr = cbfs.InCsr(edge_index, n)
+    step = 512
+    for c0 in range(0, n, step):
+        anchors = np.arange(c0, min(n, c0 + step), dtype=np.int64)
+        hops = cbfs.bfs_hops(csr, anchors).astype(np.int64)  # [N, k], 0xFFFF = cannot reach
+        reach = hops != 0xFFFF
+        r = reach.sum(axis=0)
+        totsp = np.where(reach, hops, 0).sum(axis=0)
+        for j in range(anchors.size):
+            if totsp[j] > 0 and n > 1:
+                cc = (float(r[j]) - 1.0) / float(totsp[j])
+                cc *= (float(r[j]) - 1.0) / (n - 1)
+                out[c0 + j] = cc
+    return out
+
+
+def closeness_centrality_anchors(edge_index, num_nodes: int, k: int) -> list:
+    return stable_top_k(closeness_scores(edge_index, num_nodes), k)

@@ -108,6 +108,11 @@ def main():
     pr = nx.pagerank(G3)
     out["samplers/pagerank_scores"] = np.asarray([pr[i] for i in range(n3)], dtype=np.float64)
     out["samplers/degree"] = np.asarray([G3.degree(i) for i in range(n3)], dtype=np.int64)
+    for k3 in (1, 16, 64, 256):
+        out[f"samplers/closeness_centrality/{k3}"] = np.asarray(
+            utils.sample_anchor_nodes(data3, k3, "closeness_centrality"), dtype=np.int64)
+    cc = nx.closeness_centrality(G3)
+    out["samplers/closeness_scores"] = np.asarray([cc[i] for i in range(n3)], dtype=np.float64)
     np.random.seed(42)
     out["samplers/stochastic_89250_256"] = np.asarray(
         utils.sample_anchor_nodes(RefData(None, 89250), 256, "stochastic"), dtype=np.int64)

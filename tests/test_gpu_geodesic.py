@@ -204,6 +204,27 @@ def test_deep_path_uses_many_distance_planes(dev):
     assert np.array_equal(_bits(feats), _bits(cbfs.normalise(want)))
 
 
+def test_handle_reuse_after_a_deeper_run(dev):
+    """A run of depth ~100 on a handle that earlier saw depth 699: the high deep-hop bit planes of the
+    first run must not leak into the second (they are cleared at hop 15 of every deep run)."""
+    n = 700
+    a = np.arange(n - 1)
+    path = np.stack([np.concatenate([a, a + 1]), np.concatenate([a + 1, a])]).astype(np.int64)
+    r = np.arange(200)
+    ring = np.stack([np.concatenate([r, (r + 1) % 200]), np.concatenate([(r + 1) % 200, r])]).astype(np.int64)
+    eng = dev.GeodesicEngine(n, path.shape[1], 64)
+    anchors = np.array([0, 5, 699, 100], dtype=np.int64)
+    a_d = torch.as_tensor(anchors).cuda()
+    for ei in (path, ring, path, ring):
+        eng.csr.build(torch.as_tensor(ei).cuda())
+        eng.bfs.run(a_d)
+        got = eng.bfs.hops_u16().cpu().numpy()
+        assert np.array_equal(got, _oracle_hops(ei, n, anchors))
+        feats = eng.bfs.features().cpu().numpy()
+        want = np.where(got == 0xFFFF, np.float32(0), np.float32(1) / (got.astype(np.float32) + np.float32(1)))
+        assert np.array_equal(_bits(feats), _bits(want.astype(np.float32)))
+
+
 def test_uint16_overflow_is_reported(dev):
     n = 65600
     ei = np.stack([np.arange(n - 1), np.arange(1, n)]).astype(np.int64)

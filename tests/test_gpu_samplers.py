@@ -78,3 +78,35 @@ def test_flickr_shape_degree_and_pagerank_1024_anchors(dev):
     assert dev.topk_stable(deg, 1024).cpu().tolist() == s.degree_centrality_anchors(ei, shape.num_nodes, 1024)
     x, _ = csr.pagerank()
     assert abs(float(x.sum()) - 1.0) < 1e-9
+
+
+def test_closeness_scores_bit_equal_and_anchor_lists(dev, golden_small):
+    """nx.closeness_centrality (utils.py:50-54) from the MS-BFS with every node as an anchor."""
+    from graphpope_b200 import utils
+    ei, n = golden_small["samplers/edge_index"], int(golden_small["samplers/n"])
+    csr = dev.DeviceCsr(n, ei.shape[1]).build(torch.as_tensor(ei).cuda())
+    got = csr.closeness().cpu().numpy()
+    assert np.array_equal(got, golden_small["samplers/closeness_scores"])  # float64, bit for bit
+    for k in (1, 16, 64, 256):
+        assert utils.sample_anchor_nodes(Data(ei, n), k, "closeness_centrality") == \
+            golden_small[f"samplers/closeness_centrality/{k}"].tolist()
+
+
+@pytest.mark.parametrize("case", ["directed-sparse", "path", "multi-chunk"])
+def test_closeness_matches_oracle_on_hard_graphs(dev, case):
+    """Unreachable pairs and dangling nodes (asymmetric digraph), hop counts beyond 15 (a path: the
+    deep bit planes and the wide adder), and more nodes than one 4096-anchor pass."""
+    from oracle import samplers as s
+    if case == "directed-sparse":
+        n = 700
+        ei = synth.random_digraph(n, 1500, seed=31)
+    elif case == "path":
+        n = 300
+        a = np.arange(n - 1)
+        ei = np.stack([np.concatenate([a, a + 1]), np.concatenate([a + 1, a])]).astype(np.int64)
+    else:
+        n = 9000
+        ei = synth.chung_lu_symmetric(n, 40000, 2.2, seed=33)
+    csr = dev.DeviceCsr(n, ei.shape[1]).build(torch.as_tensor(ei).cuda())
+    got = csr.closeness().cpu().numpy()
+    assert np.array_equal(got, s.closeness_scores(ei, n))

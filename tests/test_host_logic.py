@@ -53,13 +53,15 @@ def test_host_centralities_use_networkx_top_k_rule():
     import networkx as nx
     ei = np.array([[0, 1, 1, 2, 2, 3, 3, 4, 1, 3], [1, 0, 2, 1, 3, 2, 4, 3, 3, 1]])
     data = Data(ei, 6)
-    got = utils.sample_anchor_nodes(data, 3, "closeness_centrality")
+    got = utils.sample_anchor_nodes(data, 3, "betweenness_centrality")
     G = nx.DiGraph(); G.add_nodes_from(range(6)); G.add_edges_from(zip(*ei.tolist()))
-    score = nx.closeness_centrality(G)
+    score = nx.betweenness_centrality(G)
     want = [k for k, _ in sorted(score.items(), key=lambda kv: kv[1])][-3:]
     assert got == want
-    for method in ("betweenness_centrality", "clustering_coefficient"):
-        assert len(utils.sample_anchor_nodes(data, 2, method)) == 2
+    assert len(utils.sample_anchor_nodes(data, 2, "clustering_coefficient")) == 2
+    if not torch.cuda.is_available():  # closeness now runs on the device and must fail loudly without one
+        with pytest.raises(RuntimeError):
+            utils.sample_anchor_nodes(data, 3, "closeness_centrality")
 
 
 def test_merge_dicts_and_concat():

@@ -40,3 +40,12 @@ def test_top_k_quirks():
     assert s.stable_top_k(score, 2) == [2, 4]          # ties -> larger ids, ascending score order
     assert s.stable_top_k(score, 0) == [1, 3, 0, 2, 4]  # list[-0:] is the whole list
     assert s.stable_top_k(score, 9) == [1, 3, 0, 2, 4]
+
+
+def test_closeness_matches_reference(golden_small):
+    ei = golden_small["samplers/edge_index"]
+    n = int(golden_small["samplers/n"])
+    x = s.closeness_scores(ei, n)
+    assert np.array_equal(x, golden_small["samplers/closeness_scores"])  # same operation order -> bit-equal float64
+    for k in (1, 16, 64, 256):
+        assert s.closeness_centrality_anchors(ei, n, k) == golden_small[f"samplers/closeness_centrality/{k}"].tolist()
