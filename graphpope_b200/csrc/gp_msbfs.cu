@@ -219,6 +219,12 @@ __device__ __forceinline__ bool finalize_row(const LevelCtx<VW> &c, size_t off, 
     return incomplete;
 }
 
+// Warp-iterations cached per CTA: enough for GP_BFS_CACHE_ITERS * 24 tiles per SM whatever the launch shape.
+__host__ __device__ constexpr int bfs_cache_iters(int nt, int minb)
+{
+    return (GP_BFS_CACHE_ITERS * 24 + (nt / 32) * minb - 1) / ((nt / 32) * minb);
+}
+
 // Descriptor and column indices of the 32 slots of tile `t0 / 32` (one degree class per tile).
 //   lead = {row or -1, count | chunks << 8 | first << 30, hub index, log2 G}, cols = <= 4 columns or -1.
 __device__ __forceinline__ void load_tile(const BfsParams &p, const int *s_ent_base, const int *s_slot_base, int t0,
@@ -249,7 +255,7 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
 {
     constexpr int VW = WB;
     constexpr int WARPS = NT / 32;
-    constexpr int JT = GP_BFS_CACHE_ITERS * WARPS;  // tiles of this CTA whose work items live in shared memory
+    constexpr int JT = bfs_cache_iters(NT, MINB) * WARPS;  // tiles of this CTA whose work items live in shared memory
     static_assert(GP_SLOT_EDGES == 4, "slot layout is int4");
     // Work cache: a CTA visits the same tiles every level, so the descriptors and column indices of
     // its first JT tiles are loaded ONCE into shared memory; a level then costs a single dependent
@@ -542,10 +548,10 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
     }
 }
 
-template <int WB, int NT>
+template <int WB, int NT, int MINB>
 constexpr size_t bfs_cache_bytes()
 {
-    constexpr int tiles = GP_BFS_CACHE_ITERS * (NT / 32);
+    constexpr int tiles = bfs_cache_iters(NT, MINB) * (NT / 32);
     return (size_t)tiles * 32 * (2 * sizeof(int4) + GP_BFS_DONE_BATCHES);
 }
 
@@ -563,19 +569,19 @@ int launch_bfs_cfg(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int cfg
         GP_CUDA_CHECK(cudaGetDevice(&dev));
         GP_CUDA_CHECK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         const int dyn_room = smem_optin - (int)fa.sharedSizeBytes;
-        const int cache_bytes = (int)bfs_cache_bytes<WB, NT>();
+        const int cache_bytes = (int)bfs_cache_bytes<WB, NT, MINB>();
         int dyn_max = cache_bytes + GP_BFS_MAP_SMEM_MAX;
         if (dyn_max > dyn_room) dyn_max = dyn_room;
         GP_REQUIRE(dyn_max >= cache_bytes, GP_ERR_CUDA, "msbfs work cache does not fit in shared memory");
         GP_CUDA_CHECK(cudaFuncSetAttribute(msbfs_kernel<WB, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
         GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, msbfs_kernel<WB, NT, MINB>, NT,
-                                                                    bfs_cache_bytes<WB, NT>()));
+                                                                    bfs_cache_bytes<WB, NT, MINB>()));
         GP_REQUIRE(occ >= 1, GP_ERR_CUDA, "msbfs kernel does not fit on an SM");
         if (occ > MINB) occ = MINB;
         h->map_smem_bytes = 0;
         if (cache_bytes + want_map <= dyn_max && getenv("GP_BFS_NO_MAP") == nullptr) {
             GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_map, msbfs_kernel<WB, NT, MINB>, NT,
-                                                                        bfs_cache_bytes<WB, NT>() + want_map));
+                                                                        bfs_cache_bytes<WB, NT, MINB>() + want_map));
             if (occ_map >= occ) h->map_smem_bytes = want_map;
         }
         h->grid_blocks = occ * gp_sm_count();
@@ -591,7 +597,7 @@ int launch_bfs_cfg(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int cfg
     const unsigned ev_flags = gp_is_capturing() ? cudaEventRecordExternal : cudaEventRecordDefault;
     GP_CUDA_CHECK(cudaEventRecordWithFlags(h->ev_start, stream, ev_flags));
     GP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)msbfs_kernel<WB, NT, MINB>, dim3(h->grid_blocks),
-                                              dim3(NT), args, bfs_cache_bytes<WB, NT>() + h->map_smem_bytes, stream));
+                                              dim3(NT), args, bfs_cache_bytes<WB, NT, MINB>() + h->map_smem_bytes, stream));
     GP_CUDA_CHECK(cudaEventRecordWithFlags(h->ev_stop, stream, ev_flags));
     return GP_OK;
 }
@@ -605,14 +611,17 @@ int launch_bfs(gp_msbfs *h, const BfsParams &p, cudaStream_t stream)
     if (cfg < 0) {
         const char *s = getenv("GP_BFS_CFG");
         cfg = s ? atoi(s) : GP_BFS_DEFAULT_CFG;
-        if (cfg < 0 || cfg > 4) cfg = GP_BFS_DEFAULT_CFG;
+        if (cfg < 0 || cfg > 7) cfg = GP_BFS_DEFAULT_CFG;
     }
     switch (cfg) {
         case 0: return launch_bfs_cfg<WB, 768, 1>(h, p, stream, 0);   // 85 regs, 24 warps/SM, one tile queue per SM
         case 1: return launch_bfs_cfg<WB, 384, 2>(h, p, stream, 1);   // 85 regs, 24 warps/SM
         case 2: return launch_bfs_cfg<WB, 512, 1>(h, p, stream, 2);   // 128 regs, 16 warps/SM
         case 3: return launch_bfs_cfg<WB, 1024, 1>(h, p, stream, 3);  // 64 regs, 32 warps/SM
-        default: return launch_bfs_cfg<WB, 512, 2>(h, p, stream, 4);  // 64 regs, 32 warps/SM, two queues
+        case 4: return launch_bfs_cfg<WB, 512, 2>(h, p, stream, 4);   // 64 regs, 32 warps/SM, two queues
+        case 5: return launch_bfs_cfg<WB, 320, 2>(h, p, stream, 5);   // 102 regs, 20 warps/SM
+        case 6: return launch_bfs_cfg<WB, 256, 2>(h, p, stream, 6);   // 128 regs, 16 warps/SM
+        default: return launch_bfs_cfg<WB, 640, 1>(h, p, stream, 7);  // 102 regs, 20 warps/SM, one queue
     }
 }
 

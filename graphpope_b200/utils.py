@@ -43,6 +43,55 @@ from . import _lib
 SYMMETRIZE = os.environ.get("GRAPHPOPE_SYMMETRIZE", "0") == "1"
 VERBOSE = os.environ.get("GRAPHPOPE_QUIET", "0") != "1"
 
+
+def _output_device() -> str:
+    """``GRAPHPOPE_OUTPUT=cuda`` keeps the ``[N, F+K]`` matrix in HBM (the trainer's
+    ``x[n_id]`` gathers, main.py:120,177, then run on the device and the 91 MB device->host copy plus the
+    host concat disappear).  Default ``cpu`` = the reference's contract."""
+    return os.environ.get("GRAPHPOPE_OUTPUT", "cpu")
+
+
+def _cache_dir():
+    """``GRAPHPOPE_CACHE_DIR`` extends the reference's in-process memo (utils.py:195-208) across runs
+    (SURVEY §8f rank 4): the float32 ``[N, K]`` distance block is stored under a key derived from the
+    graph, the anchors and the options.  Unset = no files are read or written."""
+    return os.environ.get("GRAPHPOPE_CACHE_DIR") or None
+
+
+def block_cache_key(edge_index, num_nodes, anchors, symmetrize=False) -> str:
+    import hashlib
+
+    h = hashlib.sha256()
+    h.update(b"graphpope-geodesic-block-v1")
+    h.update(np.int64([int(num_nodes), int(bool(symmetrize))]).tobytes())
+    ei = torch.as_tensor(edge_index).to(device="cpu", dtype=torch.int64).contiguous()
+    h.update(np.int64(list(ei.shape)).tobytes())
+    h.update(ei.numpy().tobytes())
+    h.update(np.ascontiguousarray(np.asarray(anchors, dtype=np.int64)).tobytes())
+    return h.hexdigest()
+
+
+def _cached_block(data):
+    d = _cache_dir()
+    if d is None:
+        return None, None
+    key = block_cache_key(_edge_index_of(data), data.num_nodes, data.anchor_nodes, SYMMETRIZE)
+    path = osp.join(d, key + ".pt")
+    if osp.exists(path):
+        blk = torch.load(path, map_location="cpu")
+        if tuple(blk.shape) == (int(data.num_nodes), len(data.anchor_nodes)) and blk.dtype == torch.float32:
+            return blk, path
+    return None, path
+
+
+def _store_block(path, block):
+    if path is None:
+        return
+    os.makedirs(osp.dirname(path), exist_ok=True)
+    tmp = path + ".tmp%d" % os.getpid()
+    torch.save(block.detach().cpu().contiguous(), tmp)
+    os.replace(tmp, path)  # atomic: DDP ranks may race to write the same key
+
 _HOST_CENTRALITIES = ("betweenness_centrality", "eigenvector_centrality", "clustering_coefficient")
 
 last_stats: dict = {}  # stats of the most recent MS-BFS (levels, edges examined, ...)
@@ -164,15 +213,37 @@ def get_geodesic_distance_vector(data, num_workers):
     Reads ``data.anchor_nodes``.  Always float32 (the reference yields int64 in the degenerate case
     where every entry is 0).
     """
-    out, _, stats = _dev.geodesic_embed_host(_edge_index_of(data), int(data.num_nodes), data.anchor_nodes,
-                                             None, SYMMETRIZE)
-    last_stats.update(stats)
+    blk, path = _cached_block(data)
+    if blk is not None:
+        return blk.cuda() if _output_device() == "cuda" else blk
+    if _output_device() == "cuda":
+        out = _device_features(data, None)
+    else:
+        out, _, stats = _dev.geodesic_embed_host(_edge_index_of(data), int(data.num_nodes), data.anchor_nodes,
+                                                 None, SYMMETRIZE)
+        last_stats.update(stats)
+    _store_block(path, out)
+    return out
+
+
+def _device_features(data, x):
+    """Device-resident result: edge_index (and x) go up once, the ``[N, F+K]`` matrix stays in HBM."""
+    _lib.require_cuda()
+    n = int(data.num_nodes)
+    ei = _edge_index_of(data).cuda(non_blocking=True)
+    anchors = torch.as_tensor(np.asarray(data.anchor_nodes, dtype=np.int64)).cuda(non_blocking=True)
+    eng = _dev.GeodesicEngine(n, ei.size(1), max(1, anchors.numel()), SYMMETRIZE)
+    x_d = None if x is None else x.to(device="cuda", dtype=torch.float32, non_blocking=True).contiguous()
+    out = eng.run(ei, anchors, x_d)
+    last_stats.update(eng.bfs.stats())  # syncs; surfaces index errors
     return out
 
 
 def concat_into_features(embedding_matrix, data):
     """utils.py:129-135: ``torch.cat((data.x, embedding), 1)``."""
     emb = torch.as_tensor(embedding_matrix)
+    if emb.is_cuda and not data.x.is_cuda:
+        return torch.cat((data.x.to(emb.device), emb), 1)  # GRAPHPOPE_OUTPUT=cuda: the result lives in HBM
     return torch.cat((data.x, emb.to(data.x.device)), 1)
 
 
@@ -186,12 +257,16 @@ def attach_distance_embedding(data, dataset, num_anchor_nodes, sampling_method, 
                                             sampling_method=sampling_method)
     _say('deriving shortest paths to anchor nodes...')
     x = data.x
-    if x.dtype != torch.float32:
-        # torch.cat type-promotes; keep that behaviour by taking the slow generic route
+    if x.dtype != torch.float32 or _cache_dir() is not None:
+        # torch.cat type-promotes; keep that behaviour by taking the generic route (also the cached one:
+        # the cache holds the [N, K] block, not the concatenation)
         return concat_into_features(get_geodesic_distance_vector(data, num_workers), data)
-    out, _, stats = _dev.geodesic_embed_host(_edge_index_of(data), int(data.num_nodes), data.anchor_nodes,
-                                             x, SYMMETRIZE)
-    last_stats.update(stats)
+    if _output_device() == "cuda":
+        out = _device_features(data, x)
+    else:
+        out, _, stats = _dev.geodesic_embed_host(_edge_index_of(data), int(data.num_nodes), data.anchor_nodes,
+                                                 x, SYMMETRIZE)
+        last_stats.update(stats)
     _say('feature matrix is blessed by the POPE!')
     return out
 
@@ -218,7 +293,7 @@ def attach_node2vec(data, dataset, num_anchor_nodes, sampling_method, distance_f
         anchor_emb = torch.as_tensor(kmeans.cluster_centers_)
         _say('K means cluster anchor nodes derived!')
     block = _dev.cdist_minmax(table, anchor_emb, mode, apply_minmax=True)
-    out = concat_into_features(block.cpu(), data)
+    out = concat_into_features(block if _output_device() == "cuda" else block.cpu(), data)
     _say('feature matrix is blessed by the POPE')
     return out
 

@@ -315,3 +315,30 @@ def test_normalize_into_matches_convention(dev):
     got = out.cpu().numpy()
     assert np.array_equal(_bits(got[:, 2:]), _bits(cbfs.normalise(d)))
     assert np.all(got[:, :2] == -1.0)
+
+
+def test_device_resident_output_equals_host_output(dev, monkeypatch):
+    """GRAPHPOPE_OUTPUT=cuda: same bits, but the [N, F+K] matrix stays in HBM so the
+    trainer's x[n_id] gathers (main.py:120,177) run on the device."""
+    from graphpope_b200 import utils
+    n, f, k = 3000, 12, 40
+    ei = synth.random_digraph(n, 20000, seed=5)
+    x = torch.as_tensor(np.random.default_rng(1).standard_normal((n, f)).astype(np.float32))
+
+    class D:
+        pass
+
+    def run():
+        d = D()
+        d.num_nodes, d.edge_index, d.x = n, torch.as_tensor(ei), x
+        np.random.seed(7)
+        return utils.attach_distance_embedding(d, "toy", k, "stochastic", None, 4)
+
+    monkeypatch.delenv("GRAPHPOPE_OUTPUT", raising=False)
+    host = run()
+    monkeypatch.setenv("GRAPHPOPE_OUTPUT", "cuda")
+    devout = run()
+    assert not host.is_cuda and devout.is_cuda
+    assert torch.equal(devout.cpu(), host)
+    n_id = torch.tensor([5, 0, 2999, 17], device="cuda")
+    assert torch.equal(devout[n_id].cpu(), host[n_id.cpu()])

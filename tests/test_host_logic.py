@@ -143,3 +143,36 @@ def test_host_concat_matches_torch_cat():
         assert rc == 0
         assert torch.equal(view, torch.cat((x, b), 1))
         assert torch.isnan(wide[:, 0]).all() and torch.isnan(wide[:, -2:]).all()
+
+
+def test_block_cache_key_and_hit_path(tmp_path, monkeypatch):
+    """GRAPHPOPE_CACHE_DIR (SURVEY §8f rank 4): the [N, K] block is stored once and served from disk after;
+    the key depends on the graph, the anchors and the options."""
+    ei = np.array([[0, 1, 2], [1, 2, 0]])
+    k1 = utils.block_cache_key(ei, 3, [0, 2])
+    assert k1 == utils.block_cache_key(torch.as_tensor(ei), 3, np.array([0, 2]))
+    assert k1 != utils.block_cache_key(ei, 3, [2, 0])
+    assert k1 != utils.block_cache_key(ei, 4, [0, 2])
+    assert k1 != utils.block_cache_key(ei[:, ::-1].copy(), 3, [0, 2])
+    assert k1 != utils.block_cache_key(ei, 3, [0, 2], symmetrize=True)
+
+    calls = []
+
+    def fake_embed(edge_index, n, anchors, x, sym):
+        calls.append(1)
+        return torch.arange(n * len(anchors), dtype=torch.float32).view(n, len(anchors)), None, {}
+
+    monkeypatch.setenv("GRAPHPOPE_CACHE_DIR", str(tmp_path))
+    monkeypatch.setattr(utils._dev, "geodesic_embed_host", fake_embed)
+    d = Data(ei, 3, torch.ones(3, 2))
+    d.anchor_nodes = [0, 2]
+    a = utils.get_geodesic_distance_vector(d, 4)
+    b = utils.get_geodesic_distance_vector(d, 4)
+    assert len(calls) == 1 and torch.equal(a, b) and len(list(tmp_path.iterdir())) == 1
+    d.anchor_nodes = [1, 2]
+    utils.get_geodesic_distance_vector(d, 4)
+    assert len(calls) == 2 and len(list(tmp_path.iterdir())) == 2
+    # the concat route goes through the cache too
+    monkeypatch.setattr(utils, "sample_anchor_nodes", lambda **kw: [0, 2])
+    out = utils.attach_distance_embedding(d, "toy", 2, "stochastic", None, 4)
+    assert len(calls) == 2 and out.shape == (3, 4) and torch.equal(out[:, 2:], a)
