@@ -250,7 +250,7 @@ __device__ __forceinline__ void load_tile(const BfsParams &p, const int *s_ent_b
 }
 
 // WB lane words per node row = one thread loads a whole row (8, 16 or 32 bytes).
-template <int WB, int NT, int MINB>
+template <int WB, int NT, int MINB, bool MAPG>
 __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
 {
     constexpr int VW = WB;
@@ -280,7 +280,9 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
     const long long gtid = (long long)blockIdx.x * NT + tid;
     const int gwarp = blockIdx.x * WARPS + warp, total_warps = gridDim.x * WARPS;
     const int n = p.n, lw = p.batches * WB;
-    const bool use_map = p.map_smem_words > 0;
+    // MAPG: the per-hop bitmaps do not fit in shared memory (large graphs); the same filter then reads
+    // them straight from global memory (L1 resident within a level; the barrier's acquire drops stale lines)
+    const bool use_map = MAPG || p.map_smem_words > 0;
     u64 gathers = 0;
 
     for (int i = tid; i < GP_BFS_MAX_LANE_WORDS * 2; i += NT) s_live32[i] = 0;
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
             uint4 *map_z = reinterpret_cast<uint4 *>(p.nzmap + (size_t)((level + 1) % 3) * p.map_stride);
             const int quads = p.map_stride >> 2;  // padded to a multiple of 4 words
             for (long long i = gtid; i < quads; i += gthreads) map_z[i] = make_uint4(0, 0, 0, 0);
-            if (map_level) {
+            if (map_level && !MAPG) {
                 const uint4 *map_r = reinterpret_cast<const uint4 *>(p.nzmap + (size_t)((level - 1) % 3) * p.map_stride);
                 uint4 *s_map4 = reinterpret_cast<uint4 *>(s_map);
 #pragma unroll 4
@@ -378,6 +380,7 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
             }
             const u64 *cur_b_rows = c.cur + (size_t)b * n * WB;
             const u32 *s_map_b = s_map + (size_t)b * p.nzwords;
+            const u32 *g_map_b = p.nzmap + (size_t)((level - 1) % 3) * p.map_stride + (size_t)b * p.nzwords;
             c.map_w = use_map ? map_w + (size_t)b * p.nzwords : nullptr;
             // tile queue of this batch: every warp starts with tile `warp`, the rest are handed out on
             // demand; the index of the NEXT tile is requested before the current one is processed
@@ -419,7 +422,7 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
 #pragma unroll
                 for (int i = 0; i < GP_SLOT_EDGES; ++i) {
                     // gather only neighbours whose frontier row is non-zero at this hop
-                    const bool nz = v[i] >= 0 && (!map_level || ((s_map_b[v[i] >> 5] >> (v[i] & 31)) & 1u));
+                    const bool nz = v[i] >= 0 && (!map_level || (((MAPG ? g_map_b[v[i] >> 5] : s_map_b[v[i] >> 5]) >> (v[i] & 31)) & 1u));
                     needbits |= (u32)nz << i;
                 }
             }
@@ -555,16 +558,16 @@ constexpr size_t bfs_cache_bytes()
     return (size_t)tiles * 32 * (2 * sizeof(int4) + GP_BFS_DONE_BATCHES);
 }
 
-template <int WB, int NT, int MINB>
-int launch_bfs_cfg(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int cfg_id)
+template <int WB, int NT, int MINB, bool MAPG>
+int launch_bfs_variant(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int cfg_id)
 {
     // Frontier bitmaps are staged in shared memory when they fit without costing a resident CTA.
     const int want_map = (int)((size_t)p.map_stride * sizeof(u32));
-    const int key = (cfg_id * 8 + WB) * 4 + 1;
+    const int key = (cfg_id * 8 + WB) * 4 + 1 + (MAPG ? 2 : 0);
     if (h->grid_blocks == 0 || h->grid_cfg != key || h->map_want_bytes != want_map) {
         int occ = 0, occ_map = 0;
         cudaFuncAttributes fa;
-        GP_CUDA_CHECK(cudaFuncGetAttributes(&fa, msbfs_kernel<WB, NT, MINB>));
+        GP_CUDA_CHECK(cudaFuncGetAttributes(&fa, msbfs_kernel<WB, NT, MINB, MAPG>));
         int smem_optin = 0, dev = 0;
         GP_CUDA_CHECK(cudaGetDevice(&dev));
         GP_CUDA_CHECK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -573,14 +576,14 @@ int launch_bfs_cfg(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int cfg
         int dyn_max = cache_bytes + GP_BFS_MAP_SMEM_MAX;
         if (dyn_max > dyn_room) dyn_max = dyn_room;
         GP_REQUIRE(dyn_max >= cache_bytes, GP_ERR_CUDA, "msbfs work cache does not fit in shared memory");
-        GP_CUDA_CHECK(cudaFuncSetAttribute(msbfs_kernel<WB, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
-        GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, msbfs_kernel<WB, NT, MINB>, NT,
+        GP_CUDA_CHECK(cudaFuncSetAttribute(msbfs_kernel<WB, NT, MINB, MAPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+        GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, msbfs_kernel<WB, NT, MINB, MAPG>, NT,
                                                                     bfs_cache_bytes<WB, NT, MINB>()));
         GP_REQUIRE(occ >= 1, GP_ERR_CUDA, "msbfs kernel does not fit on an SM");
         if (occ > MINB) occ = MINB;
         h->map_smem_bytes = 0;
-        if (cache_bytes + want_map <= dyn_max && getenv("GP_BFS_NO_MAP") == nullptr) {
-            GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_map, msbfs_kernel<WB, NT, MINB>, NT,
+        if (!MAPG && cache_bytes + want_map <= dyn_max && getenv("GP_BFS_NO_MAP") == nullptr) {
+            GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_map, msbfs_kernel<WB, NT, MINB, MAPG>, NT,
                                                                         bfs_cache_bytes<WB, NT, MINB>() + want_map));
             if (occ_map >= occ) h->map_smem_bytes = want_map;
         }
@@ -596,10 +599,22 @@ int launch_bfs_cfg(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int cfg
     // inside a graph capture the timing events become event-record nodes (re-recorded on every replay)
     const unsigned ev_flags = gp_is_capturing() ? cudaEventRecordExternal : cudaEventRecordDefault;
     GP_CUDA_CHECK(cudaEventRecordWithFlags(h->ev_start, stream, ev_flags));
-    GP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)msbfs_kernel<WB, NT, MINB>, dim3(h->grid_blocks),
+    GP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)msbfs_kernel<WB, NT, MINB, MAPG>, dim3(h->grid_blocks),
                                               dim3(NT), args, bfs_cache_bytes<WB, NT, MINB>() + h->map_smem_bytes, stream));
     GP_CUDA_CHECK(cudaEventRecordWithFlags(h->ev_stop, stream, ev_flags));
     return GP_OK;
+}
+
+// The shared-memory variant when the bitmaps fit next to the work cache, else (default shape only) the
+// variant that reads them from global memory.
+template <int WB, int NT, int MINB>
+int launch_bfs_cfg(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int cfg_id)
+{
+    const size_t want_map = (size_t)p.map_stride * sizeof(u32);
+    const bool fits = bfs_cache_bytes<WB, NT, MINB>() + want_map <= 200 * 1024 / (size_t)MINB;
+    if (!fits && cfg_id == GP_BFS_DEFAULT_CFG && getenv("GP_BFS_NO_MAP") == nullptr)
+        return launch_bfs_variant<WB, NT, MINB, true>(h, p, stream, cfg_id);
+    return launch_bfs_variant<WB, NT, MINB, false>(h, p, stream, cfg_id);
 }
 
 // Launch shapes (threads per CTA, CTAs per SM) trade resident warps against registers per thread,

@@ -45,6 +45,30 @@ for name, k_total in (("pubmed-shape", 256), ("flickr-shape", 1024), ("flickr-sh
     ev1.record(); torch.cuda.synchronize()
     if rank == 0: print(f"    p2p == 1-GPU: {same_p2p}; p2p step {ev0.elapsed_time(ev1) / 10:.3f} ms", flush=True)
     dist.barrier(); peer.close()
+# BASELINE config C4: Flickr-shape, 1024 anchors from the degree / PageRank samplers (device), anchor-sharded
+from graphpope_b200 import utils
+sh = synth.SHAPES["flickr-shape"]; n = sh.num_nodes
+ei = synth.make_graph(sh); ei_d = torch.as_tensor(ei).cuda()
+class _D: pass
+d = _D(); d.num_nodes, d.edge_index = n, torch.as_tensor(ei)
+for method in ("degree_centrality", "pagerank"):
+    anchors = np.asarray(utils.sample_anchor_nodes(d, 1024, method), dtype=np.int64)  # identical on every rank
+    a_d = torch.as_tensor(anchors).cuda()
+    eng = dev.GeodesicEngine(n, ei.shape[1], 1024 // world)
+    peer = gpd.PeerAssembly(eng)
+    out, deep = peer.run(ei_d, a_d, None)
+    torch.cuda.synchronize()
+    good = int(deep.item()) == 0
+    if rank == 0:
+        from oracle import cbfs, samplers
+        want_anchors = (samplers.degree_centrality_anchors if method == "degree_centrality" else samplers.pagerank_anchors)(ei, n, 1024)
+        same_list = anchors.tolist() == want_anchors
+        want = cbfs.geodesic_features(ei, n, anchors)
+        same = bool(np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32)))
+        print(f"[C4 flickr-shape K=1024 {method} G={world}] anchor list == oracle: {same_list}; features == oracle: {same}", flush=True)
+        good &= same_list and same
+    ok &= good
+    dist.barrier(); peer.close()
 t = torch.tensor([int(ok)], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0: print("DIST CHECK", "PASSED" if int(t.item()) else "FAILED", flush=True)
 dist.destroy_process_group()
