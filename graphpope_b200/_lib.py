@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_uint32, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgraphpope_b200.so")
@@ -94,6 +94,11 @@ SIGNATURES = {
     "gp_degree": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gp_pagerank": (c_int, [c_void_p, c_double, c_double, c_int32, c_void_p, POINTER(c_int32), c_void_p]),
     "gp_closeness": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "gp_kmeans_plusplus": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_uint64, c_void_p, c_void_p, c_void_p,
+                                   c_void_p]),
+    "gp_kmeans_assign": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "gp_kmeans_update": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p]),
     "gp_topk_stable_i32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "gp_topk_stable_f64": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "gp_cdist_minmax": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_void_p,

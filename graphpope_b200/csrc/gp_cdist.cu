@@ -23,11 +23,11 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cmath>
 
 namespace {
 
 constexpr int CD_TILE_M = 128;
-constexpr int CD_THREADS = 128;
 constexpr int CD_MAX_N = 256;   // anchors per column tile (UMMA N)
 constexpr int CD_KCHUNK = 64;   // bf16 elements per 128-byte swizzle row
 
@@ -40,6 +40,7 @@ struct CdistParams {
     long long ld_out, col_offset;
     float *colmin;  // [k] running per-column min (ordered-int encoded)
     float *colmax;
+    unsigned long long *best;  // k-means assignment mode: [n] packed (squared distance bits << 32 | column), min-reduced
 };
 
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
@@ -347,6 +348,8 @@ __global__ void __launch_bounds__(CD_THREADS2, 1) cdist_kernel(CdistParams p, in
             const float xx = s_xn[(it % 3) * CD_TILE_M + quad * 32 + lane];
             const float inv_xn = xx > 0.0f ? rsqrtf(xx) : 0.0f;
             const int rows_here = (int)min(32ll, max(0ll, p.n - r0));
+            float best_d = INFINITY;
+            int best_c = 0;
 #pragma unroll 1
             for (int c0 = cbase; c0 < cbase + ncols; c0 += 16) {
                 u32 v[16];
@@ -359,6 +362,19 @@ __global__ void __launch_bounds__(CD_THREADS2, 1) cdist_kernel(CdistParams p, in
                     : "r"(taddr)
                     : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (p.best != nullptr) {
+                    // k-means assignment: nearest centre of this row among the 16 columns (squared distance
+                    // xx - 2 dot + cc; no output block at all)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float d2 = fmaxf(fmaf(-2.0f, __uint_as_float(v[j]), xx + s_an[c0 + j]), 0.0f);
+                        if (c0 + j < kv && d2 < best_d) {
+                            best_d = d2;
+                            best_c = c0 + j;
+                        }
+                    }
+                    continue;
+                }
                 // thread = node row: finish the 16 entries of this row, park them in the transpose tile
                 if (mode == GP_CDIST_EUCLIDEAN) {
                     float d2[16];
@@ -428,6 +444,8 @@ __global__ void __launch_bounds__(CD_THREADS2, 1) cdist_kernel(CdistParams p, in
                 }
                 __syncwarp();
             }
+            if (p.best != nullptr && row_ok && best_d < INFINITY)
+                atomicMin(p.best + row, ((unsigned long long)__float_as_uint(best_d) << 32) | (unsigned long long)(u32)(k0 + best_c));
             // this warp has drained its part of the accumulator
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(bar_acc_empty + 8 * st);
@@ -492,6 +510,7 @@ extern "C" int gp_cdist_minmax(const float *d_emb, const float *d_anchor_emb, in
     p.ld_out = ld_out;
     p.col_offset = col_offset;
     p.colmin = p.colmax = nullptr;
+    p.best = nullptr;
     const int64_t col_tiles = gp_ceil_div(num_anchors, CD_MAX_N);
     const int64_t ktile = num_anchors < CD_MAX_N ? num_anchors : CD_MAX_N;
     const int n_pad = (int)(gp_ceil_div(ktile, 32) * 32);  // UMMA N (multiple of 16 at M = 128); the epilogue works in 32s
@@ -543,5 +562,304 @@ extern "C" int gp_cdist_minmax(const float *d_emb, const float *d_anchor_emb, in
         GP_CUDA_CHECK(cudaFreeAsync(mm, stream));
         GP_TRY(rc);
     }
+    return GP_OK;
+}
+
+
+// ================================================================= KMeans on the device
+// attach_node2vec with any sampling_method but 'stochastic' takes the KMeans cluster centres of the
+// node2vec table as anchors (utils.py:168-170).  Lloyd iterations reuse the tcgen05 kernel above in
+// "assignment" mode (nearest centre = arg-min over the pairwise block, which is never written out);
+// k-means++ seeding draws the next centre with the exponential-race form of D^2 sampling (arg-min of
+// Exp(1) / D^2), which needs a reduction instead of a prefix sum.  Parity with scikit-learn is
+// statistical (unseeded there, utils.py:169): the tests compare inertia.
+namespace {
+
+__device__ __forceinline__ u64 splitmix64(u64 x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__global__ void fill_u64_kernel(unsigned long long *p, long long n, unsigned long long v)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+constexpr int KPP_MAX_TRIALS = 8;
+
+// One k-means++ step, first half: centre `step` := row chosen[step]; D^2 of every row updated with it;
+// `trials` candidate rows for the next centre are drawn, each an exact D^2-weighted draw (arg-min of
+// Exp(1) / D^2 over the rows, one independent race per candidate).  One warp per row.
+template <int D>
+__global__ void __launch_bounds__(256)
+kpp_step_kernel(const float *__restrict__ x, long long n, const long long *chosen, int step, int k, int trials, u64 seed,
+                float *__restrict__ mind2, float *__restrict__ centers, unsigned long long *next_key)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long c = chosen[step];
+    constexpr int Q = D / 64;  // float2 per lane
+    const float2 *crow = reinterpret_cast<const float2 *>(x + (size_t)c * D);
+    float2 cv[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) cv[q] = __ldg(crow + q * 32 + lane);
+    if (warp == 0) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) reinterpret_cast<float2 *>(centers + (size_t)step * D)[q * 32 + lane] = cv[q];
+    }
+    unsigned long long best[KPP_MAX_TRIALS];
+#pragma unroll
+    for (int l = 0; l < KPP_MAX_TRIALS; ++l) best[l] = ~0ull;
+    for (long long i = warp; i < n; i += nwarps) {
+        float s = 0.0f;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const float2 v = __ldg(reinterpret_cast<const float2 *>(x + (size_t)i * D) + q * 32 + lane);
+            const float a = v.x - cv[q].x, b = v.y - cv[q].y;
+            s += a * a + b * b;
+        }
+#pragma unroll
+        for (int m = 16; m; m >>= 1) s += __shfl_xor_sync(FULL_MASK, s, m);
+        const float old = step == 0 ? INFINITY : mind2[i];
+        const float d2 = fminf(old, s);
+        if (lane == 0) mind2[i] = d2;
+        if (d2 > 0.0f && step + 1 < k && lane < trials) {
+            // lane l runs race l for this row
+            const u64 r = splitmix64(seed ^ splitmix64(((u64)i * KPP_MAX_TRIALS + (u64)lane) * 0x100000001B3ull + (u64)step));
+            const float u = ((float)(r >> 40) + 1.0f) * (1.0f / 16777216.0f);  // (0, 1]
+            const float key = -__logf(u) / d2;
+            const unsigned long long packed = ((unsigned long long)__float_as_uint(key) << 32) | (unsigned long long)(u32)i;
+#pragma unroll
+            for (int l = 0; l < KPP_MAX_TRIALS; ++l)
+                if (l == lane) best[l] = packed < best[l] ? packed : best[l];
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < KPP_MAX_TRIALS; ++l)
+        if (l == lane && lane < trials && best[l] != ~0ull) atomicMin(next_key + l, best[l]);
+}
+
+// Second half (greedy k-means++, as scikit-learn's 2 + log k local trials): the potential
+// sum_i min(D^2_i, |x_i - candidate|^2) of every candidate.  One warp per row, candidates in shared memory.
+template <int D>
+__global__ void __launch_bounds__(256)
+kpp_potential_kernel(const float *__restrict__ x, long long n, const unsigned long long *__restrict__ next_key, int trials,
+                     const float *__restrict__ mind2, double *pot)
+{
+    __shared__ float s_cand[KPP_MAX_TRIALS][D];
+    __shared__ double s_pot[KPP_MAX_TRIALS];
+    const int lane = threadIdx.x & 31;
+    for (int t = threadIdx.x; t < trials * D; t += blockDim.x) {
+        const unsigned long long kx = next_key[t / D];
+        const long long row = kx == ~0ull ? 0 : (long long)(kx & 0xFFFFFFFFull);
+        s_cand[t / D][t % D] = __ldg(x + (size_t)row * D + (t % D));
+    }
+    if (threadIdx.x < KPP_MAX_TRIALS) s_pot[threadIdx.x] = 0.0;
+    __syncthreads();
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    constexpr int Q = D / 32;
+    double local[KPP_MAX_TRIALS];
+#pragma unroll
+    for (int l = 0; l < KPP_MAX_TRIALS; ++l) local[l] = 0.0;
+    for (long long i = warp; i < n; i += nwarps) {
+        float v[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) v[q] = __ldg(x + (size_t)i * D + q * 32 + lane);
+        const float m = mind2[i];
+#pragma unroll
+        for (int l = 0; l < KPP_MAX_TRIALS; ++l) {
+            if (l < trials) {
+                float s = 0.0f;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float a = v[q] - s_cand[l][q * 32 + lane];
+                    s += a * a;
+                }
+#pragma unroll
+                for (int mm = 16; mm; mm >>= 1) s += __shfl_xor_sync(FULL_MASK, s, mm);
+                local[l] += (double)fminf(m, s);
+            }
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int l = 0; l < KPP_MAX_TRIALS; ++l)
+            if (l < trials) atomicAdd(&s_pot[l], local[l]);
+    }
+    __syncthreads();
+    if (threadIdx.x < trials) atomicAdd(pot + threadIdx.x, s_pot[threadIdx.x]);
+}
+
+__global__ void kpp_pick_kernel(const unsigned long long *next_key, const double *pot, int trials, long long *chosen,
+                                int step)
+{
+    int bl = -1;
+    double bp = 0.0;
+    for (int l = 0; l < trials; ++l) {
+        if (next_key[l] == ~0ull) continue;
+        if (bl < 0 || pot[l] < bp) {
+            bl = l;
+            bp = pot[l];
+        }
+    }
+    // every row coincides with a centre already (fewer distinct rows than centres): reuse row 0
+    chosen[step + 1] = bl < 0 ? 0 : (long long)(next_key[bl] & 0xFFFFFFFFull);
+}
+
+// sums[label] += row, counts[label]++, inertia += D^2 (one warp per row).
+template <int D>
+__global__ void __launch_bounds__(256)
+kmeans_accumulate_kernel(const float *__restrict__ x, long long n, const unsigned long long *__restrict__ best,
+                         float *sums, int *counts, double *inertia)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    double local = 0.0;
+    for (long long i = warp; i < n; i += nwarps) {
+        const unsigned long long kx = best[i];
+        const int lab = (int)(kx & 0xFFFFFFFFull);
+        float *dst = sums + (size_t)lab * D;
+        for (int t = lane; t < D; t += 32) atomicAdd(dst + t, __ldg(x + (size_t)i * D + t));
+        if (lane == 0) {
+            atomicAdd(counts + lab, 1);
+            local += (double)__uint_as_float((u32)(kx >> 32));
+        }
+    }
+    if (lane == 0 && local != 0.0) atomicAdd(inertia, local);
+}
+
+// centres := sums / counts (an empty cluster keeps its centre); shift2 = sum of squared moves.
+__global__ void kmeans_finish_kernel(const float *__restrict__ sums, const int *__restrict__ counts, long long k, int d,
+                                     float *centers, double *shift2)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double mv = 0.0;
+    if (i < k * d) {
+        const int cnt = counts[i / d];
+        const float old = centers[i];
+        const float nw = cnt > 0 ? sums[i] / (float)cnt : old;
+        centers[i] = nw;
+        mv = (double)(nw - old) * (double)(nw - old);
+    }
+#pragma unroll
+    for (int m = 16; m; m >>= 1) mv += __shfl_xor_sync(FULL_MASK, mv, m);
+    if ((threadIdx.x & 31) == 0 && mv != 0.0) atomicAdd(shift2, mv);
+}
+
+}  // namespace
+
+extern "C" int gp_kmeans_assign(const float *d_emb, const float *d_centers, int64_t num_nodes, int64_t num_centers,
+                                int64_t dim, uint64_t *d_best, gp_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GP_REQUIRE(num_nodes >= 0 && num_centers > 0, GP_ERR_INVALID, "gp_kmeans_assign: bad sizes");
+    GP_REQUIRE(dim == 64 || dim == 128, GP_ERR_UNSUPPORTED, "gp_kmeans_assign: embedding dimension must be 64 or 128");
+    if (num_nodes == 0) return GP_OK;
+    GP_REQUIRE(d_emb != nullptr && d_centers != nullptr && d_best != nullptr, GP_ERR_INVALID, "gp_kmeans_assign: NULL argument");
+    GP_LAUNCH(fill_u64_kernel, (unsigned)gp_ceil_div(num_nodes, 256), 256, 0, stream, (unsigned long long *)d_best,
+              num_nodes, ~0ull);
+    CdistParams p;
+    memset(&p, 0, sizeof(p));
+    p.emb = d_emb;
+    p.anc = d_centers;
+    p.n = num_nodes;
+    p.k = num_centers;
+    p.d = dim;
+    p.mode = GP_CDIST_EUCLIDEAN;
+    p.best = reinterpret_cast<unsigned long long *>(d_best);
+    const int64_t col_tiles = gp_ceil_div(num_centers, CD_MAX_N);
+    const int64_t ktile = num_centers < CD_MAX_N ? num_centers : CD_MAX_N;
+    const int n_pad = (int)(gp_ceil_div(ktile, 32) * 32);
+    const size_t smem = cdist_smem_bytes((int)dim, n_pad);
+    const int64_t row_tiles = gp_ceil_div(num_nodes, CD_TILE_M);
+    int grid_x = gp_sm_count();
+    if (row_tiles < grid_x) grid_x = (int)row_tiles;
+    const dim3 grid(grid_x, (unsigned)col_tiles);
+    gp_count_launch();
+    if (dim == 128) {
+        GP_CUDA_CHECK(cudaFuncSetAttribute(cdist_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cdist_kernel<128><<<grid, CD_THREADS2, smem, stream>>>(p, n_pad, 0, 0, 0);
+    } else {
+        GP_CUDA_CHECK(cudaFuncSetAttribute(cdist_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cdist_kernel<64><<<grid, CD_THREADS2, smem, stream>>>(p, n_pad, 0, 0, 0);
+    }
+    GP_CUDA_CHECK(cudaGetLastError());
+    return GP_OK;
+}
+
+extern "C" int gp_kmeans_update(const float *d_emb, const uint64_t *d_best, int64_t num_nodes, int64_t num_centers,
+                                int64_t dim, float *d_centers, float *d_sums, int32_t *d_counts, double *d_shift2,
+                                double *d_inertia, gp_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GP_REQUIRE(dim == 64 || dim == 128, GP_ERR_UNSUPPORTED, "gp_kmeans_update: embedding dimension must be 64 or 128");
+    GP_REQUIRE(d_emb && d_best && d_centers && d_sums && d_counts && d_shift2 && d_inertia, GP_ERR_INVALID,
+               "gp_kmeans_update: NULL argument");
+    GP_CUDA_CHECK(cudaMemsetAsync(d_sums, 0, sizeof(float) * (size_t)(num_centers * dim), stream));
+    GP_CUDA_CHECK(cudaMemsetAsync(d_counts, 0, sizeof(int) * (size_t)num_centers, stream));
+    GP_CUDA_CHECK(cudaMemsetAsync(d_shift2, 0, sizeof(double), stream));
+    GP_CUDA_CHECK(cudaMemsetAsync(d_inertia, 0, sizeof(double), stream));
+    const int blocks = (int)std::min<int64_t>(gp_ceil_div(num_nodes > 0 ? num_nodes : 1, 8), (int64_t)gp_sm_count() * 16);
+    if (dim == 128)
+        GP_LAUNCH(kmeans_accumulate_kernel<128>, blocks, 256, 0, stream, d_emb, num_nodes, (const unsigned long long *)d_best,
+                  d_sums, d_counts, d_inertia);
+    else
+        GP_LAUNCH(kmeans_accumulate_kernel<64>, blocks, 256, 0, stream, d_emb, num_nodes, (const unsigned long long *)d_best,
+                  d_sums, d_counts, d_inertia);
+    GP_LAUNCH(kmeans_finish_kernel, (unsigned)gp_ceil_div(num_centers * dim, 256), 256, 0, stream, d_sums, d_counts,
+              num_centers, (int)dim, d_centers, d_shift2);
+    GP_CUDA_CHECK(cudaGetLastError());
+    return GP_OK;
+}
+
+extern "C" int gp_kmeans_plusplus(const float *d_emb, int64_t num_nodes, int64_t num_centers, int64_t dim,
+                                  int64_t first_index, uint64_t seed, float *d_centers, float *d_mind2,
+                                  int64_t *d_chosen, gp_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GP_REQUIRE(dim == 64 || dim == 128, GP_ERR_UNSUPPORTED, "gp_kmeans_plusplus: embedding dimension must be 64 or 128");
+    GP_REQUIRE(num_nodes > 0 && num_centers > 0 && first_index >= 0 && first_index < num_nodes, GP_ERR_INVALID,
+               "gp_kmeans_plusplus: bad sizes");
+    GP_REQUIRE(d_emb && d_centers && d_mind2 && d_chosen, GP_ERR_INVALID, "gp_kmeans_plusplus: NULL argument");
+    // greedy k-means++: 2 + log(K) candidates per step (scikit-learn's n_local_trials), the one that lowers
+    // the potential most wins
+    int trials = 2 + (int)log((double)num_centers);
+    if (trials > KPP_MAX_TRIALS) trials = KPP_MAX_TRIALS;
+    if (trials < 1) trials = 1;
+    unsigned long long *key = nullptr;  // [KPP_MAX_TRIALS] race winners, then [KPP_MAX_TRIALS] doubles (potentials)
+    GP_CUDA_CHECK(cudaMalloc((void **)&key, 2 * KPP_MAX_TRIALS * sizeof(unsigned long long)));
+    double *pot = reinterpret_cast<double *>(key + KPP_MAX_TRIALS);
+    long long first = first_index;
+    cudaError_t e = cudaMemcpyAsync(d_chosen, &first, sizeof(long long), cudaMemcpyHostToDevice, stream);
+    const int blocks = (int)std::min<int64_t>(gp_ceil_div(num_nodes, 8), (int64_t)gp_sm_count() * 16);
+    for (int64_t s = 0; e == cudaSuccess && s < num_centers; ++s) {
+        GP_LAUNCH(fill_u64_kernel, 1, 32, 0, stream, key, (long long)KPP_MAX_TRIALS, ~0ull);
+        e = cudaMemsetAsync(pot, 0, KPP_MAX_TRIALS * sizeof(double), stream);
+        if (e != cudaSuccess) break;
+        if (dim == 128)
+            GP_LAUNCH(kpp_step_kernel<128>, blocks, 256, 0, stream, d_emb, num_nodes, (const long long *)d_chosen, (int)s,
+                      (int)num_centers, trials, (u64)seed, d_mind2, d_centers, key);
+        else
+            GP_LAUNCH(kpp_step_kernel<64>, blocks, 256, 0, stream, d_emb, num_nodes, (const long long *)d_chosen, (int)s,
+                      (int)num_centers, trials, (u64)seed, d_mind2, d_centers, key);
+        if (s + 1 < num_centers) {
+            if (dim == 128)
+                GP_LAUNCH(kpp_potential_kernel<128>, blocks, 256, 0, stream, d_emb, num_nodes, key, trials, d_mind2, pot);
+            else
+                GP_LAUNCH(kpp_potential_kernel<64>, blocks, 256, 0, stream, d_emb, num_nodes, key, trials, d_mind2, pot);
+            GP_LAUNCH(kpp_pick_kernel, 1, 1, 0, stream, key, pot, trials, (long long *)d_chosen, (int)s);
+        }
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // `first` and `key` live until the stream is done
+    cudaFree(key);
+    GP_CUDA_CHECK(e);
     return GP_OK;
 }

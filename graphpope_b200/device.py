@@ -300,3 +300,48 @@ def cdist_minmax(emb: torch.Tensor, anchor_emb: torch.Tensor, mode: int | str, a
     check(lib.gp_cdist_minmax(_ptr(emb), _ptr(anchor_emb), n, k, d, int(mode), int(bool(apply_minmax)),
                               _ptr(out), out.stride(0) if n > 1 else out.size(1), col_offset, _stream()))
     return out
+
+
+def kmeans(table: torch.Tensor, num_clusters: int, n_init: int = 10, max_iter: int = 300, tol: float = 1.0e-4,
+           seed: int | None = None):
+    """KMeans cluster centres of the node2vec table on the device (utils.py:168-170 uses scikit-learn's
+    ``KMeans(n_clusters=K).fit(table).cluster_centers_`` with its defaults: k-means++, n_init = 10,
+    max_iter = 300, tol = 1e-4 scaled by the mean feature variance, unseeded).
+
+    Returns ``(centers float32 [K, D] on the device, inertia, iterations of the best run)``.  Parity with
+    scikit-learn is statistical (the reference does not seed it): same objective, same stopping rule.
+    """
+    lib = _lib.require_cuda()
+    x = table.to(device="cuda", dtype=torch.float32).contiguous()
+    n, d = x.shape
+    k = int(num_clusters)
+    if k <= 0 or k > n:
+        raise ValueError(f"n_clusters={k} must be in [1, {n}]")
+    rng = np.random.default_rng(seed)
+    tol_abs = float(tol) * float(x.var(dim=0, unbiased=False).mean().item())  # sklearn _tolerance()
+    centers = torch.empty((k, d), dtype=torch.float32, device="cuda")
+    mind2 = torch.empty(n, dtype=torch.float32, device="cuda")
+    chosen = torch.empty(k, dtype=torch.int64, device="cuda")
+    best = torch.empty(n, dtype=torch.int64, device="cuda")  # uint64 payload
+    sums = torch.empty((k, d), dtype=torch.float32, device="cuda")
+    counts = torch.empty(k, dtype=torch.int32, device="cuda")
+    scal = torch.zeros(2, dtype=torch.float64, device="cuda")  # [shift2, inertia]
+    result = None
+    for _ in range(max(1, int(n_init))):
+        check(lib.gp_kmeans_plusplus(_ptr(x), n, k, d, int(rng.integers(0, n)), int(rng.integers(0, 2**63 - 1)),
+                                     _ptr(centers), _ptr(mind2), _ptr(chosen), _stream()))
+        iters = 0
+        for it in range(1, int(max_iter) + 1):
+            check(lib.gp_kmeans_assign(_ptr(x), _ptr(centers), n, k, d, _ptr(best), _stream()))
+            check(lib.gp_kmeans_update(_ptr(x), _ptr(best), n, k, d, _ptr(centers), _ptr(sums), _ptr(counts),
+                                       c_void_p(scal.data_ptr()), c_void_p(scal.data_ptr() + 8), _stream()))
+            iters = it
+            if it % 4 == 0 or it == max_iter:  # the stopping test needs a host round trip: every 4th iteration
+                if float(scal[0].item()) <= tol_abs:
+                    break
+        # inertia of the final centres (the update above measured the assignment to the previous ones)
+        check(lib.gp_kmeans_assign(_ptr(x), _ptr(centers), n, k, d, _ptr(best), _stream()))
+        inertia = float((best >> 32).to(torch.int32).view(torch.float32).double().sum().item())
+        if result is None or inertia < result[1]:
+            result = (centers.clone(), inertia, iters)
+    return result

@@ -23,8 +23,10 @@ What runs where
   * ``stochastic`` anchors: host numpy global RNG, exactly utils.py:22-24 (same seed, same anchors).
   * ``degree_centrality`` / ``pagerank`` / ``closeness_centrality`` anchors: device (degree array, float64
     SpMV power iteration, MS-BFS from every node + bit-sliced column sums; stable top-k).
-  * betweenness / eigenvector / clustering anchors and KMeans centres: the reference's own
-    networkx / scikit-learn calls on the host (stated scope of the port).
+  * KMeans centres of the node2vec branch: device (k-means++ + Lloyd, tensor-core assignment; statistical
+    parity with scikit-learn, which the reference runs unseeded).
+  * betweenness / eigenvector / clustering anchors: the reference's own networkx calls on the host (stated
+    scope of the port).
 There is no CPU fallback for the device parts: without the CUDA library or a GPU these functions raise.
 """
 from __future__ import annotations
@@ -286,11 +288,15 @@ def attach_node2vec(data, dataset, num_anchor_nodes, sampling_method, distance_f
         anchor_nodes = sample_anchor_nodes(data, num_anchor_nodes, sampling_method='stochastic')
         anchor_emb = table[torch.as_tensor(np.asarray(anchor_nodes, dtype=np.int64))]
     else:
-        # anything but 'stochastic' means KMeans centres (utils.py:168-170); stays on scikit-learn
-        from sklearn.cluster import KMeans
+        # anything but 'stochastic' means KMeans centres (utils.py:168-170).  Lloyd + k-means++ run on the
+        # device (tensor-core assignment); GRAPHPOPE_KMEANS=sklearn keeps the reference's scikit-learn call.
+        if os.environ.get("GRAPHPOPE_KMEANS", "device") == "sklearn" or table.size(1) not in (64, 128):
+            from sklearn.cluster import KMeans
 
-        kmeans = KMeans(n_clusters=num_anchor_nodes).fit(table.numpy())
-        anchor_emb = torch.as_tensor(kmeans.cluster_centers_)
+            kmeans = KMeans(n_clusters=num_anchor_nodes).fit(table.numpy())
+            anchor_emb = torch.as_tensor(kmeans.cluster_centers_)
+        else:
+            anchor_emb, _, _ = _dev.kmeans(table, num_anchor_nodes)
         _say('K means cluster anchor nodes derived!')
     block = _dev.cdist_minmax(table, anchor_emb, mode, apply_minmax=True)
     out = concat_into_features(block if _output_device() == "cuda" else block.cpu(), data)

@@ -208,6 +208,24 @@ int gp_host_concat(const float *h_x, int64_t num_features, const float *h_block,
 int gp_block_to_host(const float *d_block, int64_t num_nodes, int64_t block_cols, float *h_out, int64_t ld_out,
                      int64_t col_offset, gp_stream_t stream);
 
+/* ------------------------------------------------------------------ KMeans anchors (node2vec branch)
+ * attach_node2vec takes the KMeans centres of the node2vec table as anchors for every sampling_method but
+ * 'stochastic' (utils.py:168-170).  Three building blocks, driven by graphpope_b200.device.kmeans:
+ *   gp_kmeans_plusplus  k-means++ seeding (exact D^2 sampling by an exponential race); syncs.
+ *                       d_centers float32[K, D] out, d_mind2 float32[N] scratch, d_chosen int64[K] out.
+ *   gp_kmeans_assign    nearest centre of every row on the tensor cores (the pairwise kernel in arg-min
+ *                       mode, nothing but the result leaves the SM); async.  d_best uint64[N]:
+ *                       (float bits of the squared distance << 32) | centre index.
+ *   gp_kmeans_update    centres := mean of their rows (an empty cluster keeps its centre); *d_shift2 =
+ *                       sum of squared centre moves, *d_inertia = sum of squared distances; async.       */
+int gp_kmeans_plusplus(const float *d_emb, int64_t num_nodes, int64_t num_centers, int64_t dim, int64_t first_index,
+                       uint64_t seed, float *d_centers, float *d_mind2, int64_t *d_chosen, gp_stream_t stream);
+int gp_kmeans_assign(const float *d_emb, const float *d_centers, int64_t num_nodes, int64_t num_centers, int64_t dim,
+                     uint64_t *d_best, gp_stream_t stream);
+int gp_kmeans_update(const float *d_emb, const uint64_t *d_best, int64_t num_nodes, int64_t num_centers, int64_t dim,
+                     float *d_centers, float *d_sums, int32_t *d_counts, double *d_shift2, double *d_inertia,
+                     gp_stream_t stream);
+
 /* ------------------------------------------------------------------ samplers
  * degree_centrality (utils.py:38-42): in+out degree over de-duplicated edges
  * (a self-loop counts 2).  async.  d_degree int32[N].                           */

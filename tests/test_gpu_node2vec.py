@@ -109,3 +109,43 @@ def test_unsupported_dim_is_loud(dev):
     from graphpope_b200._lib import GraphpopeError
     with pytest.raises(GraphpopeError):
         dev.cdist_minmax(torch.zeros(10, 100), torch.zeros(2, 100), "euclidean")
+
+
+def test_kmeans_assign_matches_fp32_argmin():
+    """The tcgen05 kernel in arg-min mode: nearest centre and squared distance of every row."""
+    import ctypes
+    from graphpope_b200 import _lib
+    from graphpope_b200.device import _ptr, _stream
+    lib = _lib.require_cuda()
+    rng = np.random.default_rng(5)
+    for n, k, d in ((1000, 7, 64), (5000, 256, 128), (3000, 300, 128)):
+        x = torch.as_tensor(rng.standard_normal((n, d)).astype(np.float32)).cuda()
+        c = torch.as_tensor(rng.standard_normal((k, d)).astype(np.float32)).cuda()
+        best = torch.empty(n, dtype=torch.int64, device="cuda")
+        _lib.check(lib.gp_kmeans_assign(_ptr(x), _ptr(c), n, k, d, _ptr(best), _stream()))
+        lab = (best & 0xFFFFFFFF).cpu().numpy()
+        d2 = (best >> 32).to(torch.int32).view(torch.float32).cpu().numpy()
+        full = torch.cdist(x.double(), c.double()).pow(2).cpu().numpy()
+        want = full.min(axis=1)
+        assert np.allclose(d2, want, rtol=1e-4, atol=1e-4)
+        # the chosen centre is (numerically) a nearest one
+        assert np.all(full[np.arange(n), lab] <= want * (1 + 1e-4) + 1e-4)
+
+
+def test_device_kmeans_inertia_close_to_sklearn():
+    """Statistical parity (the reference runs scikit-learn unseeded, utils.py:169): same objective within
+    2 % on a clustered table and on the Gaussian table the reference's generator actually produces."""
+    from sklearn.cluster import KMeans
+    from graphpope_b200 import device as dev
+    rng = np.random.default_rng(11)
+    centres = rng.standard_normal((24, 64)).astype(np.float32) * 4
+    clustered = (centres[rng.integers(0, 24, 6000)] + rng.standard_normal((6000, 64)).astype(np.float32)).astype(np.float32)
+    gauss = synth.node2vec_table(4000, 128, seed=3)
+    for table, k in ((clustered, 24), (gauss, 32)):
+        got_c, got_inertia, iters = dev.kmeans(torch.as_tensor(table), k, n_init=4, seed=0)
+        ref = KMeans(n_clusters=k, n_init=4, random_state=0).fit(table)
+        assert got_c.shape == (k, table.shape[1]) and 1 <= iters <= 300
+        assert got_inertia <= ref.inertia_ * 1.02, (got_inertia, ref.inertia_)
+        # the reported inertia is the objective of the returned centres
+        d2 = torch.cdist(torch.as_tensor(table).double(), got_c.cpu().double()).pow(2).min(dim=1).values.sum().item()
+        assert abs(d2 - got_inertia) <= 1e-3 * d2
