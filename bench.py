@@ -275,6 +275,27 @@ def main():
     ms_per_step = total_ms / args.steps
     value = k_total * e_unique / (ms_per_step * 1e-3) / 1e9
 
+    # ---- per-stage device times (N = 1 only; same inputs, each stage timed alone after the L2 flush)
+    stages = None
+    if world == 1:
+        def timed(fn, reps=10):
+            ms = []
+            for i in range(reps):
+                flush.fill_(float(i))
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record(); torch.cuda.synchronize()
+                ms.append(a.elapsed_time(b))
+            return float(np.median(ms))
+        engine.csr.build(ei_d); engine.bfs.run(a_d); engine.bfs.features(x_d, out_d); torch.cuda.synchronize()
+        csr_ms = timed(lambda: engine.csr.build(ei_d))
+        bfs_ms_alone = timed(lambda: engine.bfs.run(a_d))
+        dec_ms = timed(lambda: engine.bfs.features(x_d, out_d))
+        b_epi = 6 * n * K_PER_GPU + 8 * n * f  # B_epi + B_cat
+        stages = {"csr_build_ms": csr_ms, "msbfs_run_ms": bfs_ms_alone, "decode_concat_ms": dec_ms,
+                  "decode_concat_gbs": b_epi / (dec_ms * 1e-3) / 1e9,
+                  "note": "each stage launched eagerly on its own (the step replays them from one CUDA graph); "
+                          "decode_concat bytes = 6*N*K + 8*N*F"}
+
     # ---- e2e: the public host-buffer API, H2D + D2H inside the timed region
     ei_h = torch.as_tensor(ei).pin_memory()
     x_h = torch.randn(n, f).pin_memory()
@@ -348,6 +369,9 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clock_info,
         }
+        if stages:
+            stages["decode_concat_frac_of_hbm_peak"] = stages["decode_concat_gbs"] / peak
+            line["stages"] = stages
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)

@@ -185,3 +185,116 @@ extern "C" int gp_closeness(const gp_csr_t *csr_, double *d_score, gp_stream_t s
     gp_msbfs_free(h);
     return rc;
 }
+
+// ================================================================= clustering coefficient (utils.py:56-60)
+// nx.clustering(G) on the DiGraph (Fagiolo's directed clustering): for node i with predecessors P and
+// successors S (self-loops dropped),
+//   t  = sum over j in chain(P, S) of |P & Pj| + |P & Sj| + |S & Pj| + |S & Sj|
+//   c  = 0 if t == 0 else t / (2 * (dt * (dt - 1) - 2 * db)),   dt = |P| + |S|, db = |P & S|.
+// One CTA per node: P and S become two node bitmaps in shared memory, then every (j, k in Pj or Sj) pair
+// is two bit tests; all counts are integers and the one division is float64, so the scores are bit-equal
+// to networkx's.  Graphs whose two bitmaps do not fit in shared memory are not supported (the host layer
+// then keeps the reference's networkx call).
+namespace {
+
+constexpr int CL_THREADS = 256;
+
+__global__ void __launch_bounds__(CL_THREADS)
+clustering_kernel(const int *__restrict__ row_start, const int *__restrict__ deg, const int *__restrict__ col,
+                  const int *__restrict__ rowptr_in, const int *__restrict__ col_in, long long n, int words,
+                  double *__restrict__ score)
+{
+    extern __shared__ u32 s_bits[];  // [2][words]: membership in P, in S
+    __shared__ unsigned long long s_t;
+    __shared__ int s_db, s_dt;
+    u32 *bp = s_bits, *bs = s_bits + words;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int w = tid; w < 2 * words; w += CL_THREADS) s_bits[w] = 0;
+    __syncthreads();
+    for (long long i = blockIdx.x; i < n; i += gridDim.x) {
+        const int s0 = row_start[i], sd = deg[i];            // successors: col[s0 .. s0 + sd)
+        const int p0 = rowptr_in[i], pd = rowptr_in[i + 1] - p0;  // predecessors: col_in[p0 .. p0 + pd)
+        if (tid == 0) {
+            s_t = 0;
+            s_db = 0;
+            s_dt = 0;
+        }
+        for (int e = tid; e < pd; e += CL_THREADS) {
+            const int v = col_in[p0 + e];
+            if (v != i) atomicOr(&bp[v >> 5], 1u << (v & 31));
+        }
+        for (int e = tid; e < sd; e += CL_THREADS) {
+            const int v = col[s0 + e];
+            if (v != i) atomicOr(&bs[v >> 5], 1u << (v & 31));
+        }
+        __syncthreads();
+        // dt, db
+        int dt = 0, db = 0;
+        for (int e = tid; e < pd; e += CL_THREADS) dt += col_in[p0 + e] != i;
+        for (int e = tid; e < sd; e += CL_THREADS) {
+            const int v = col[s0 + e];
+            if (v != i) {
+                ++dt;
+                db += (bp[v >> 5] >> (v & 31)) & 1u;
+            }
+        }
+        dt = __reduce_add_sync(FULL_MASK, dt);
+        db = __reduce_add_sync(FULL_MASK, db);
+        if (lane == 0) {
+            atomicAdd(&s_dt, dt);
+            atomicAdd(&s_db, db);
+        }
+        // triangles: one warp per j of chain(P, S), lanes over the neighbours k of j
+        unsigned long long t = 0;
+        for (int e = warp; e < pd + sd; e += CL_THREADS / 32) {
+            const int j = e < pd ? col_in[p0 + e] : col[s0 + (e - pd)];
+            if (j == i) continue;
+            const int js0 = row_start[j], jsd = deg[j];
+            const int jp0 = rowptr_in[j], jpd = rowptr_in[j + 1] - jp0;
+            for (int q = lane; q < jpd + jsd; q += 32) {
+                const int k = q < jpd ? col_in[jp0 + q] : col[js0 + (q - jpd)];
+                if (k != j) t += ((bp[k >> 5] >> (k & 31)) & 1u) + ((bs[k >> 5] >> (k & 31)) & 1u);
+            }
+        }
+        for (int m = 16; m; m >>= 1) t += shfl_xor_u64(t, m);
+        if (lane == 0 && t) atomicAdd(&s_t, t);
+        __syncthreads();
+        if (tid == 0) {
+            const double tt = (double)s_t;
+            const long long dtl = s_dt, dbl = s_db;
+            score[i] = s_t == 0 ? 0.0 : __ddiv_rn(tt, (double)((dtl * (dtl - 1) - 2 * dbl) * 2));
+        }
+        // clear exactly the bits that were set
+        for (int e = tid; e < pd; e += CL_THREADS) bp[col_in[p0 + e] >> 5] = 0;
+        for (int e = tid; e < sd; e += CL_THREADS) bs[col[s0 + e] >> 5] = 0;
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+extern "C" int gp_clustering(const gp_csr_t *csr_, double *d_score, gp_stream_t stream_)
+{
+    gp_csr *csr = const_cast<gp_csr *>(csr_);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GP_REQUIRE(csr != nullptr && d_score != nullptr, GP_ERR_INVALID, "gp_clustering: NULL argument");
+    GP_REQUIRE(csr->built, GP_ERR_INVALID, "gp_clustering: the CSR has not been built");
+    const long long n = csr->num_nodes;
+    if (n == 0) return GP_OK;
+    const int words = (int)((n + 31) / 32);
+    const size_t smem = 2 * (size_t)words * sizeof(u32);
+    GP_REQUIRE(smem <= 200 * 1024, GP_ERR_UNSUPPORTED,
+               "gp_clustering: two %lld-node bitmaps do not fit in shared memory", n);
+    GP_TRY(gp_csr_ensure_in(csr, stream));
+    GP_CUDA_CHECK(cudaFuncSetAttribute(clustering_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)(200 * 1024 / (smem > 0 ? smem : 1));
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (long long)gp_sm_count() * per_sm;
+    if (blocks > n) blocks = n;
+    GP_LAUNCH(clustering_kernel, (unsigned)blocks, CL_THREADS, smem, stream, csr->row_start, csr->deg, csr->col,
+              csr->rowptr_in, csr->col_in, n, words, d_score);
+    GP_CUDA_CHECK(cudaGetLastError());
+    GP_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return GP_OK;
+}

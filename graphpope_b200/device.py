@@ -93,6 +93,12 @@ class DeviceCsr:
         check(self._lib.gp_closeness(self._h, _ptr(x), _stream()))
         return x
 
+    def clustering(self) -> torch.Tensor:
+        """networkx ``clustering(G)`` on the DiGraph (utils.py:56-60): float64[N], bit-equal scores."""
+        x = torch.empty(self.num_nodes, dtype=torch.float64, device="cuda")
+        check(self._lib.gp_clustering(self._h, _ptr(x), _stream()))
+        return x
+
     def close(self):
         if self._h:
             self._lib.gp_csr_free(self._h)

@@ -21,11 +21,12 @@ the CPU process pool it sized (utils.py:98) is replaced by one multi-source BFS 
 What runs where
   * geodesic distances, 1/(d+1) normalisation, concat: device (libgraphpope_b200.so).
   * ``stochastic`` anchors: host numpy global RNG, exactly utils.py:22-24 (same seed, same anchors).
-  * ``degree_centrality`` / ``pagerank`` / ``closeness_centrality`` anchors: device (degree array, float64
-    SpMV power iteration, MS-BFS from every node + bit-sliced column sums; stable top-k).
+  * ``degree_centrality`` / ``pagerank`` / ``closeness_centrality`` / ``clustering_coefficient`` anchors: device
+    (degree array, float64 SpMV power iteration, MS-BFS from every node + bit-sliced column sums, directed
+    triangle counting; stable top-k).
   * KMeans centres of the node2vec branch: device (k-means++ + Lloyd, tensor-core assignment; statistical
     parity with scikit-learn, which the reference runs unseeded).
-  * betweenness / eigenvector / clustering anchors: the reference's own networkx calls on the host (stated
+  * betweenness / eigenvector anchors: the reference's own networkx calls on the host (stated
     scope of the port).
 There is no CPU fallback for the device parts: without the CUDA library or a GPU these functions raise.
 """
@@ -94,7 +95,7 @@ def _store_block(path, block):
     torch.save(block.detach().cpu().contiguous(), tmp)
     os.replace(tmp, path)  # atomic: DDP ranks may race to write the same key
 
-_HOST_CENTRALITIES = ("betweenness_centrality", "eigenvector_centrality", "clustering_coefficient")
+_HOST_CENTRALITIES = ("betweenness_centrality", "eigenvector_centrality", "clustering_coefficient")  # clustering: large graphs only
 
 last_stats: dict = {}  # stats of the most recent MS-BFS (levels, edges examined, ...)
 
@@ -149,6 +150,12 @@ def sample_anchor_nodes(data, num_anchor_nodes, sampling_method):
         # every node as an anchor of the MS-BFS + bit-sliced column sums (gp_closeness.cu)
         csr = _device_csr(data)
         return _dev.topk_stable(csr.closeness(), num_anchor_nodes).cpu().tolist()
+
+    if sampling_method == 'clustering_coefficient' and int(data.num_nodes) <= 800_000:
+        # directed triangle counting against shared-memory node bitmaps (gp_closeness.cu); larger graphs
+        # keep the networkx call below
+        csr = _device_csr(data)
+        return _dev.topk_stable(csr.clustering(), num_anchor_nodes).cpu().tolist()
 
     if sampling_method in _HOST_CENTRALITIES:
         # Not re-implemented (north_star): the reference's own networkx call, same top-k rule.

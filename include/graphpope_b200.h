@@ -240,6 +240,10 @@ int gp_pagerank(const gp_csr_t *csr, double alpha, double tol, int32_t max_iter,
  * anchor plus bit-sliced column sums; float64 in networkx's operation order (bit-equal).  syncs.
  * d_score float64[N].                                                                             */
 int gp_closeness(const gp_csr_t *csr, double *d_score, gp_stream_t stream);
+/* clustering_coefficient (utils.py:56-60 -> nx.clustering on the DiGraph, Fagiolo's directed clustering):
+ * integer triangle and degree counts from shared-memory node bitmaps, one float64 division (bit-equal).
+ * syncs.  d_score float64[N].  GP_ERR_UNSUPPORTED when two N-bit maps do not fit in shared memory.   */
+int gp_clustering(const gp_csr_t *csr, double *d_score, gp_stream_t stream);
 /* Stable top-k of utils.py:29-30 / 41-42: ascending stable sort by score, keep
  * the last k (ties keep ascending node id; output in ascending-score order).
  * async.  d_out int64[min(k, N)] (k == 0 returns all N: list[-0:] quirk).       */

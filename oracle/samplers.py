@@ -3,8 +3,8 @@
 TEST INFRASTRUCTURE — see oracle/__init__.py.
 
 Only the samplers the device path re-implements are restated here
-(stochastic, degree_centrality, pagerank, closeness_centrality).  The other three
-centralities stay on the reference's own networkx calls in the product
+(stochastic, degree_centrality, pagerank, closeness_centrality, clustering_coefficient).
+The other two centralities stay on the reference's own networkx calls in the product
 (north_star).
 
 Third-party arithmetic restated: networkx (unpinned by the reference's
@@ -138,3 +138,30 @@ def closeness_scores(edge_index, num_nodes: int) -> np.ndarray:
 
 def closeness_centrality_anchors(edge_index, num_nodes: int, k: int) -> list:
     return stable_top_k(closeness_scores(edge_index, num_nodes), k)
+
+
+def clustering_scores(edge_index, num_nodes: int) -> np.ndarray:
+    """networkx ``clustering(G)`` on the DiGraph restated (utils.py:56-60 call site; Fagiolo's directed
+    clustering, ``_directed_triangles_and_degree_iter``): integer counts, one true division."""
+    n = int(num_nodes)
+    s, d = dedup_edges(edge_index, n)
+    succ = [set() for _ in range(n)]
+    pred = [set() for _ in range(n)]
+    for u, v in zip(s.tolist(), d.tolist()):
+        if u != v:
+            succ[u].add(v)
+            pred[v].add(u)
+    out = np.zeros(n, dtype=np.float64)
+    for i in range(n):
+        P, S = pred[i], succ[i]
+        t = 0
+        for j in list(P) + list(S):
+            t += len(P & pred[j]) + len(P & succ[j]) + len(S & pred[j]) + len(S & succ[j])
+        dt = len(P) + len(S)
+        db = len(P & S)
+        out[i] = 0.0 if t == 0 else t / ((dt * (dt - 1) - 2 * db) * 2)
+    return out
+
+
+def clustering_coefficient_anchors(edge_index, num_nodes: int, k: int) -> list:
+    return stable_top_k(clustering_scores(edge_index, num_nodes), k)

@@ -111,6 +111,11 @@ def main():
     for k3 in (1, 16, 64, 256):
         out[f"samplers/closeness_centrality/{k3}"] = np.asarray(
             utils.sample_anchor_nodes(data3, k3, "closeness_centrality"), dtype=np.int64)
+    for k3 in (1, 16, 64, 256):
+        out[f"samplers/clustering_coefficient/{k3}"] = np.asarray(
+            utils.sample_anchor_nodes(data3, k3, "clustering_coefficient"), dtype=np.int64)
+    cl = nx.clustering(G3)
+    out["samplers/clustering_scores"] = np.asarray([cl[i] for i in range(n3)], dtype=np.float64)
     cc = nx.closeness_centrality(G3)
     out["samplers/closeness_scores"] = np.asarray([cc[i] for i in range(n3)], dtype=np.float64)
     np.random.seed(42)

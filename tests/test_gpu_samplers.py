@@ -110,3 +110,27 @@ def test_closeness_matches_oracle_on_hard_graphs(dev, case):
     csr = dev.DeviceCsr(n, ei.shape[1]).build(torch.as_tensor(ei).cuda())
     got = csr.closeness().cpu().numpy()
     assert np.array_equal(got, s.closeness_scores(ei, n))
+
+
+def test_clustering_scores_bit_equal_and_anchor_lists(dev, golden_small):
+    """nx.clustering on the DiGraph (utils.py:56-60) from shared-memory node bitmaps."""
+    from graphpope_b200 import utils
+    ei, n = golden_small["samplers/edge_index"], int(golden_small["samplers/n"])
+    csr = dev.DeviceCsr(n, ei.shape[1]).build(torch.as_tensor(ei).cuda())
+    got = csr.clustering().cpu().numpy()
+    assert np.array_equal(got, golden_small["samplers/clustering_scores"])
+    for k in (1, 16, 64, 256):
+        assert utils.sample_anchor_nodes(Data(ei, n), k, "clustering_coefficient") == \
+            golden_small[f"samplers/clustering_coefficient/{k}"].tolist()
+
+
+def test_clustering_matches_oracle_on_a_dense_directed_multigraph(dev):
+    """Self-loops, reciprocal edges, duplicates and a hub: every term of the directed formula."""
+    from oracle import samplers as s
+    n = 400
+    rng = np.random.default_rng(8)
+    ei = synth.random_digraph(n, 6000, seed=41)
+    hub = np.stack([np.zeros(300, dtype=np.int64), rng.choice(n, 300, replace=False)])
+    ei = np.concatenate([ei, hub, hub[::-1][:, :150]], axis=1)
+    csr = dev.DeviceCsr(n, ei.shape[1]).build(torch.as_tensor(ei).cuda())
+    assert np.array_equal(csr.clustering().cpu().numpy(), s.clustering_scores(ei, n))

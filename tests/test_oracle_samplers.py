@@ -49,3 +49,12 @@ def test_closeness_matches_reference(golden_small):
     assert np.array_equal(x, golden_small["samplers/closeness_scores"])  # same operation order -> bit-equal float64
     for k in (1, 16, 64, 256):
         assert s.closeness_centrality_anchors(ei, n, k) == golden_small[f"samplers/closeness_centrality/{k}"].tolist()
+
+
+def test_clustering_matches_reference(golden_small):
+    ei = golden_small["samplers/edge_index"]
+    n = int(golden_small["samplers/n"])
+    x = s.clustering_scores(ei, n)
+    assert np.array_equal(x, golden_small["samplers/clustering_scores"])  # integer counts, one division
+    for k in (1, 16, 64, 256):
+        assert s.clustering_coefficient_anchors(ei, n, k) == golden_small[f"samplers/clustering_coefficient/{k}"].tolist()
