@@ -1,8 +1,7 @@
 // gp_sort.cu — onesweep LSD radix sort + fused unique-compaction (see gp_sort.cuh).
 //
-// Used by the CSR builder (to_networkx replacement, reference utils.py:121), by the
-// degree-ordered work lists of the MS-BFS and by the stable top-k of the centrality
-// samplers (utils.py:29-30,41-42).
+// Used by the stable top-k of the centrality samplers (utils.py:29-30,41-42).  (The CSR builder
+// used it in its first version; it is now a counting sort by row + in-row sorts, gp_csr.cu.)
 #include "gp_sort.cuh"
 
 namespace {
