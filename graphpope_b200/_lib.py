@@ -72,6 +72,7 @@ SIGNATURES = {
     "gp_msbfs_free": (c_int, [c_void_p]),
     "gp_geodesic_run": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                 c_void_p, c_int64, c_int64, c_void_p]),
+    "gp_concat_x": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "gp_msbfs_planes": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int32),
                                 POINTER(c_int32), POINTER(c_int32), c_void_p]),
     "gp_decode_gathered": (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int64, c_int32, c_int32, c_int32,
@@ -95,6 +96,7 @@ SIGNATURES = {
     "gp_pagerank": (c_int, [c_void_p, c_double, c_double, c_int32, c_void_p, POINTER(c_int32), c_void_p]),
     "gp_closeness": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gp_clustering": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "gp_betweenness": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gp_kmeans_plusplus": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_uint64, c_void_p, c_void_p, c_void_p,
                                    c_void_p]),
     "gp_kmeans_assign": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),

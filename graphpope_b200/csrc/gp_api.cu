@@ -311,13 +311,50 @@ cudaStream_t g_capture_stream = nullptr;
 uint64_t g_pipe_clock = 0;
 bool g_capturing = false;
 
+struct SideCopy {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+
+SideCopy &side_copy_state()
+{
+    static thread_local SideCopy sc;
+    return sc;
+}
+
 int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t e, const int64_t *d_anchors,
                        int64_t k, const float *d_x, int64_t f, int64_t ldx, float *d_out, int64_t ldo,
                        int64_t coff, cudaStream_t s)
 {
-    GP_TRY(gp_csr_build(csr, d_ei, e, s));
-    GP_TRY(gp_msbfs_run(bfs, d_anchors, k, s));
-    if (d_out != nullptr) GP_TRY(gp_msbfs_features(bfs, d_x, f, ldx, d_out, ldo, coff, s));
+    // concat_into_features' copy of x (utils.py:133-134) does not depend on the traversal: the csr build
+    // and the MS-BFS are latency-bound and leave HBM idle, so the copy runs beside them as ONE strided
+    // device-to-device transfer on a side stream (a parallel branch of the captured graph) and the
+    // epilogue then only writes the K anchor columns.  GP_XCOPY_OVERLAP=0 keeps the copy in the epilogue.
+    static int overlap = -1;
+    if (overlap < 0) {
+        const char *ev = getenv("GP_XCOPY_OVERLAP");
+        overlap = ev ? atoi(ev) : 1;
+    }
+    const bool side_copy = overlap && d_out != nullptr && d_x != nullptr && f > 0 && csr->num_nodes > 0;
+    SideCopy &sc = side_copy_state();
+    if (side_copy) {
+        if (sc.stream == nullptr) {
+            GP_CUDA_CHECK(cudaStreamCreateWithFlags(&sc.stream, cudaStreamNonBlocking));
+            GP_CUDA_CHECK(cudaEventCreateWithFlags(&sc.fork, cudaEventDisableTiming));
+            GP_CUDA_CHECK(cudaEventCreateWithFlags(&sc.join, cudaEventDisableTiming));
+        }
+        GP_CUDA_CHECK(cudaEventRecord(sc.fork, s));
+        GP_CUDA_CHECK(cudaStreamWaitEvent(sc.stream, sc.fork, 0));
+        GP_CUDA_CHECK(cudaMemcpy2DAsync(d_out, (size_t)ldo * sizeof(float), d_x, (size_t)ldx * sizeof(float),
+                                        (size_t)f * sizeof(float), (size_t)csr->num_nodes,
+                                        cudaMemcpyDeviceToDevice, sc.stream));
+        GP_CUDA_CHECK(cudaEventRecord(sc.join, sc.stream));
+    }
+    int rc = gp_csr_build(csr, d_ei, e, s);
+    if (rc == GP_OK) rc = gp_msbfs_run(bfs, d_anchors, k, s);
+    if (side_copy) GP_CUDA_CHECK(cudaStreamWaitEvent(s, sc.join, 0));  // always re-join (a capture must not end forked)
+    GP_TRY(rc);
+    if (d_out != nullptr) GP_TRY(gp_msbfs_features(bfs, side_copy ? nullptr : d_x, f, ldx, d_out, ldo, coff, s));
     else GP_TRY(gp_msbfs_pack(bfs, (int32_t)coff, nullptr, nullptr, nullptr, nullptr, nullptr, s));  // coff = slot
     return GP_OK;
 }
@@ -405,6 +442,19 @@ extern "C" int gp_geodesic_run(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_
     }
     return run_pipeline_eager(csr, bfs, d_edge_index, num_edges, d_anchors, num_anchors, d_x, num_features, ld_x,
                               d_out, ld_out, col_offset, stream);
+}
+
+extern "C" int gp_concat_x(const float *d_x, int64_t num_nodes, int64_t num_features, int64_t ld_x, float *d_out,
+                           int64_t ld_out, gp_stream_t stream)
+{
+    GP_REQUIRE(num_nodes >= 0 && num_features >= 0 && ld_x >= num_features && ld_out >= num_features, GP_ERR_INVALID,
+               "gp_concat_x: inconsistent sizes");
+    if (num_nodes == 0 || num_features == 0) return GP_OK;
+    GP_REQUIRE(d_x != nullptr && d_out != nullptr, GP_ERR_INVALID, "gp_concat_x: NULL argument");
+    GP_CUDA_CHECK(cudaMemcpy2DAsync(d_out, (size_t)ld_out * sizeof(float), d_x, (size_t)ld_x * sizeof(float),
+                                    (size_t)num_features * sizeof(float), (size_t)num_nodes,
+                                    cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return GP_OK;
 }
 
 // Sharded form: csr build + ms-bfs + pack into exchange slot `slot` (graph-replayed like gp_geodesic_run).

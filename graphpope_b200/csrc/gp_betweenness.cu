@@ -1,0 +1,398 @@
+// gp_betweenness.cu — betweenness-centrality scores for the 'betweenness_centrality' anchor sampler
+// (reference utils.py:32-36: nx.betweenness_centrality(G), then the stable top-k of utils.py:35-36).
+//
+// networkx runs Brandes' algorithm once per source s (betweenness.py: _single_source_shortest_path_basic,
+// _accumulate_basic, _rescale with normalized=True, endpoints=False on the DiGraph):
+//   forward   sigma[s] = 1; BFS over out-edges; sigma[w] = sum of sigma[v] over predecessors v one hop closer
+//   backward  in reverse BFS order: coeff = (1 + delta[w]) / sigma[w]; delta[v] += sigma[v] * coeff for every
+//             predecessor v of w;  betweenness[w] += delta[w]  (w != s)
+//   rescale   betweenness[v] *= 1 / ((N-1)(N-2))   (N > 2)
+// = N BFS runs; the reference does them in Python (hours at Flickr size).  Here: 32 sources per batch, ONE LANE
+// PER SOURCE.  Per-batch state is node-major — dist[N][32] (hop count per source, u8 or u16), sigma[N][32] and
+// coeff[N][32] float64 — so the 32 lanes of a warp read one 32-byte sector of hop counts and one 256-byte row
+// of path counts per neighbour, fully coalesced.  Both sweeps are level-synchronous and *pull* (owner
+// computes): forward, an unsettled row sums sigma over its in-neighbours settled one level earlier; backward,
+// a row at level l sums sigma[v] * coeff[w] over its out-neighbours w at level l+1, where
+// coeff[w] = (1 + delta[w]) / sigma[w] was stored when w was finalised.  No atomics touch floating-point
+// data, every sum has a fixed order (neighbours ascending; hub rows: 64-edge chunks whose partial sums are
+// added in chunk order by the last-arriving warp), so the scores are run-to-run deterministic.  They are NOT
+// bit-equal to networkx: its delta sums run in reverse BFS-queue order, which depends on the column order of
+// edge_index; sigma is exact (integer-valued), delta and the scores agree to a few ulp (tests: rtol 1e-10).
+//
+// One persistent cooperative kernel walks all levels of a group of batches with a grid barrier per level;
+// work is dealt in tiles of items (row or 64-edge chunk of a row) from rotating ticket counters.
+#include <vector>
+
+#include "gp_internal.h"
+
+namespace {
+
+constexpr int BC_LANES = 32;    // sources per batch = lanes of a warp
+constexpr int BC_CHUNK = 64;    // edges per work item
+constexpr int BC_TILE = 4;      // items per ticket
+constexpr int BC_THREADS = 512;
+constexpr int BC_MINB = 2;
+constexpr int BC_UNROLL = 8;    // neighbour hop-count loads in flight per lane
+
+struct BcList {
+    const int4 *items;       // {row, first edge, count | chunk << 8, hub slot or -1}
+    int num_items;
+    const int *col;          // column array the items index
+    const int *hub_chunks;   // [hubs] chunks of each chunked row
+    const int *hub_first;    // [hubs] first partial slot of each chunked row
+};
+
+struct BcParams {
+    BcList fwd, bwd;         // in-edge items (forward sweep), out-edge items (backward sweep)
+    long long n;
+    void *dist;              // [n][32] hop count from the lane's source (all ones = not reached)
+    double *sigma;           // [n][32] shortest-path counts
+    double *coeff;           // [n][32] (1 + delta) / sigma of finalised rows
+    double *partial;         // [chunks of chunked rows][32]
+    u32 *arrive;             // [hubs] arrival counters (left at zero by the finaliser)
+    double *bc;              // [n] running sum of delta over the sources done so far
+    u32 *sync;               // [0] barrier, [1..3] ticket counters, [4..6] "something settled" flags, [7] overflow
+    long long batch0, batch1;
+};
+
+__device__ __forceinline__ double warp_sum_f64(double v)
+{
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v = __dadd_rn(v, __shfl_xor_sync(FULL_MASK, v, m));
+    return v;
+}
+
+template <typename DT>
+__device__ __forceinline__ DT ld_dist(const DT *p)
+{
+    return __ldcg(p);
+}
+
+// One sweep over a work list.  FWD: settle level `lvl + 1` from level `lvl`.  !FWD: finalise level `lvl`
+// from level `lvl + 1` (`maxl` = deepest level of the batch, whose rows have delta = 0).
+template <typename DT, bool FWD>
+__device__ __forceinline__ void bc_sweep(const BcParams &p, const BcList &L, int lvl, int maxl, u32 *ticket, u32 *flag)
+{
+    constexpr DT INF = (DT)~(DT)0;
+    const int lane = threadIdx.x & 31;
+    DT *dist = reinterpret_cast<DT *>(p.dist);
+    const DT want = (DT)(FWD ? lvl : lvl + 1);   // hop count a contributing neighbour must have
+    const bool leaf = !FWD && (lvl + 1 == maxl);  // neighbours at the deepest level: coeff = 1 / sigma
+    bool found_any = false;
+    const int tiles = (L.num_items + BC_TILE - 1) / BC_TILE;
+    u32 next = 0;
+    if (lane == 0) next = atomicAdd(ticket, 1u);
+    for (;;) {
+        const u32 t = __shfl_sync(FULL_MASK, next, 0);
+        if (t >= (u32)tiles) break;
+        if (lane == 0) next = atomicAdd(ticket, 1u);  // fetched while this tile is processed
+        const int i1 = min((int)(t + 1) * BC_TILE, L.num_items);
+        for (int i = (int)t * BC_TILE; i < i1; ++i) {
+            const int4 it = __ldg(L.items + i);
+            const int row = it.x, beg = it.y, cnt = it.z & 0xFF, chunk = it.z >> 8, hub = it.w;
+            const size_t rbase = (size_t)row * BC_LANES + lane;
+            const DT dr = ld_dist(dist + rbase);
+            const bool mine = FWD ? (dr == INF) : (dr == (DT)lvl);
+            if (!__any_sync(FULL_MASK, mine)) continue;
+            double sv = 0.0;
+            if (!FWD && mine) sv = __ldcg(p.sigma + rbase);
+            double acc = 0.0;
+            for (int base = 0; base < cnt; base += 32) {
+                const int c = (base + lane < cnt) ? __ldg(L.col + beg + base + lane) : row;
+                const int m = min(32, cnt - base);
+                for (int j0 = 0; j0 < m; j0 += BC_UNROLL) {
+                    int v[BC_UNROLL];
+                    DT dv[BC_UNROLL];
+#pragma unroll
+                    for (int q = 0; q < BC_UNROLL; ++q) {
+                        // padding slots re-read the row itself, whose hop count never equals `want`
+                        v[q] = __shfl_sync(FULL_MASK, c, (j0 + q) & 31);
+                        if (j0 + q >= m) v[q] = row;
+                    }
+#pragma unroll
+                    for (int q = 0; q < BC_UNROLL; ++q) dv[q] = ld_dist(dist + (size_t)v[q] * BC_LANES + lane);
+#pragma unroll
+                    for (int q = 0; q < BC_UNROLL; ++q) {
+                        if (mine && dv[q] == want) {
+                            const size_t vb = (size_t)v[q] * BC_LANES + lane;
+                            if (FWD) {
+                                acc = __dadd_rn(acc, __ldcg(p.sigma + vb));
+                            } else {
+                                const double cw = leaf ? __ddiv_rn(1.0, __ldcg(p.sigma + vb)) : __ldcg(p.coeff + vb);
+                                acc = __dadd_rn(acc, __dmul_rn(sv, cw));
+                            }
+                        }
+                    }
+                }
+            }
+            if (hub >= 0) {
+                // chunk of a long row: park the partial sum; the warp that arrives last adds them in chunk order
+                const int chunks = __ldg(L.hub_chunks + hub), first = __ldg(L.hub_first + hub);
+                p.partial[((size_t)first + chunk) * BC_LANES + lane] = acc;
+                __syncwarp();
+                u32 old = 0;
+                if (lane == 0) {
+                    __threadfence();  // the warp's 32 partial sums before the arrival
+                    old = atomicAdd(p.arrive + hub, 1u);
+                }
+                old = __shfl_sync(FULL_MASK, old, 0);
+                if (old != (u32)(chunks - 1)) continue;
+                __threadfence();
+                if (lane == 0) p.arrive[hub] = 0;
+                acc = 0.0;
+                for (int ch0 = 0; ch0 < chunks; ch0 += 8) {  // eight loads in flight, added in chunk order
+                    double part[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        part[q] = ch0 + q < chunks ? __ldcg(p.partial + ((size_t)first + ch0 + q) * BC_LANES + lane) : 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (ch0 + q < chunks) acc = __dadd_rn(acc, part[q]);
+                }
+            }
+            if (FWD) {
+                if (mine && acc != 0.0) {  // sigma >= 1 for every settled node, so a non-zero sum = "has a parent"
+                    p.sigma[rbase] = acc;
+                    dist[rbase] = (DT)(lvl + 1);
+                    found_any = true;
+                }
+            } else {
+                if (mine) p.coeff[rbase] = __ddiv_rn(__dadd_rn(1.0, acc), sv);
+                const double tot = warp_sum_f64(mine ? acc : 0.0);
+                if (lane == 0) p.bc[row] = __dadd_rn(__ldcg(p.bc + row), tot);  // the row has one owner per sweep
+            }
+        }
+    }
+    if (FWD && __any_sync(FULL_MASK, found_any) && lane == 0) st_relaxed_u32(flag, 1u);
+}
+
+template <typename DT>
+__global__ void __launch_bounds__(BC_THREADS, BC_MINB) bc_kernel(BcParams p)
+{
+    constexpr DT INF = (DT)~(DT)0;
+    const int lane = threadIdx.x & 31;
+    const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    DT *dist = reinterpret_cast<DT *>(p.dist);
+    u32 target = 0;  // barrier arrivals so far (the counter is zeroed before every launch)
+    u32 pass = 0;    // sweeps so far: ticket counter / flag `pass % 3` is live, `(pass + 1) % 3` is being cleared
+    bool overflow = false;
+    for (long long batch = p.batch0; batch < p.batch1 && !overflow; ++batch) {
+        const long long src = batch * BC_LANES + lane;  // this lane's source node (>= n: idle lane)
+        for (long long w = gwarp; w < p.n; w += nwarps) {
+            dist[(size_t)w * BC_LANES + lane] = (w == src) ? (DT)0 : INF;
+            if (w == src) p.sigma[(size_t)w * BC_LANES + lane] = 1.0;
+        }
+        grid_barrier(p.sync, target, gridDim.x);
+        int lvl = 0;
+        for (;;) {
+            bc_sweep<DT, true>(p, p.fwd, lvl, 0, p.sync + 1 + pass % 3, p.sync + 4 + pass % 3);
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                // counter / flag of the NEXT sweep: last touched two sweeps ago, i.e. before the previous barrier
+                p.sync[1 + (pass + 1) % 3] = 0;
+                p.sync[4 + (pass + 1) % 3] = 0;
+            }
+            grid_barrier(p.sync, target, gridDim.x);
+            const u32 found = ld_relaxed_u32(p.sync + 4 + pass % 3);
+            ++pass;
+            if (!found) break;
+            ++lvl;
+            if (lvl + 1 >= (int)INF) {  // the next level could not be told from "not reached"
+                overflow = true;
+                break;
+            }
+        }
+        if (overflow) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) p.sync[7] = 1;
+            break;
+        }
+        const int maxl = lvl;  // levels 0..maxl exist; rows at maxl have delta = 0 and contribute nothing
+        for (int l = maxl - 1; l >= 1; --l) {
+            bc_sweep<DT, false>(p, p.bwd, l, maxl, p.sync + 1 + pass % 3, nullptr);
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                // counter / flag of the NEXT sweep: last touched two sweeps ago, i.e. before the previous barrier
+                p.sync[1 + (pass + 1) % 3] = 0;
+                p.sync[4 + (pass + 1) % 3] = 0;
+            }
+            grid_barrier(p.sync, target, gridDim.x);
+            ++pass;
+        }
+    }
+}
+
+__global__ void bc_scale_kernel(double *bc, long long n, double scale)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) bc[i] = __dmul_rn(bc[i], scale);
+}
+
+// Work list of one direction, built on the host from the row extents (setup only: N integers each way).
+struct HostList {
+    std::vector<int4> items;
+    std::vector<int> hub_chunks, hub_first;
+    int partial_slots = 0;
+};
+
+// keep_empty: rows without neighbours still get an item (backward sweep: their coeff = 1 / sigma must be
+// written for their predecessors to read; forward, a row without in-edges is never settled and is skipped).
+void build_list(const std::vector<int> &first, const std::vector<int> &count, bool keep_empty, HostList &out)
+{
+    const size_t n = count.size();
+    out.items.reserve(n + n / 8);
+    for (size_t r = 0; r < n; ++r) {
+        const int d = count[r];
+        if (d == 0 && !keep_empty) continue;
+        if (d <= BC_CHUNK) {
+            out.items.push_back(make_int4((int)r, first[r], d, -1));
+            continue;
+        }
+        const int chunks = (d + BC_CHUNK - 1) / BC_CHUNK;
+        const int hub = (int)out.hub_chunks.size();
+        out.hub_chunks.push_back(chunks);
+        out.hub_first.push_back(out.partial_slots);
+        out.partial_slots += chunks;
+        for (int c = 0; c < chunks; ++c) {
+            const int cnt = (c + 1 < chunks) ? BC_CHUNK : d - c * BC_CHUNK;
+            out.items.push_back(make_int4((int)r, first[r] + c * BC_CHUNK, cnt | (c << 8), hub));
+        }
+    }
+}
+
+struct DevList {
+    int4 *items = nullptr;
+    int *hub_chunks = nullptr, *hub_first = nullptr;
+    ~DevList()
+    {
+        cudaFree(items);
+        cudaFree(hub_chunks);
+        cudaFree(hub_first);
+    }
+};
+
+int upload_list(const HostList &h, DevList &d, BcList &out, const int *col, cudaStream_t stream)
+{
+    const size_t ni = h.items.size() ? h.items.size() : 1, nh = h.hub_chunks.size() ? h.hub_chunks.size() : 1;
+    GP_CUDA_CHECK(cudaMalloc((void **)&d.items, ni * sizeof(int4)));
+    GP_CUDA_CHECK(cudaMalloc((void **)&d.hub_chunks, nh * sizeof(int)));
+    GP_CUDA_CHECK(cudaMalloc((void **)&d.hub_first, nh * sizeof(int)));
+    if (!h.items.empty())
+        GP_CUDA_CHECK(cudaMemcpyAsync(d.items, h.items.data(), h.items.size() * sizeof(int4), cudaMemcpyHostToDevice, stream));
+    if (!h.hub_chunks.empty()) {
+        GP_CUDA_CHECK(cudaMemcpyAsync(d.hub_chunks, h.hub_chunks.data(), h.hub_chunks.size() * sizeof(int),
+                                      cudaMemcpyHostToDevice, stream));
+        GP_CUDA_CHECK(cudaMemcpyAsync(d.hub_first, h.hub_first.data(), h.hub_first.size() * sizeof(int),
+                                      cudaMemcpyHostToDevice, stream));
+    }
+    out.items = d.items;
+    out.num_items = (int)h.items.size();
+    out.col = col;
+    out.hub_chunks = d.hub_chunks;
+    out.hub_first = d.hub_first;
+    return GP_OK;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+};
+
+template <typename DT>
+int run_batches(const BcParams &base, long long batches, int group, u32 *h_overflow, cudaStream_t stream)
+{
+    int occ = 0;
+    GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bc_kernel<DT>, BC_THREADS, 0));
+    GP_REQUIRE(occ >= 1, GP_ERR_CUDA, "betweenness kernel does not fit on an SM");
+    if (occ > BC_MINB) occ = BC_MINB;
+    const int blocks = occ * gp_sm_count();
+    *h_overflow = 0;
+    for (long long b0 = 0; b0 < batches && !*h_overflow; b0 += group) {
+        BcParams p = base;
+        p.batch0 = b0;
+        p.batch1 = b0 + group < batches ? b0 + group : batches;
+        GP_CUDA_CHECK(cudaMemsetAsync(p.sync, 0, 8 * sizeof(u32), stream));
+        void *args[] = {&p};
+        gp_count_launch();
+        GP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)bc_kernel<DT>, dim3(blocks), dim3(BC_THREADS), args, 0,
+                                                  stream));
+        GP_CUDA_CHECK(cudaMemcpyAsync(h_overflow, p.sync + 7, sizeof(u32), cudaMemcpyDeviceToHost, stream));
+        GP_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    return GP_OK;
+}
+
+}  // namespace
+
+extern "C" int gp_betweenness(const gp_csr_t *csr_, double *d_score, gp_stream_t stream_)
+{
+    gp_csr *csr = const_cast<gp_csr *>(csr_);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GP_REQUIRE(csr != nullptr && d_score != nullptr, GP_ERR_INVALID, "gp_betweenness: NULL argument");
+    GP_REQUIRE(csr->built, GP_ERR_INVALID, "gp_betweenness: the CSR has not been built");
+    const long long n = csr->num_nodes;
+    if (n == 0) return GP_OK;
+    GP_CUDA_CHECK(cudaMemsetAsync(d_score, 0, (size_t)n * sizeof(double), stream));
+    if (n <= 2) {  // no node can lie strictly inside a path (and networkx skips the rescale)
+        GP_CUDA_CHECK(cudaStreamSynchronize(stream));
+        return GP_OK;
+    }
+    GP_TRY(gp_csr_ensure_in(csr, stream));
+
+    // ---- work lists (host, from the row extents)
+    std::vector<int> first_in((size_t)n + 1), cnt_in((size_t)n), first_out((size_t)n), cnt_out((size_t)n);
+    GP_CUDA_CHECK(cudaMemcpyAsync(first_in.data(), csr->rowptr_in, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    GP_CUDA_CHECK(cudaMemcpyAsync(first_out.data(), csr->row_start, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    GP_CUDA_CHECK(cudaMemcpyAsync(cnt_out.data(), csr->deg, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    GP_CUDA_CHECK(cudaStreamSynchronize(stream));
+    for (long long r = 0; r < n; ++r) cnt_in[(size_t)r] = first_in[(size_t)r + 1] - first_in[(size_t)r];
+    first_in.resize((size_t)n);
+    HostList hf, hb;
+    build_list(first_in, cnt_in, false, hf);
+    build_list(first_out, cnt_out, true, hb);
+
+    DevList df, db;
+    BcParams p;
+    memset(&p, 0, sizeof(p));
+    GP_TRY(upload_list(hf, df, p.fwd, csr->col_in, stream));
+    GP_TRY(upload_list(hb, db, p.bwd, csr->col, stream));
+    p.n = n;
+    p.bc = d_score;
+
+    DevBuf dist, sigma, coeff, partial, arrive, sync;
+    const size_t cells = (size_t)n * BC_LANES;
+    const size_t slots = (size_t)(hf.partial_slots > hb.partial_slots ? hf.partial_slots : hb.partial_slots);
+    const size_t hubs = hf.hub_chunks.size() > hb.hub_chunks.size() ? hf.hub_chunks.size() : hb.hub_chunks.size();
+    GP_CUDA_CHECK(cudaMalloc(&dist.p, cells * sizeof(uint16_t)));
+    GP_CUDA_CHECK(cudaMalloc(&sigma.p, cells * sizeof(double)));
+    GP_CUDA_CHECK(cudaMalloc(&coeff.p, cells * sizeof(double)));
+    GP_CUDA_CHECK(cudaMalloc(&partial.p, (slots ? slots : 1) * BC_LANES * sizeof(double)));
+    GP_CUDA_CHECK(cudaMalloc(&arrive.p, (hubs ? hubs : 1) * sizeof(u32)));
+    GP_CUDA_CHECK(cudaMalloc(&sync.p, 8 * sizeof(u32)));
+    GP_CUDA_CHECK(cudaMemsetAsync(arrive.p, 0, (hubs ? hubs : 1) * sizeof(u32), stream));
+    p.dist = dist.p;
+    p.sigma = (double *)sigma.p;
+    p.coeff = (double *)coeff.p;
+    p.partial = (double *)partial.p;
+    p.arrive = (u32 *)arrive.p;
+    p.sync = (u32 *)sync.p;
+
+    const long long batches = (n + BC_LANES - 1) / BC_LANES;
+    int group = 128;  // batches per cooperative launch: bounds the run time of one launch
+    if (const char *e = getenv("GP_BC_GROUP")) group = atoi(e) > 0 ? atoi(e) : group;
+    u32 overflow = 0;
+    // 8-bit hop counts first (one 32-byte sector per neighbour); a graph deeper than 253 hops restarts with 16 bits
+    GP_TRY(run_batches<uint8_t>(p, batches, group, &overflow, stream));
+    if (overflow) {
+        GP_CUDA_CHECK(cudaMemsetAsync(d_score, 0, (size_t)n * sizeof(double), stream));
+        GP_CUDA_CHECK(cudaMemsetAsync(arrive.p, 0, (hubs ? hubs : 1) * sizeof(u32), stream));
+        GP_TRY(run_batches<uint16_t>(p, batches, group, &overflow, stream));
+        GP_REQUIRE(!overflow, GP_ERR_LEVEL_OVERFLOW, "gp_betweenness: a hop distance >= 65534");
+    }
+    // _rescale(normalized=True, directed=True, endpoints=False): scale = 1 / ((N-1) * (N-2)), Python float ops
+    const double scale = 1.0 / ((double)(n - 1) * (double)(n - 2));
+    if (scale != 1.0) {
+        GP_LAUNCH(bc_scale_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, d_score, n, scale);
+        GP_CUDA_CHECK(cudaGetLastError());
+    }
+    GP_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return GP_OK;
+}

@@ -99,6 +99,13 @@ class DeviceCsr:
         check(self._lib.gp_clustering(self._h, _ptr(x), _stream()))
         return x
 
+    def betweenness(self) -> torch.Tensor:
+        """networkx ``betweenness_centrality`` defaults (utils.py:32-36): float64[N]; path counts exact, scores
+        within a few ulp of networkx (its summation order follows the BFS queue; ours is fixed by node id)."""
+        x = torch.empty(self.num_nodes, dtype=torch.float64, device="cuda")
+        check(self._lib.gp_betweenness(self._h, _ptr(x), _stream()))
+        return x
+
     def close(self):
         if self._h:
             self._lib.gp_csr_free(self._h)

@@ -14,6 +14,7 @@ agnostic so the world_size-2 ``gloo`` tests can drive it with CPU tensors.
 """
 from __future__ import annotations
 
+import os
 from ctypes import c_void_p
 
 import torch
@@ -186,6 +187,7 @@ class PeerAssembly:
             self.base.append(ptr.value)
             self._opened.append(ptr.value)
         self.step = 0
+        self._side = None
         self.flag = torch.zeros(1, dtype=torch.int32, device="cuda")
 
     def close(self):
@@ -215,6 +217,18 @@ class PeerAssembly:
             self._shard_key, self._shard = key, anchors[lo:hi].contiguous()
         edge_index = edge_index.contiguous()
         eng.csr._edges, eng.bfs._anchors, eng.bfs.num_anchors = edge_index, self._shard, hi - lo
+        # concat_into_features' copy of x (utils.py:133-134) does not depend on the traversal: one strided
+        # device-to-device transfer on a side stream while this rank builds, traverses and packs
+        side = None
+        if x is not None and f > 0 and n > 0 and os.environ.get("GP_XCOPY_OVERLAP", "1") != "0":
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            side = self._side
+            side.wait_stream(torch.cuda.current_stream())
+            check(self.lib.gp_concat_x(_ptr(x), n, f, x.stride(0) if n > 1 else f, _ptr(out),
+                                       out.stride(0) if n > 1 else f + k, c_void_p(side.cuda_stream)))
+            x.record_stream(side)
+            out.record_stream(side)
         check(self.lib.gp_geodesic_run_packed(eng.csr._h, eng.bfs._h, _ptr(edge_index), edge_index.size(1),
                                               _ptr(self._shard), hi - lo, slot, _stream()))
         packed, stride = ctypes.c_void_p(), ctypes.c_int64()
@@ -229,6 +243,9 @@ class PeerAssembly:
         for r in range(self.world):
             base = packed.value - slot * self.slot_stride_words * 8 if r == self.rank else self.base[r]
             ptrs[r] = base + slot * self.slot_stride_words * 8
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+            x = None  # already in place
         check(self.lib.gp_decode_peers(ptrs, self.world, n, hi - lo, batches.value, wb.value, stride.value, _ptr(x), f,
                                        x.stride(0) if x is not None and n > 1 else f, _ptr(out),
                                        out.stride(0) if n > 1 else f + k, f, _stream()))

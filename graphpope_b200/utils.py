@@ -21,13 +21,14 @@ the CPU process pool it sized (utils.py:98) is replaced by one multi-source BFS 
 What runs where
   * geodesic distances, 1/(d+1) normalisation, concat: device (libgraphpope_b200.so).
   * ``stochastic`` anchors: host numpy global RNG, exactly utils.py:22-24 (same seed, same anchors).
-  * ``degree_centrality`` / ``pagerank`` / ``closeness_centrality`` / ``clustering_coefficient`` anchors: device
-    (degree array, float64 SpMV power iteration, MS-BFS from every node + bit-sliced column sums, directed
-    triangle counting; stable top-k).
+  * ``degree_centrality`` / ``pagerank`` / ``closeness_centrality`` / ``clustering_coefficient`` /
+    ``betweenness_centrality`` anchors: device (degree array, float64 SpMV power iteration, MS-BFS from every
+    node + bit-sliced column sums, directed triangle counting, Brandes with 32 sources per warp-wide batch;
+    stable top-k).
   * KMeans centres of the node2vec branch: device (k-means++ + Lloyd, tensor-core assignment; statistical
     parity with scikit-learn, which the reference runs unseeded).
-  * betweenness / eigenvector anchors: the reference's own networkx calls on the host (stated
-    scope of the port).
+  * eigenvector anchors: the reference's own networkx call on the host (stated scope of the port,
+    SURVEY.md §8 a3x / §8f).
 There is no CPU fallback for the device parts: without the CUDA library or a GPU these functions raise.
 """
 from __future__ import annotations
@@ -156,6 +157,12 @@ def sample_anchor_nodes(data, num_anchor_nodes, sampling_method):
         # keep the networkx call below
         csr = _device_csr(data)
         return _dev.topk_stable(csr.clustering(), num_anchor_nodes).cpu().tolist()
+
+    if sampling_method == 'betweenness_centrality' and os.environ.get("GRAPHPOPE_BETWEENNESS", "cuda") != "networkx":
+        # Brandes, 32 sources per warp-wide batch, level-synchronous pull sweeps (gp_betweenness.cu); scores
+        # within a few ulp of networkx (GRAPHPOPE_BETWEENNESS=networkx keeps the reference's call below)
+        csr = _device_csr(data)
+        return _dev.topk_stable(csr.betweenness(), num_anchor_nodes).cpu().tolist()
 
     if sampling_method in _HOST_CENTRALITIES:
         # Not re-implemented (north_star): the reference's own networkx call, same top-k rule.

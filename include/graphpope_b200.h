@@ -141,6 +141,13 @@ int gp_geodesic_run(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_edge_index,
                     const int64_t *d_anchors, int64_t num_anchors, const float *d_x, int64_t num_features,
                     int64_t ld_x, float *d_out, int64_t ld_out, int64_t col_offset, gp_stream_t stream);
 
+/* async.  The x half of concat_into_features (utils.py:133-134) alone: d_out[:, 0:F] = d_x as ONE strided
+ * device-to-device transfer, so it can run on a side stream beside the (latency-bound) csr build and
+ * MS-BFS; gp_geodesic_run does exactly that internally (GP_XCOPY_OVERLAP=0 moves the copy back into the
+ * epilogue kernel).  Follow with gp_msbfs_features / gp_decode_peers called with d_x == NULL.        */
+int gp_concat_x(const float *d_x, int64_t num_nodes, int64_t num_features, int64_t ld_x, float *d_out,
+                int64_t ld_out, gp_stream_t stream);
+
 /* Bit-sliced result planes of the last run, for the multi-GPU gather
  * (anchor-sharded ranks exchange these instead of uint16/fp32 columns):
  * plane 0 = "reached" mask, planes 1..num_planes-1 = distance bits 0.. ;
@@ -244,6 +251,12 @@ int gp_closeness(const gp_csr_t *csr, double *d_score, gp_stream_t stream);
  * integer triangle and degree counts from shared-memory node bitmaps, one float64 division (bit-equal).
  * syncs.  d_score float64[N].  GP_ERR_UNSUPPORTED when two N-bit maps do not fit in shared memory.   */
 int gp_clustering(const gp_csr_t *csr, double *d_score, gp_stream_t stream);
+/* betweenness_centrality (utils.py:32-36 -> nx.betweenness_centrality defaults: Brandes, normalized, no
+ * endpoints, on the DiGraph): 32 sources per batch, one warp lane per source, level-synchronous pull sweeps in
+ * one persistent kernel (gp_betweenness.cu).  Path counts are exact; the float64 dependency sums have a fixed
+ * order that differs from networkx's queue order, so scores agree to a few ulp, not bit for bit.  syncs.
+ * d_score float64[N].                                                                                  */
+int gp_betweenness(const gp_csr_t *csr, double *d_score, gp_stream_t stream);
 /* Stable top-k of utils.py:29-30 / 41-42: ascending stable sort by score, keep
  * the last k (ties keep ascending node id; output in ascending-score order).
  * async.  d_out int64[min(k, N)] (k == 0 returns all N: list[-0:] quirk).       */

@@ -3,9 +3,9 @@
 TEST INFRASTRUCTURE — see oracle/__init__.py.
 
 Only the samplers the device path re-implements are restated here
-(stochastic, degree_centrality, pagerank, closeness_centrality, clustering_coefficient).
-The other two centralities stay on the reference's own networkx calls in the product
-(north_star).
+(stochastic, degree_centrality, pagerank, closeness_centrality, clustering_coefficient,
+betweenness_centrality).  eigenvector_centrality stays on the reference's own networkx
+call in the product (north_star).
 
 Third-party arithmetic restated: networkx (unpinned by the reference's
 requirements.txt; 3.6.1 installed) ``degree_centrality`` and
@@ -165,3 +165,133 @@ def clustering_scores(edge_index, num_nodes: int) -> np.ndarray:
 
 def clustering_coefficient_anchors(edge_index, num_nodes: int, k: int) -> list:
     return stable_top_k(clustering_scores(edge_index, num_nodes), k)
+
+
+def betweenness_scores(edge_index, num_nodes: int) -> np.ndarray:
+    """networkx ``betweenness_centrality(G)`` defaults restated (utils.py:32-36 call site): Brandes'
+    algorithm per source exactly as ``_single_source_shortest_path_basic`` / ``_accumulate_basic`` /
+    ``_rescale(normalized=True, directed=True, endpoints=False)`` do it, adjacency in ``to_networkx``
+    insertion order (first appearance of each edge in ``edge_index``), so the float64 sums run in the
+    same order and the scores are bit-equal to networkx's.  Pure-Python loops: small graphs only.
+    """
+    from collections import deque
+
+    n = int(num_nodes)
+    ei = np.asarray(edge_index, dtype=np.int64).reshape(2, -1)
+    adj = [dict() for _ in range(n)]  # insertion-ordered successor sets, as the DiGraph keeps them
+    for u, v in zip(ei[0].tolist(), ei[1].tolist()):
+        adj[u][v] = None
+    adj = [list(a) for a in adj]
+    bc = [0.0] * n
+    for s in range(n):
+        S = []
+        P = [[] for _ in range(n)]
+        sigma = [0.0] * n
+        D = {}
+        sigma[s] = 1.0
+        D[s] = 0
+        Q = deque([s])
+        while Q:
+            v = Q.popleft()
+            S.append(v)
+            Dv = D[v]
+            sigmav = sigma[v]
+            for w in adj[v]:
+                if w not in D:
+                    Q.append(w)
+                    D[w] = Dv + 1
+                if D[w] == Dv + 1:
+                    sigma[w] += sigmav
+                    P[w].append(v)
+        delta = dict.fromkeys(S, 0)
+        while S:
+            w = S.pop()
+            coeff = (1 + delta[w]) / sigma[w]
+            for v in P[w]:
+                delta[v] += sigma[v] * coeff
+            if w != s:
+                bc[w] += delta[w]
+    N = n - 1
+    if N >= 2:
+        scale = 1 / (N * (N - 1))
+        if scale != 1:
+            bc = [b * scale for b in bc]
+    return np.asarray(bc, dtype=np.float64)
+
+
+def betweenness_levelsync_scores(edge_index, num_nodes: int) -> np.ndarray:
+    """The SAME quantity in the order the device kernel (gp_betweenness.cu) sums it: level-synchronous
+    pull sweeps, neighbours in ascending id, ``coeff = (1 + delta) / sigma`` stored per finalised node,
+    32 sources per batch whose deltas meet in a butterfly sum.  Used by the CPU tests to show that this
+    re-ordering stays within a few ulp of the networkx order (the device itself is checked on the GPU).
+    """
+    n = int(num_nodes)
+    s_, d_ = dedup_edges(edge_index, n)
+    succ = [[] for _ in range(n)]
+    pred = [[] for _ in range(n)]
+    for u, v in sorted(zip(s_.tolist(), d_.tolist())):
+        succ[u].append(v)
+    for u, v in sorted(zip(s_.tolist(), d_.tolist()), key=lambda e: (e[1], e[0])):
+        pred[v].append(u)
+    bc = np.zeros(n, dtype=np.float64)
+    for b0 in range(0, n, 32):
+        lanes = list(range(b0, min(n, b0 + 32)))
+        per_level = {}  # (level, row) -> [32 lane deltas]
+        maxl_all = 0
+        state = []
+        for s in lanes:
+            dist = [-1] * n
+            sigma = [0.0] * n
+            dist[s] = 0
+            sigma[s] = 1.0
+            lvl = 0
+            while True:
+                new = []
+                for w in range(n):
+                    if dist[w] != -1:
+                        continue
+                    acc = 0.0
+                    for v in pred[w]:
+                        if dist[v] == lvl:
+                            acc = acc + sigma[v]
+                    if acc != 0.0:
+                        new.append((w, acc))
+                for w, acc in new:
+                    dist[w] = lvl + 1
+                    sigma[w] = acc
+                if not new:
+                    break
+                lvl += 1
+            state.append((dist, sigma))
+            maxl_all = max(maxl_all, lvl)
+        coeffs = [[0.0] * n for _ in lanes]
+        for l in range(maxl_all - 1, 0, -1):
+            for v in range(n):
+                vals = [0.0] * 32
+                hit = False
+                for li, (dist, sigma) in enumerate(state):
+                    if dist[v] != l:
+                        continue
+                    hit = True
+                    acc = 0.0
+                    for w in succ[v]:
+                        if dist[w] == l + 1:
+                            cw = 1.0 / sigma[w] if l + 1 == maxl_all else coeffs[li][w]
+                            acc = acc + sigma[v] * cw
+                    coeffs[li][v] = (1.0 + acc) / sigma[v]
+                    vals[li] = acc
+                if hit:
+                    m = 16
+                    while m >= 1:  # butterfly: every lane ends with the same total
+                        vals = [vals[i] + vals[i ^ m] for i in range(32)]
+                        m >>= 1
+                    bc[v] = bc[v] + vals[0]
+    if n - 1 >= 2:
+        scale = 1.0 / (float(n - 1) * float(n - 2))
+        if scale != 1.0:
+            bc = bc * scale
+    return bc
+
+
+def betweenness_centrality_anchors(edge_index, num_nodes: int, k: int) -> list:
+    return stable_top_k(betweenness_scores(edge_index, num_nodes), k)

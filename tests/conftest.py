@@ -26,5 +26,10 @@ def golden_pubmed():
     return np.load(os.path.join(GOLDEN_DIR, "reference_pubmed_shape.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_betweenness():
+    return np.load(os.path.join(GOLDEN_DIR, "reference_betweenness.npz"))
+
+
 def micro_names(golden):
     return sorted({k.split("/")[1] for k in golden.files if k.startswith("micro/")})

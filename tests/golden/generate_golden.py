@@ -4,6 +4,7 @@ Run in the build container only (needs /root/reference):
 
     python tests/golden/generate_golden.py            # small fixtures, seconds
     python tests/golden/generate_golden.py --pubmed   # + full C1 config (~2 min, 6 workers)
+    python tests/golden/generate_golden.py --betweenness   # ONLY reference_betweenness.npz (seconds)
 
 The reference has no tests or golden vectors of its own, so these
 files ARE the parity pins: every value below is produced by
@@ -53,11 +54,34 @@ def ref_rows(utils, n, edges, anchors):
     return np.asarray([rows[i] for i in range(n)], dtype=np.float64)
 
 
+def betweenness_fixture(utils):
+    """reference_betweenness.npz: utils.sample_anchor_nodes(..., 'betweenness_centrality') (utils.py:32-36) and
+    the nx.betweenness_centrality scores it ranks, on a 600-node graph with a symmetric heavy-tailed part and
+    an asymmetric part (so in- and out-neighbourhoods differ)."""
+    import networkx as nx
+
+    n = 600
+    ei = synth.chung_lu_symmetric(n, 3600, 2.2, seed=41)
+    ei = np.concatenate([ei, synth.random_digraph(n, 150, seed=42)], axis=1)
+    data = RefData(torch.tensor(ei), n)
+    out = {"n": np.int64(n), "edge_index": ei}
+    for k in (1, 16, 64, 256):
+        out[f"anchors/{k}"] = np.asarray(utils.sample_anchor_nodes(data, k, "betweenness_centrality"), dtype=np.int64)
+    bc = nx.betweenness_centrality(utils.to_networkx(data))
+    out["scores"] = np.asarray([bc[i] for i in range(n)], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "reference_betweenness.npz"), **out)
+    print("wrote reference_betweenness.npz; non-zero scores:", int((out["scores"] > 0).sum()))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pubmed", action="store_true")
+    ap.add_argument("--betweenness", action="store_true")
     args = ap.parse_args()
     utils = load_reference_utils()
+    if args.betweenness:
+        betweenness_fixture(utils)
+        return
     out = {}
 
     # 1. micro graphs through utils.shortest_path_length (utils.py:64-81)

@@ -134,3 +134,66 @@ def test_clustering_matches_oracle_on_a_dense_directed_multigraph(dev):
     ei = np.concatenate([ei, hub, hub[::-1][:, :150]], axis=1)
     csr = dev.DeviceCsr(n, ei.shape[1]).build(torch.as_tensor(ei).cuda())
     assert np.array_equal(csr.clustering().cpu().numpy(), s.clustering_scores(ei, n))
+
+
+def _assert_same_ranking(got, want, k, rtol=1e-10):
+    """Top-k lists agree wherever the reference's own scores separate the candidates by more than rtol."""
+    from oracle import samplers as s
+    a, b = s.stable_top_k(got, k), s.stable_top_k(want, k)
+    if a == b:
+        return
+    cut = want[b[0]]  # smallest selected reference score
+    for u, v in zip(a, b):
+        if u != v:
+            assert abs(want[u] - want[v]) <= rtol * max(abs(want[u]), abs(want[v]), 1e-300) or \
+                abs(want[u] - cut) <= rtol * abs(cut), (u, v, want[u], want[v])
+
+
+def test_betweenness_scores_and_anchor_lists(dev, golden_betweenness):
+    """nx.betweenness_centrality (utils.py:32-36): Brandes with 32 sources per warp-wide batch."""
+    from graphpope_b200 import utils
+    g = golden_betweenness
+    ei, n = g["edge_index"], int(g["n"])
+    csr = dev.DeviceCsr(n, ei.shape[1]).build(torch.as_tensor(ei).cuda())
+    got = csr.betweenness().cpu().numpy()
+    want = g["scores"]
+    assert np.array_equal(got == 0, want == 0)
+    assert np.allclose(got, want, rtol=1e-10, atol=0)  # tolerance of this sampler: summation order differs
+    again = csr.betweenness().cpu().numpy()
+    assert np.array_equal(got, again)  # fixed summation order: run-to-run bit-equal
+    for k in (1, 16, 64, 256):
+        _assert_same_ranking(got, want, k)
+    assert utils.sample_anchor_nodes(Data(ei, n), 16, "betweenness_centrality") == g["anchors/16"].tolist()
+
+
+@pytest.mark.parametrize("case", ["directed-sparse", "path", "hub", "tiny"])
+def test_betweenness_matches_oracle_on_hard_graphs(dev, case):
+    """Unreachable pairs and dangling nodes; a 300-node path (hop counts beyond 253: the 16-bit restart);
+    a star-of-stars whose centre row is cut into 64-edge chunks; graphs of 1..3 nodes (no rescale)."""
+    from oracle import samplers as s
+    if case == "directed-sparse":
+        n = 700
+        ei = synth.random_digraph(n, 1500, seed=31)
+    elif case == "path":
+        n = 300
+        a = np.arange(n - 1)
+        ei = np.stack([np.concatenate([a, a + 1]), np.concatenate([a + 1, a])]).astype(np.int64)
+    elif case == "hub":
+        n = 500
+        spokes = np.arange(1, 300)
+        leaves = np.arange(300, 500)
+        src = np.concatenate([np.zeros_like(spokes), spokes, spokes[:200], leaves])
+        dst = np.concatenate([spokes, np.zeros_like(spokes), leaves, spokes[:200]])
+        extra = synth.random_digraph(n, 300, seed=7)
+        ei = np.concatenate([np.stack([src, dst]).astype(np.int64), extra], axis=1)
+    else:
+        for n, edges in ((1, [(0, 0)]), (2, [(0, 1), (1, 0)]), (3, [(0, 1), (1, 2)])):
+            ei = np.asarray(edges, dtype=np.int64).T.copy()
+            csr = dev.DeviceCsr(n, ei.shape[1]).build(torch.as_tensor(ei).cuda())
+            assert np.array_equal(csr.betweenness().cpu().numpy(), s.betweenness_scores(ei, n))
+        return
+    csr = dev.DeviceCsr(n, ei.shape[1]).build(torch.as_tensor(ei).cuda())
+    got = csr.betweenness().cpu().numpy()
+    want = s.betweenness_scores(ei, n)
+    assert np.array_equal(got == 0, want == 0)
+    assert np.allclose(got, want, rtol=1e-10, atol=0)
