@@ -7,10 +7,10 @@
 //   backward  in reverse BFS order: coeff = (1 + delta[w]) / sigma[w]; delta[v] += sigma[v] * coeff for every
 //             predecessor v of w;  betweenness[w] += delta[w]  (w != s)
 //   rescale   betweenness[v] *= 1 / ((N-1)(N-2))   (N > 2)
-// = N BFS runs; the reference does them in Python (hours at Flickr size).  Here: 32 sources per batch, ONE LANE
-// PER SOURCE.  Per-batch state is node-major — dist[N][32] (hop count per source, u8 or u16), sigma[N][32] and
-// coeff[N][32] float64 — so the 32 lanes of a warp read one 32-byte sector of hop counts and one 256-byte row
-// of path counts per neighbour, fully coalesced.  Both sweeps are level-synchronous and *pull* (owner
+// = N BFS runs; the reference does them in Python (hours at Flickr size).  Here: 32*S sources per batch, S = 1, 2
+// or 4 sources PER LANE.  Per-batch state is node-major — dist[N][32*S] (hop count per source, u8 or u16),
+// sigma[N][32*S] and coeff[N][32*S] float64 — so a warp reads the hop counts of one neighbour for all sources of
+// the batch with one coalesced request (one word per lane) and its path counts as one contiguous row.  Both sweeps are level-synchronous and *pull* (owner
 // computes): forward, an unsettled row sums sigma over its in-neighbours settled one level earlier; backward,
 // a row at level l sums sigma[v] * coeff[w] over its out-neighbours w at level l+1, where
 // coeff[w] = (1 + delta[w]) / sigma[w] was stored when w was finalised.  No atomics touch floating-point
@@ -27,11 +27,10 @@
 
 namespace {
 
-constexpr int BC_LANES = 32;    // sources per batch = lanes of a warp
 constexpr int BC_CHUNK = 64;    // edges per work item
-constexpr int BC_TILE = 4;      // items per ticket
-constexpr int BC_THREADS = 512;
-constexpr int BC_MINB = 2;
+constexpr int BC_TILE = 4;      // items per ticket; their descriptors, row states and columns are fetched together
+constexpr int BC_THREADS = 256;
+constexpr int BC_MINB = 3;
 constexpr int BC_UNROLL = 8;    // neighbour hop-count loads in flight per lane
 
 struct BcList {
@@ -45,10 +44,10 @@ struct BcList {
 struct BcParams {
     BcList fwd, bwd;         // in-edge items (forward sweep), out-edge items (backward sweep)
     long long n;
-    void *dist;              // [n][32] hop count from the lane's source (all ones = not reached)
-    double *sigma;           // [n][32] shortest-path counts
-    double *coeff;           // [n][32] (1 + delta) / sigma of finalised rows
-    double *partial;         // [chunks of chunked rows][32]
+    void *dist;              // [n][32 * S] hop count from each source of the batch (all ones = not reached)
+    double *sigma;           // [n][32 * S] shortest-path counts
+    double *coeff;           // [n][32 * S] (1 + delta) / sigma of finalised rows
+    double *partial;         // [chunks of chunked rows][32 * S]
     u32 *arrive;             // [hubs] arrival counters (left at zero by the finaliser)
     double *bc;              // [n] running sum of delta over the sources done so far
     u32 *sync;               // [0] barrier, [1..3] ticket counters, [4..6] "something settled" flags, [7] overflow
@@ -62,21 +61,39 @@ __device__ __forceinline__ double warp_sum_f64(double v)
     return v;
 }
 
-template <typename DT>
-__device__ __forceinline__ DT ld_dist(const DT *p)
+// A lane's S hop counts of one row as one aligned load / store (L2-coherent load: other SMs write these words).
+template <int BYTES>
+__device__ __forceinline__ u64 ld_state(const void *p)
 {
-    return __ldcg(p);
+    if (BYTES == 1) return __ldcg(reinterpret_cast<const unsigned char *>(p));
+    if (BYTES == 2) return __ldcg(reinterpret_cast<const unsigned short *>(p));
+    if (BYTES == 4) return __ldcg(reinterpret_cast<const unsigned int *>(p));
+    return __ldcg(reinterpret_cast<const unsigned long long *>(p));
+}
+
+template <int BYTES>
+__device__ __forceinline__ void st_state(void *p, u64 v)
+{
+    if (BYTES == 1) *reinterpret_cast<unsigned char *>(p) = (unsigned char)v;
+    else if (BYTES == 2) *reinterpret_cast<unsigned short *>(p) = (unsigned short)v;
+    else if (BYTES == 4) *reinterpret_cast<unsigned int *>(p) = (unsigned int)v;
+    else *reinterpret_cast<unsigned long long *>(p) = v;
 }
 
 // One sweep over a work list.  FWD: settle level `lvl + 1` from level `lvl`.  !FWD: finalise level `lvl`
 // from level `lvl + 1` (`maxl` = deepest level of the batch, whose rows have delta = 0).
-template <typename DT, bool FWD>
+// A lane owns S sources: its S hop counts of a row are one word, its S sigma / coeff values one 8*S-byte run.
+template <typename DT, int S, bool FWD>
 __device__ __forceinline__ void bc_sweep(const BcParams &p, const BcList &L, int lvl, int maxl, u32 *ticket, u32 *flag)
 {
     constexpr DT INF = (DT)~(DT)0;
+    constexpr int BYTES = S * (int)sizeof(DT);
+    constexpr int BITS = 8 * (int)sizeof(DT);
+    constexpr int W = 32 * S;  // sources per batch
     const int lane = threadIdx.x & 31;
-    DT *dist = reinterpret_cast<DT *>(p.dist);
+    char *dist = reinterpret_cast<char *>(p.dist);
     const DT want = (DT)(FWD ? lvl : lvl + 1);   // hop count a contributing neighbour must have
+    const DT own = (DT)(FWD ? INF : (DT)lvl);     // hop count of the (row, source) pairs this sweep finalises
     const bool leaf = !FWD && (lvl + 1 == maxl);  // neighbours at the deepest level: coeff = 1 / sigma
     bool found_any = false;
     const int tiles = (L.num_items + BC_TILE - 1) / BC_TILE;
@@ -86,79 +103,129 @@ __device__ __forceinline__ void bc_sweep(const BcParams &p, const BcList &L, int
         const u32 t = __shfl_sync(FULL_MASK, next, 0);
         if (t >= (u32)tiles) break;
         if (lane == 0) next = atomicAdd(ticket, 1u);  // fetched while this tile is processed
-        const int i1 = min((int)(t + 1) * BC_TILE, L.num_items);
-        for (int i = (int)t * BC_TILE; i < i1; ++i) {
-            const int4 it = __ldg(L.items + i);
-            const int row = it.x, beg = it.y, cnt = it.z & 0xFF, chunk = it.z >> 8, hub = it.w;
-            const size_t rbase = (size_t)row * BC_LANES + lane;
-            const DT dr = ld_dist(dist + rbase);
-            const bool mine = FWD ? (dr == INF) : (dr == (DT)lvl);
-            if (!__any_sync(FULL_MASK, mine)) continue;
-            double sv = 0.0;
-            if (!FWD && mine) sv = __ldcg(p.sigma + rbase);
-            double acc = 0.0;
+        const int i0 = (int)t * BC_TILE;
+        // round trip 1: the tile's descriptors (lane k holds item k); round trip 2: every item's row state and
+        // first 32 columns, issued together
+        int4 mine_it = make_int4(0, 0, 0, -1);
+        if (lane < BC_TILE && i0 + lane < L.num_items) mine_it = __ldg(L.items + i0 + lane);
+        u64 rowraw[BC_TILE];
+        int col0[BC_TILE];
+#pragma unroll
+        for (int k = 0; k < BC_TILE; ++k) {
+            const int row = __shfl_sync(FULL_MASK, mine_it.x, k), beg = __shfl_sync(FULL_MASK, mine_it.y, k);
+            const int cnt = __shfl_sync(FULL_MASK, mine_it.z, k) & 0xFF;
+            rowraw[k] = ld_state<BYTES>(dist + ((size_t)row * 32 + lane) * BYTES);
+            col0[k] = lane < cnt ? __ldg(L.col + beg + lane) : row;
+        }
+#pragma unroll
+        for (int k = 0; k < BC_TILE; ++k) {
+            if (i0 + k >= L.num_items) break;
+            const int row = __shfl_sync(FULL_MASK, mine_it.x, k), beg = __shfl_sync(FULL_MASK, mine_it.y, k);
+            const int z = __shfl_sync(FULL_MASK, mine_it.z, k), hub = __shfl_sync(FULL_MASK, mine_it.w, k);
+            const int cnt = z & 0xFF, chunk = z >> 8;
+            u32 mine = 0;  // bit s: source s of this lane is finalised by this sweep
+#pragma unroll
+            for (int s = 0; s < S; ++s) mine |= ((DT)(rowraw[k] >> (s * BITS)) == own ? 1u : 0u) << s;
+            if (!__any_sync(FULL_MASK, mine != 0)) continue;
+            const size_t rbase = ((size_t)row * 32 + lane) * S;
+            double sv[S], acc[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                acc[s] = 0.0;
+                sv[s] = (!FWD && ((mine >> s) & 1u)) ? __ldcg(p.sigma + rbase + s) : 0.0;
+            }
             for (int base = 0; base < cnt; base += 32) {
-                const int c = (base + lane < cnt) ? __ldg(L.col + beg + base + lane) : row;
+                int c = col0[k];
+                if (base > 0) c = (base + lane < cnt) ? __ldg(L.col + beg + base + lane) : row;
                 const int m = min(32, cnt - base);
                 for (int j0 = 0; j0 < m; j0 += BC_UNROLL) {
                     int v[BC_UNROLL];
-                    DT dv[BC_UNROLL];
+                    u64 dv[BC_UNROLL];
 #pragma unroll
                     for (int q = 0; q < BC_UNROLL; ++q) {
-                        // padding slots re-read the row itself, whose hop count never equals `want`
+                        // padding slots re-read the row itself, whose own hop counts never equal `want`
                         v[q] = __shfl_sync(FULL_MASK, c, (j0 + q) & 31);
                         if (j0 + q >= m) v[q] = row;
                     }
 #pragma unroll
-                    for (int q = 0; q < BC_UNROLL; ++q) dv[q] = ld_dist(dist + (size_t)v[q] * BC_LANES + lane);
+                    for (int q = 0; q < BC_UNROLL; ++q) dv[q] = ld_state<BYTES>(dist + ((size_t)v[q] * 32 + lane) * BYTES);
 #pragma unroll
                     for (int q = 0; q < BC_UNROLL; ++q) {
-                        if (mine && dv[q] == want) {
-                            const size_t vb = (size_t)v[q] * BC_LANES + lane;
-                            if (FWD) {
-                                acc = __dadd_rn(acc, __ldcg(p.sigma + vb));
-                            } else {
-                                const double cw = leaf ? __ddiv_rn(1.0, __ldcg(p.sigma + vb)) : __ldcg(p.coeff + vb);
-                                acc = __dadd_rn(acc, __dmul_rn(sv, cw));
+                        const size_t vb = ((size_t)v[q] * 32 + lane) * S;
+#pragma unroll
+                        for (int s = 0; s < S; ++s) {
+                            if (((mine >> s) & 1u) && (DT)(dv[q] >> (s * BITS)) == want) {
+                                if (FWD) {
+                                    acc[s] = __dadd_rn(acc[s], __ldcg(p.sigma + vb + s));
+                                } else {
+                                    const double cw = leaf ? __ddiv_rn(1.0, __ldcg(p.sigma + vb + s)) : __ldcg(p.coeff + vb + s);
+                                    acc[s] = __dadd_rn(acc[s], __dmul_rn(sv[s], cw));
+                                }
                             }
                         }
                     }
                 }
             }
             if (hub >= 0) {
-                // chunk of a long row: park the partial sum; the warp that arrives last adds them in chunk order
+                // chunk of a long row: park the partial sums; the warp that arrives last adds them in chunk order
                 const int chunks = __ldg(L.hub_chunks + hub), first = __ldg(L.hub_first + hub);
-                p.partial[((size_t)first + chunk) * BC_LANES + lane] = acc;
+                double *slot = p.partial + ((size_t)first + chunk) * W + (size_t)lane * S;
+#pragma unroll
+                for (int s = 0; s < S; ++s) slot[s] = acc[s];
                 __syncwarp();
                 u32 old = 0;
                 if (lane == 0) {
-                    __threadfence();  // the warp's 32 partial sums before the arrival
+                    __threadfence();  // the warp's partial sums before the arrival
                     old = atomicAdd(p.arrive + hub, 1u);
                 }
                 old = __shfl_sync(FULL_MASK, old, 0);
                 if (old != (u32)(chunks - 1)) continue;
                 __threadfence();
                 if (lane == 0) p.arrive[hub] = 0;
-                acc = 0.0;
-                for (int ch0 = 0; ch0 < chunks; ch0 += 8) {  // eight loads in flight, added in chunk order
-                    double part[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        part[q] = ch0 + q < chunks ? __ldcg(p.partial + ((size_t)first + ch0 + q) * BC_LANES + lane) : 0.0;
+                for (int s = 0; s < S; ++s) acc[s] = 0.0;
+                const double *part = p.partial + (size_t)first * W + (size_t)lane * S;
+                for (int ch0 = 0; ch0 < chunks; ch0 += 4) {  // 4 * S loads in flight, added in chunk order
+                    double pv[4][S];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        if (ch0 + q < chunks) acc = __dadd_rn(acc, part[q]);
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int s = 0; s < S; ++s)
+                            pv[q][s] = ch0 + q < chunks ? __ldcg(part + (size_t)(ch0 + q) * W + s) : 0.0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (ch0 + q < chunks) {
+#pragma unroll
+                            for (int s = 0; s < S; ++s) acc[s] = __dadd_rn(acc[s], pv[q][s]);
+                        }
                 }
             }
             if (FWD) {
-                if (mine && acc != 0.0) {  // sigma >= 1 for every settled node, so a non-zero sum = "has a parent"
-                    p.sigma[rbase] = acc;
-                    dist[rbase] = (DT)(lvl + 1);
+                u64 raw = rowraw[k];
+                bool changed = false;
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    // sigma >= 1 for every settled node, so a non-zero sum means "has a parent at level lvl"
+                    if (((mine >> s) & 1u) && acc[s] != 0.0) {
+                        p.sigma[rbase + s] = acc[s];
+                        raw = (raw & ~((u64)INF << (s * BITS))) | ((u64)(DT)(lvl + 1) << (s * BITS));
+                        changed = true;
+                    }
+                }
+                if (changed) {  // the lane owns the whole word: readers see the old or the new hop counts
+                    st_state<BYTES>(dist + ((size_t)row * 32 + lane) * BYTES, raw);
                     found_any = true;
                 }
             } else {
-                if (mine) p.coeff[rbase] = __ddiv_rn(__dadd_rn(1.0, acc), sv);
-                const double tot = warp_sum_f64(mine ? acc : 0.0);
+                double mysum = 0.0;
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    if ((mine >> s) & 1u) {
+                        p.coeff[rbase + s] = __ddiv_rn(__dadd_rn(1.0, acc[s]), sv[s]);
+                        mysum = __dadd_rn(mysum, acc[s]);
+                    }
+                }
+                const double tot = warp_sum_f64(mysum);
                 if (lane == 0) p.bc[row] = __dadd_rn(__ldcg(p.bc + row), tot);  // the row has one owner per sweep
             }
         }
@@ -166,27 +233,35 @@ __device__ __forceinline__ void bc_sweep(const BcParams &p, const BcList &L, int
     if (FWD && __any_sync(FULL_MASK, found_any) && lane == 0) st_relaxed_u32(flag, 1u);
 }
 
-template <typename DT>
-__global__ void __launch_bounds__(BC_THREADS, BC_MINB) bc_kernel(BcParams p)
+template <typename DT, int S>
+__global__ void __launch_bounds__(BC_THREADS, (S == 4 ? 2 : BC_MINB)) bc_kernel(BcParams p)
 {
     constexpr DT INF = (DT)~(DT)0;
+    constexpr int BYTES = S * (int)sizeof(DT);
+    constexpr int BITS = 8 * (int)sizeof(DT);
+    constexpr int W = 32 * S;
     const int lane = threadIdx.x & 31;
     const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    DT *dist = reinterpret_cast<DT *>(p.dist);
+    char *dist = reinterpret_cast<char *>(p.dist);
     u32 target = 0;  // barrier arrivals so far (the counter is zeroed before every launch)
     u32 pass = 0;    // sweeps so far: ticket counter / flag `pass % 3` is live, `(pass + 1) % 3` is being cleared
     bool overflow = false;
     for (long long batch = p.batch0; batch < p.batch1 && !overflow; ++batch) {
-        const long long src = batch * BC_LANES + lane;  // this lane's source node (>= n: idle lane)
+        const long long src0 = batch * W + (long long)lane * S;  // this lane's first source (>= n: idle)
         for (long long w = gwarp; w < p.n; w += nwarps) {
-            dist[(size_t)w * BC_LANES + lane] = (w == src) ? (DT)0 : INF;
-            if (w == src) p.sigma[(size_t)w * BC_LANES + lane] = 1.0;
+            u64 raw = ~0ull;
+            const long long rel = w - src0;
+            if (rel >= 0 && rel < S) {
+                raw &= ~((u64)INF << (rel * BITS));
+                p.sigma[((size_t)w * 32 + lane) * S + rel] = 1.0;
+            }
+            st_state<BYTES>(dist + ((size_t)w * 32 + lane) * BYTES, raw);
         }
         grid_barrier(p.sync, target, gridDim.x);
         int lvl = 0;
         for (;;) {
-            bc_sweep<DT, true>(p, p.fwd, lvl, 0, p.sync + 1 + pass % 3, p.sync + 4 + pass % 3);
+            bc_sweep<DT, S, true>(p, p.fwd, lvl, 0, p.sync + 1 + pass % 3, p.sync + 4 + pass % 3);
             if (blockIdx.x == 0 && threadIdx.x == 0) {
                 // counter / flag of the NEXT sweep: last touched two sweeps ago, i.e. before the previous barrier
                 p.sync[1 + (pass + 1) % 3] = 0;
@@ -208,9 +283,8 @@ __global__ void __launch_bounds__(BC_THREADS, BC_MINB) bc_kernel(BcParams p)
         }
         const int maxl = lvl;  // levels 0..maxl exist; rows at maxl have delta = 0 and contribute nothing
         for (int l = maxl - 1; l >= 1; --l) {
-            bc_sweep<DT, false>(p, p.bwd, l, maxl, p.sync + 1 + pass % 3, nullptr);
+            bc_sweep<DT, S, false>(p, p.bwd, l, maxl, p.sync + 1 + pass % 3, nullptr);
             if (blockIdx.x == 0 && threadIdx.x == 0) {
-                // counter / flag of the NEXT sweep: last touched two sweeps ago, i.e. before the previous barrier
                 p.sync[1 + (pass + 1) % 3] = 0;
                 p.sync[4 + (pass + 1) % 3] = 0;
             }
@@ -296,13 +370,14 @@ struct DevBuf {
     ~DevBuf() { cudaFree(p); }
 };
 
-template <typename DT>
-int run_batches(const BcParams &base, long long batches, int group, u32 *h_overflow, cudaStream_t stream)
+template <typename DT, int S>
+int run_batches(const BcParams &base, long long n, int group, u32 *h_overflow, cudaStream_t stream)
 {
+    const long long batches = (n + 32 * S - 1) / (32 * S);
     int occ = 0;
-    GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bc_kernel<DT>, BC_THREADS, 0));
+    GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bc_kernel<DT, S>, BC_THREADS, 0));
     GP_REQUIRE(occ >= 1, GP_ERR_CUDA, "betweenness kernel does not fit on an SM");
-    if (occ > BC_MINB) occ = BC_MINB;
+    if (occ > (S == 4 ? 2 : BC_MINB)) occ = (S == 4 ? 2 : BC_MINB);
     const int blocks = occ * gp_sm_count();
     *h_overflow = 0;
     for (long long b0 = 0; b0 < batches && !*h_overflow; b0 += group) {
@@ -312,7 +387,7 @@ int run_batches(const BcParams &base, long long batches, int group, u32 *h_overf
         GP_CUDA_CHECK(cudaMemsetAsync(p.sync, 0, 8 * sizeof(u32), stream));
         void *args[] = {&p};
         gp_count_launch();
-        GP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)bc_kernel<DT>, dim3(blocks), dim3(BC_THREADS), args, 0,
+        GP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)bc_kernel<DT, S>, dim3(blocks), dim3(BC_THREADS), args, 0,
                                                   stream));
         GP_CUDA_CHECK(cudaMemcpyAsync(h_overflow, p.sync + 7, sizeof(u32), cudaMemcpyDeviceToHost, stream));
         GP_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -357,14 +432,22 @@ extern "C" int gp_betweenness(const gp_csr_t *csr_, double *d_score, gp_stream_t
     p.n = n;
     p.bc = d_score;
 
+    // sources per lane (1, 2 or 4 -> 32, 64 or 128 sources per batch): more sources per batch amortise the
+    // per-level barrier and list scan and give a lane more independent loads per round trip; small graphs use
+    // fewer so that idle lanes do not pay.  GP_BC_SOURCES overrides.
+    int spl = n >= 4096 ? 4 : (n >= 1024 ? 2 : 1);
+    if (const char *e = getenv("GP_BC_SOURCES")) {
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4) spl = v;
+    }
     DevBuf dist, sigma, coeff, partial, arrive, sync;
-    const size_t cells = (size_t)n * BC_LANES;
+    const size_t cells = (size_t)n * 32 * spl;
     const size_t slots = (size_t)(hf.partial_slots > hb.partial_slots ? hf.partial_slots : hb.partial_slots);
     const size_t hubs = hf.hub_chunks.size() > hb.hub_chunks.size() ? hf.hub_chunks.size() : hb.hub_chunks.size();
     GP_CUDA_CHECK(cudaMalloc(&dist.p, cells * sizeof(uint16_t)));
     GP_CUDA_CHECK(cudaMalloc(&sigma.p, cells * sizeof(double)));
     GP_CUDA_CHECK(cudaMalloc(&coeff.p, cells * sizeof(double)));
-    GP_CUDA_CHECK(cudaMalloc(&partial.p, (slots ? slots : 1) * BC_LANES * sizeof(double)));
+    GP_CUDA_CHECK(cudaMalloc(&partial.p, (slots ? slots : 1) * 32 * spl * sizeof(double)));
     GP_CUDA_CHECK(cudaMalloc(&arrive.p, (hubs ? hubs : 1) * sizeof(u32)));
     GP_CUDA_CHECK(cudaMalloc(&sync.p, 8 * sizeof(u32)));
     GP_CUDA_CHECK(cudaMemsetAsync(arrive.p, 0, (hubs ? hubs : 1) * sizeof(u32), stream));
@@ -375,16 +458,20 @@ extern "C" int gp_betweenness(const gp_csr_t *csr_, double *d_score, gp_stream_t
     p.arrive = (u32 *)arrive.p;
     p.sync = (u32 *)sync.p;
 
-    const long long batches = (n + BC_LANES - 1) / BC_LANES;
-    int group = 128;  // batches per cooperative launch: bounds the run time of one launch
+    int group = 64;  // batches per cooperative launch: bounds the run time of one launch
     if (const char *e = getenv("GP_BC_GROUP")) group = atoi(e) > 0 ? atoi(e) : group;
     u32 overflow = 0;
-    // 8-bit hop counts first (one 32-byte sector per neighbour); a graph deeper than 253 hops restarts with 16 bits
-    GP_TRY(run_batches<uint8_t>(p, batches, group, &overflow, stream));
+    // 8-bit hop counts first (one sector per neighbour and 32 sources); a graph deeper than 253 hops restarts
+    // with 16 bits
+    if (spl == 4) GP_TRY((run_batches<uint8_t, 4>(p, n, group, &overflow, stream)));
+    else if (spl == 2) GP_TRY((run_batches<uint8_t, 2>(p, n, group, &overflow, stream)));
+    else GP_TRY((run_batches<uint8_t, 1>(p, n, group, &overflow, stream)));
     if (overflow) {
         GP_CUDA_CHECK(cudaMemsetAsync(d_score, 0, (size_t)n * sizeof(double), stream));
         GP_CUDA_CHECK(cudaMemsetAsync(arrive.p, 0, (hubs ? hubs : 1) * sizeof(u32), stream));
-        GP_TRY(run_batches<uint16_t>(p, batches, group, &overflow, stream));
+        if (spl == 4) GP_TRY((run_batches<uint16_t, 4>(p, n, group, &overflow, stream)));
+        else if (spl == 2) GP_TRY((run_batches<uint16_t, 2>(p, n, group, &overflow, stream)));
+        else GP_TRY((run_batches<uint16_t, 1>(p, n, group, &overflow, stream)));
         GP_REQUIRE(!overflow, GP_ERR_LEVEL_OVERFLOW, "gp_betweenness: a hop distance >= 65534");
     }
     // _rescale(normalized=True, directed=True, endpoints=False): scale = 1 / ((N-1) * (N-2)), Python float ops

@@ -166,11 +166,14 @@ def test_betweenness_scores_and_anchor_lists(dev, golden_betweenness):
     assert utils.sample_anchor_nodes(Data(ei, n), 16, "betweenness_centrality") == g["anchors/16"].tolist()
 
 
+@pytest.mark.parametrize("spl", [1, 2, 4])
 @pytest.mark.parametrize("case", ["directed-sparse", "path", "hub", "tiny"])
-def test_betweenness_matches_oracle_on_hard_graphs(dev, case):
+def test_betweenness_matches_oracle_on_hard_graphs(dev, case, spl, monkeypatch):
     """Unreachable pairs and dangling nodes; a 300-node path (hop counts beyond 253: the 16-bit restart);
-    a star-of-stars whose centre row is cut into 64-edge chunks; graphs of 1..3 nodes (no rescale)."""
+    a star-of-stars whose centre row is cut into 64-edge chunks; graphs of 1..3 nodes (no rescale) — each
+    with 1, 2 and 4 sources per lane (32 / 64 / 128 sources per batch)."""
     from oracle import samplers as s
+    monkeypatch.setenv("GP_BC_SOURCES", str(spl))
     if case == "directed-sparse":
         n = 700
         ei = synth.random_digraph(n, 1500, seed=31)

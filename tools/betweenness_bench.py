@@ -31,14 +31,17 @@ def main():
     csr = dev.DeviceCsr(n, ei.shape[1]).build(ei_d)
     e = csr.info()["num_edges"]
     torch.cuda.synchronize()
-    for rep in range(2):
-        t = time.perf_counter()
-        score = csr.betweenness()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t
-        print(f"{args.workload}: N={n} E'={e} betweenness of all nodes in {dt:.3f} s "
-              f"= {n * e / dt / 1e9:.1f} G source-edges/s ({2 * n * e / dt / 1e9:.1f} G edge visits/s, both sweeps)",
-              flush=True)
+    for spl in (1, 2, 4):
+        os.environ["GP_BC_SOURCES"] = str(spl)
+        for rep in range(2):
+            t = time.perf_counter()
+            score = csr.betweenness()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t
+            print(f"{args.workload}: N={n} E'={e} {32 * spl} sources per batch: betweenness of all nodes in {dt:.3f} s "
+                  f"= {n * e / dt / 1e9:.1f} G source-edges/s ({2 * n * e / dt / 1e9:.1f} G edge visits/s, both sweeps)",
+                  flush=True)
+    del os.environ["GP_BC_SOURCES"]
     s = score.cpu().numpy()
     print("sum", float(s.sum()), "max", float(s.max()), "argmax", int(s.argmax()), "non-zero", int((s > 0).sum()))
 
