@@ -21,6 +21,7 @@
 //
 // One persistent cooperative kernel walks all levels of a group of batches with a grid barrier per level;
 // work is dealt in tiles of items (row or 64-edge chunk of a row) from rotating ticket counters.
+#include <chrono>
 #include <vector>
 
 #include "gp_internal.h"
@@ -32,6 +33,14 @@ constexpr int BC_TILE = 4;      // items per ticket; their descriptors, row stat
 constexpr int BC_THREADS = 256;
 constexpr int BC_MINB = 3;
 constexpr int BC_UNROLL = 8;    // neighbour hop-count loads in flight per lane
+// Words of the sync block.  The barrier word is polled by every CTA while late warps still draw tickets, so the
+// barrier, each ticket counter and each flag live in their own 128-byte line.
+constexpr int BC_SYNC_BARRIER = 0;
+constexpr int BC_SYNC_TICKET = 32;    // + 32 * (sweep % 3)
+constexpr int BC_SYNC_FLAG = 128;     // + 32 * (sweep % 3)
+constexpr int BC_SYNC_OVERFLOW = 224;
+constexpr int BC_SYNC_SWEEPS = 225;
+constexpr int BC_SYNC_WORDS = 256;
 
 struct BcList {
     const int4 *items;       // {row, first edge, count | chunk << 8, hub slot or -1}
@@ -50,7 +59,7 @@ struct BcParams {
     double *partial;         // [chunks of chunked rows][32 * S]
     u32 *arrive;             // [hubs] arrival counters (left at zero by the finaliser)
     double *bc;              // [n] running sum of delta over the sources done so far
-    u32 *sync;               // [0] barrier, [1..3] ticket counters, [4..6] "something settled" flags, [7] overflow
+    u32 *sync;               // BC_SYNC_* words: barrier, 3 ticket counters, 3 "something settled" flags, overflow
     long long batch0, batch1;
 };
 
@@ -97,12 +106,14 @@ __device__ __forceinline__ void bc_sweep(const BcParams &p, const BcList &L, int
     const bool leaf = !FWD && (lvl + 1 == maxl);  // neighbours at the deepest level: coeff = 1 / sigma
     bool found_any = false;
     const int tiles = (L.num_items + BC_TILE - 1) / BC_TILE;
-    u32 next = 0;
-    if (lane == 0) next = atomicAdd(ticket, 1u);
+    // first tile of a warp: its own index (no atomic); further tiles are drawn from the ticket counter, each
+    // fetched while the previous tile is processed
+    const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+    u32 next = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     for (;;) {
         const u32 t = __shfl_sync(FULL_MASK, next, 0);
         if (t >= (u32)tiles) break;
-        if (lane == 0) next = atomicAdd(ticket, 1u);  // fetched while this tile is processed
+        if (lane == 0) next = nwarps + atomicAdd(ticket, 1u);
         const int i0 = (int)t * BC_TILE;
         // round trip 1: the tile's descriptors (lane k holds item k); round trip 2: every item's row state and
         // first 32 columns, issued together
@@ -258,17 +269,17 @@ __global__ void __launch_bounds__(BC_THREADS, (S == 4 ? 2 : BC_MINB)) bc_kernel(
             }
             st_state<BYTES>(dist + ((size_t)w * 32 + lane) * BYTES, raw);
         }
-        grid_barrier(p.sync, target, gridDim.x);
+        grid_barrier(p.sync + BC_SYNC_BARRIER, target, gridDim.x);
         int lvl = 0;
         for (;;) {
-            bc_sweep<DT, S, true>(p, p.fwd, lvl, 0, p.sync + 1 + pass % 3, p.sync + 4 + pass % 3);
+            bc_sweep<DT, S, true>(p, p.fwd, lvl, 0, p.sync + BC_SYNC_TICKET + 32 * (pass % 3), p.sync + BC_SYNC_FLAG + 32 * (pass % 3));
             if (blockIdx.x == 0 && threadIdx.x == 0) {
                 // counter / flag of the NEXT sweep: last touched two sweeps ago, i.e. before the previous barrier
-                p.sync[1 + (pass + 1) % 3] = 0;
-                p.sync[4 + (pass + 1) % 3] = 0;
+                p.sync[BC_SYNC_TICKET + 32 * ((pass + 1) % 3)] = 0;
+                p.sync[BC_SYNC_FLAG + 32 * ((pass + 1) % 3)] = 0;
             }
-            grid_barrier(p.sync, target, gridDim.x);
-            const u32 found = ld_relaxed_u32(p.sync + 4 + pass % 3);
+            grid_barrier(p.sync + BC_SYNC_BARRIER, target, gridDim.x);
+            const u32 found = ld_relaxed_u32(p.sync + BC_SYNC_FLAG + 32 * (pass % 3));
             ++pass;
             if (!found) break;
             ++lvl;
@@ -278,20 +289,21 @@ __global__ void __launch_bounds__(BC_THREADS, (S == 4 ? 2 : BC_MINB)) bc_kernel(
             }
         }
         if (overflow) {
-            if (blockIdx.x == 0 && threadIdx.x == 0) p.sync[7] = 1;
+            if (blockIdx.x == 0 && threadIdx.x == 0) p.sync[BC_SYNC_OVERFLOW] = 1;
             break;
         }
         const int maxl = lvl;  // levels 0..maxl exist; rows at maxl have delta = 0 and contribute nothing
         for (int l = maxl - 1; l >= 1; --l) {
-            bc_sweep<DT, S, false>(p, p.bwd, l, maxl, p.sync + 1 + pass % 3, nullptr);
+            bc_sweep<DT, S, false>(p, p.bwd, l, maxl, p.sync + BC_SYNC_TICKET + 32 * (pass % 3), nullptr);
             if (blockIdx.x == 0 && threadIdx.x == 0) {
-                p.sync[1 + (pass + 1) % 3] = 0;
-                p.sync[4 + (pass + 1) % 3] = 0;
+                p.sync[BC_SYNC_TICKET + 32 * ((pass + 1) % 3)] = 0;
+                p.sync[BC_SYNC_FLAG + 32 * ((pass + 1) % 3)] = 0;
             }
-            grid_barrier(p.sync, target, gridDim.x);
+            grid_barrier(p.sync + BC_SYNC_BARRIER, target, gridDim.x);
             ++pass;
         }
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.sync[BC_SYNC_SWEEPS] = pass;  // sweeps of this launch (diagnostics)
 }
 
 __global__ void bc_scale_kernel(double *bc, long long n, double scale)
@@ -365,6 +377,11 @@ int upload_list(const HostList &h, DevList &d, BcList &out, const int *col, cuda
     return GP_OK;
 }
 
+double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 struct DevBuf {
     void *p = nullptr;
     ~DevBuf() { cudaFree(p); }
@@ -380,17 +397,26 @@ int run_batches(const BcParams &base, long long n, int group, u32 *h_overflow, c
     if (occ > (S == 4 ? 2 : BC_MINB)) occ = (S == 4 ? 2 : BC_MINB);
     const int blocks = occ * gp_sm_count();
     *h_overflow = 0;
+    const bool trace = getenv("GP_BC_TRACE") != nullptr;
     for (long long b0 = 0; b0 < batches && !*h_overflow; b0 += group) {
+        const double t0 = trace ? now_ms() : 0.0;
         BcParams p = base;
         p.batch0 = b0;
         p.batch1 = b0 + group < batches ? b0 + group : batches;
-        GP_CUDA_CHECK(cudaMemsetAsync(p.sync, 0, 8 * sizeof(u32), stream));
+        GP_CUDA_CHECK(cudaMemsetAsync(p.sync, 0, BC_SYNC_WORDS * sizeof(u32), stream));
         void *args[] = {&p};
         gp_count_launch();
         GP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)bc_kernel<DT, S>, dim3(blocks), dim3(BC_THREADS), args, 0,
                                                   stream));
-        GP_CUDA_CHECK(cudaMemcpyAsync(h_overflow, p.sync + 7, sizeof(u32), cudaMemcpyDeviceToHost, stream));
+        GP_CUDA_CHECK(cudaMemcpyAsync(h_overflow, p.sync + BC_SYNC_OVERFLOW, sizeof(u32), cudaMemcpyDeviceToHost, stream));
         GP_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (trace) {
+            u32 sweeps = 0;
+            GP_CUDA_CHECK(cudaMemcpy(&sweeps, p.sync + BC_SYNC_SWEEPS, sizeof(u32), cudaMemcpyDeviceToHost));
+            const double t1 = now_ms();
+            fprintf(stderr, "[gp_betweenness] S=%d bytes=%d blocks=%d batches %lld..%lld: %u sweeps, %.3f ms (%.1f us per sweep)\n",
+                    S, (int)sizeof(DT), blocks, b0, p.batch1, sweeps, t1 - t0, sweeps ? (t1 - t0) * 1e3 / sweeps : 0.0);
+        }
     }
     return GP_OK;
 }
@@ -433,9 +459,9 @@ extern "C" int gp_betweenness(const gp_csr_t *csr_, double *d_score, gp_stream_t
     p.bc = d_score;
 
     // sources per lane (1, 2 or 4 -> 32, 64 or 128 sources per batch): more sources per batch amortise the
-    // per-level barrier and list scan and give a lane more independent loads per round trip; small graphs use
-    // fewer so that idle lanes do not pay.  GP_BC_SOURCES overrides.
-    int spl = n >= 4096 ? 4 : (n >= 1024 ? 2 : 1);
+    // per-level barrier and list scan; the work per source stays the same (the sweeps are bound by instruction
+    // issue), so the gain flattens: Flickr-shape 3.8 / 3.0 / 3.7 s for 1 / 2 / 4.  GP_BC_SOURCES overrides.
+    int spl = n >= 512 ? 2 : 1;
     if (const char *e = getenv("GP_BC_SOURCES")) {
         const int v = atoi(e);
         if (v == 1 || v == 2 || v == 4) spl = v;
@@ -449,7 +475,7 @@ extern "C" int gp_betweenness(const gp_csr_t *csr_, double *d_score, gp_stream_t
     GP_CUDA_CHECK(cudaMalloc(&coeff.p, cells * sizeof(double)));
     GP_CUDA_CHECK(cudaMalloc(&partial.p, (slots ? slots : 1) * 32 * spl * sizeof(double)));
     GP_CUDA_CHECK(cudaMalloc(&arrive.p, (hubs ? hubs : 1) * sizeof(u32)));
-    GP_CUDA_CHECK(cudaMalloc(&sync.p, 8 * sizeof(u32)));
+    GP_CUDA_CHECK(cudaMalloc(&sync.p, BC_SYNC_WORDS * sizeof(u32)));
     GP_CUDA_CHECK(cudaMemsetAsync(arrive.p, 0, (hubs ? hubs : 1) * sizeof(u32), stream));
     p.dist = dist.p;
     p.sigma = (double *)sigma.p;

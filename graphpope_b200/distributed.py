@@ -217,10 +217,11 @@ class PeerAssembly:
             self._shard_key, self._shard = key, anchors[lo:hi].contiguous()
         edge_index = edge_index.contiguous()
         eng.csr._edges, eng.bfs._anchors, eng.bfs.num_anchors = edge_index, self._shard, hi - lo
-        # concat_into_features' copy of x (utils.py:133-134) does not depend on the traversal: one strided
-        # device-to-device transfer on a side stream while this rank builds, traverses and packs
+        # concat_into_features' copy of x (utils.py:133-134) does not depend on the traversal; opt-in
+        # (GP_XCOPY_OVERLAP=1): one strided device-to-device transfer on a side stream while this rank builds,
+        # traverses and packs.  Off by default: on one GPU the overlapped forms measured slower than the fused copy.
         side = None
-        if x is not None and f > 0 and n > 0 and os.environ.get("GP_XCOPY_OVERLAP", "1") != "0":
+        if x is not None and f > 0 and n > 0 and os.environ.get("GP_XCOPY_OVERLAP", "0") != "0":
             if self._side is None:
                 self._side = torch.cuda.Stream()
             side = self._side

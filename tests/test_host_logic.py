@@ -49,10 +49,14 @@ def test_unknown_sampler_raises_like_the_reference():
         utils.sample_anchor_nodes(Data(np.zeros((2, 0), np.int64), 5), 2, "kmeans")
 
 
-def test_host_centralities_use_networkx_top_k_rule():
+def test_host_centralities_use_networkx_top_k_rule(monkeypatch):
     import networkx as nx
     ei = np.array([[0, 1, 1, 2, 2, 3, 3, 4, 1, 3], [1, 0, 2, 1, 3, 2, 4, 3, 3, 1]])
     data = Data(ei, 6)
+    if not torch.cuda.is_available():  # betweenness runs on the device by default and must fail loudly without one
+        with pytest.raises(RuntimeError):
+            utils.sample_anchor_nodes(data, 3, "betweenness_centrality")
+    monkeypatch.setenv("GRAPHPOPE_BETWEENNESS", "networkx")  # the reference's own call, kept as an option
     got = utils.sample_anchor_nodes(data, 3, "betweenness_centrality")
     G = nx.DiGraph(); G.add_nodes_from(range(6)); G.add_edges_from(zip(*ei.tolist()))
     score = nx.betweenness_centrality(G)
