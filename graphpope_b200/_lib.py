@@ -97,6 +97,7 @@ SIGNATURES = {
     "gp_closeness": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gp_clustering": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gp_betweenness": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "gp_eigenvector": (c_int, [c_void_p, c_double, c_int32, c_void_p, POINTER(c_int32), c_void_p]),
     "gp_kmeans_plusplus": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_uint64, c_void_p, c_void_p, c_void_p,
                                    c_void_p]),
     "gp_kmeans_assign": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),

@@ -243,6 +243,120 @@ extern "C" int gp_pagerank(const gp_csr_t *csr_, double alpha, double tol, int32
     return GP_OK;
 }
 
+// ------------------------------------------------------------------------------------------ eigenvector
+// eigenvector_centrality (utils.py:44-48 -> nx.eigenvector_centrality_numpy): the eigenvector of A^T for
+// its largest real eigenvalue (in-edge centrality), unit L2 norm, positive sum.  networkx hands the matrix to
+// ARPACK; here: power iteration on (A^T + I) — the shift makes the Perron root strictly dominant also on
+// periodic graphs — in float64, one thread per row with the in-neighbours added in ascending order, fixed-
+// order reductions, until the L1 change of the normalised vector drops below N * tol.
+namespace {
+
+__global__ void ev_fill_kernel(double *x, long long n, double v)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = v;
+}
+
+__device__ __forceinline__ void block_partial(double v, double *partial)
+{
+    __shared__ double s_part[8];
+    for (int m = 16; m; m >>= 1) v += __shfl_xor_sync(FULL_MASK, v, m);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_part[w];
+        partial[blockIdx.x] = t;
+    }
+}
+
+// y = (A^T + I) x; partial[b] = this block's share of |y|^2
+__global__ void __launch_bounds__(256)
+ev_pull_kernel(const int *__restrict__ rp_in, const int *__restrict__ col_in, const double *__restrict__ x, long long n,
+               double *__restrict__ y, double *__restrict__ partial)
+{
+    double ss = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+        const int s = rp_in[v], e = rp_in[v + 1];
+        double acc = x[v];
+        int j = s;
+        for (; j + 4 <= e; j += 4) {
+            const double c0 = x[col_in[j]], c1 = x[col_in[j + 1]], c2 = x[col_in[j + 2]], c3 = x[col_in[j + 3]];
+            acc = __dadd_rn(acc, c0);
+            acc = __dadd_rn(acc, c1);
+            acc = __dadd_rn(acc, c2);
+            acc = __dadd_rn(acc, c3);
+        }
+        for (; j < e; ++j) acc = __dadd_rn(acc, x[col_in[j]]);
+        y[v] = acc;
+        ss += acc * acc;
+    }
+    block_partial(ss, partial);
+}
+
+// x_new = y / |y|; partial[b] = this block's share of |x_new - x|_1.  `ss` holds |y|^2.
+__global__ void __launch_bounds__(256)
+ev_scale_kernel(const double *__restrict__ y, const double *__restrict__ ss, double *__restrict__ x, long long n,
+                double *__restrict__ partial)
+{
+    const double norm = sqrt(*ss);
+    double err = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+        const double xv = __ddiv_rn(y[v], norm);
+        err += fabs(xv - x[v]);
+        x[v] = xv;
+    }
+    block_partial(err, partial);
+}
+
+}  // namespace
+
+extern "C" int gp_eigenvector(const gp_csr_t *csr_, double tol, int32_t max_iter, double *d_x, int32_t *iterations,
+                              gp_stream_t stream_)
+{
+    gp_csr *csr = const_cast<gp_csr *>(csr_);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GP_REQUIRE(csr != nullptr && d_x != nullptr, GP_ERR_INVALID, "gp_eigenvector: NULL argument");
+    GP_REQUIRE(csr->built, GP_ERR_INVALID, "gp_eigenvector: the CSR has not been built");
+    GP_REQUIRE(tol >= 0 && max_iter >= 1, GP_ERR_INVALID, "gp_eigenvector: bad tolerance / iteration limit");
+    if (iterations) *iterations = 0;
+    const long long n = csr->num_nodes;
+    if (n == 0) return GP_OK;
+    GP_TRY(gp_csr_ensure_in(csr, stream));
+    const int nblocks = blocks_for(n);
+    DevBuf b_y, b_partial, b_small;
+    GP_CUDA_CHECK(cudaMalloc(&b_y.p, sizeof(double) * n));
+    GP_CUDA_CHECK(cudaMalloc(&b_partial.p, sizeof(double) * nblocks));
+    GP_CUDA_CHECK(cudaMalloc(&b_small.p, 64));
+    double *y = (double *)b_y.p, *partial = (double *)b_partial.p, *scalar = (double *)b_small.p;
+    GP_LAUNCH(ev_fill_kernel, nblocks, 256, 0, stream, d_x, n, 1.0 / sqrt((double)n));
+    bool converged = false;
+    int it = 0;
+    const int check_every = 8;  // one host round trip per 8 iterations
+    while (it < max_iter && !converged) {
+        double h_err = 0.0;
+        for (int q = 0; q < check_every && it < max_iter; ++q, ++it) {
+            GP_LAUNCH(ev_pull_kernel, nblocks, 256, 0, stream, csr->rowptr_in, csr->col_in, d_x, n, y, partial);
+            GP_LAUNCH(pr_err_kernel, 1, 256, 0, stream, (const double *)partial, nblocks, scalar);
+            GP_LAUNCH(ev_scale_kernel, nblocks, 256, 0, stream, y, scalar, d_x, n, partial);
+            GP_LAUNCH(pr_err_kernel, 1, 256, 0, stream, (const double *)partial, nblocks, scalar + 1);
+        }
+        GP_CUDA_CHECK(cudaMemcpyAsync(&h_err, scalar + 1, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        GP_CUDA_CHECK(cudaStreamSynchronize(stream));
+        converged = h_err <= (double)n * tol;
+    }
+    int csr_err = 0;
+    GP_CUDA_CHECK(cudaMemcpy(&csr_err, &csr->meta[GP_META_ERROR], sizeof(int), cudaMemcpyDeviceToHost));
+    GP_REQUIRE(!(csr_err & GP_DEV_ERR_EDGE_RANGE), GP_ERR_INDEX_RANGE,
+               "edge_index holds an entry outside [0, %lld)", n);
+    if (iterations) *iterations = it;
+    GP_REQUIRE(converged, GP_ERR_NOT_CONVERGED,
+               "eigenvector centrality: power iteration did not reach tol %.3g in %d iterations", tol, max_iter);
+    return GP_OK;
+}
+
 static int topk_common(const int *d_score_i32, const double *d_score_f64, int64_t n, int64_t k, int64_t *d_out,
                        cudaStream_t stream)
 {

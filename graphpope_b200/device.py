@@ -106,6 +106,14 @@ class DeviceCsr:
         check(self._lib.gp_betweenness(self._h, _ptr(x), _stream()))
         return x
 
+    def eigenvector(self, tol: float = 1e-15, max_iter: int = 20000):
+        """networkx ``eigenvector_centrality_numpy`` (utils.py:44-48) by power iteration on ``A^T + I``:
+        (float64[N] unit-norm positive vector, iterations).  Agrees with ARPACK to rounding, not bit for bit."""
+        x = torch.empty(self.num_nodes, dtype=torch.float64, device="cuda")
+        it = c_int32(0)
+        check(self._lib.gp_eigenvector(self._h, tol, max_iter, _ptr(x), byref(it), _stream()))
+        return x, it.value
+
     def close(self):
         if self._h:
             self._lib.gp_csr_free(self._h)

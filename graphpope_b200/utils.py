@@ -27,8 +27,9 @@ What runs where
     stable top-k).
   * KMeans centres of the node2vec branch: device (k-means++ + Lloyd, tensor-core assignment; statistical
     parity with scikit-learn, which the reference runs unseeded).
-  * eigenvector anchors: the reference's own networkx call on the host (stated scope of the port,
-    SURVEY.md §8 a3x / §8f).
+  * ``eigenvector_centrality`` anchors: device (float64 power iteration on ``A^T + I``; strong connectivity
+    checked with two single-anchor MS-BFS sweeps, as networkx >= 3.2 refuses disconnected graphs).
+    ``GRAPHPOPE_BETWEENNESS=networkx`` / ``GRAPHPOPE_EIGENVECTOR=networkx`` keep the reference's own calls.
 There is no CPU fallback for the device parts: without the CUDA library or a GPU these functions raise.
 """
 from __future__ import annotations
@@ -163,6 +164,25 @@ def sample_anchor_nodes(data, num_anchor_nodes, sampling_method):
         # within a few ulp of networkx (GRAPHPOPE_BETWEENNESS=networkx keeps the reference's call below)
         csr = _device_csr(data)
         return _dev.topk_stable(csr.betweenness(), num_anchor_nodes).cpu().tolist()
+
+    if sampling_method == 'eigenvector_centrality' and os.environ.get("GRAPHPOPE_EIGENVECTOR", "cuda") != "networkx":
+        # float64 power iteration on A^T + I (gp_sampler.cu); networkx hands the matrix to ARPACK, whose random
+        # start makes even the reference reproducible only to ~1e-16 (GRAPHPOPE_EIGENVECTOR=networkx keeps its call)
+        import networkx as nx
+
+        n = int(data.num_nodes)
+        if n == 0:
+            raise nx.NetworkXPointlessConcept("cannot compute centrality for the null graph")
+        ei = _edge_index_of(data)
+        # eigenvector_centrality_numpy refuses graphs that are not strongly connected (networkx >= 3.2):
+        # node 0 must reach, and be reached by, every node — two single-anchor sweeps of the MS-BFS
+        for e in (ei, ei.flip(0)):
+            _, hops, _ = _dev.geodesic_embed_host(e.contiguous(), n, [0], None, False, want_hops=True)
+            if bool((hops.numpy() == _lib.GP_UNREACHABLE_U16).any()):
+                raise nx.AmbiguousSolution(
+                    "`eigenvector_centrality_numpy` does not give consistent results for disconnected graphs")
+        score, _ = _device_csr(data).eigenvector()
+        return _dev.topk_stable(score, num_anchor_nodes).cpu().tolist()
 
     if sampling_method in _HOST_CENTRALITIES:
         # Not re-implemented (north_star): the reference's own networkx call, same top-k rule.

@@ -258,6 +258,13 @@ int gp_clustering(const gp_csr_t *csr, double *d_score, gp_stream_t stream);
  * order that differs from networkx's queue order, so scores agree to a few ulp, not bit for bit.  syncs.
  * d_score float64[N].                                                                                  */
 int gp_betweenness(const gp_csr_t *csr, double *d_score, gp_stream_t stream);
+/* eigenvector_centrality (utils.py:44-48 -> nx.eigenvector_centrality_numpy: eigenvector of A^T for the
+ * largest real eigenvalue, unit L2 norm, positive): float64 power iteration on (A^T + I) until the L1 change
+ * of the normalised vector is <= N * tol.  networkx uses ARPACK, so scores agree to rounding (tests: 1e-9), not
+ * bit for bit; the caller checks strong connectivity first, as networkx >= 3.2 does.  syncs.  d_x float64[N].
+ * GP_ERR_NOT_CONVERGED after max_iter iterations (graphs with a tiny spectral gap, e.g. long paths).    */
+int gp_eigenvector(const gp_csr_t *csr, double tol, int32_t max_iter, double *d_x, int32_t *iterations,
+                   gp_stream_t stream);
 /* Stable top-k of utils.py:29-30 / 41-42: ascending stable sort by score, keep
  * the last k (ties keep ascending node id; output in ascending-score order).
  * async.  d_out int64[min(k, N)] (k == 0 returns all N: list[-0:] quirk).       */

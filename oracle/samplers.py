@@ -3,9 +3,8 @@
 TEST INFRASTRUCTURE — see oracle/__init__.py.
 
 Only the samplers the device path re-implements are restated here
-(stochastic, degree_centrality, pagerank, closeness_centrality, clustering_coefficient,
-betweenness_centrality).  eigenvector_centrality stays on the reference's own networkx
-call in the product (north_star).
+(all seven: stochastic, degree_centrality, pagerank, closeness_centrality,
+clustering_coefficient, betweenness_centrality, eigenvector_centrality).
 
 Third-party arithmetic restated: networkx (unpinned by the reference's
 requirements.txt; 3.6.1 installed) ``degree_centrality`` and
@@ -295,3 +294,32 @@ def betweenness_levelsync_scores(edge_index, num_nodes: int) -> np.ndarray:
 
 def betweenness_centrality_anchors(edge_index, num_nodes: int, k: int) -> list:
     return stable_top_k(betweenness_scores(edge_index, num_nodes), k)
+
+
+def eigenvector_scores(edge_index, num_nodes: int) -> np.ndarray:
+    """networkx ``eigenvector_centrality_numpy(G)`` defaults restated (utils.py:44-48 call site; networkx
+    3.6.1): refuse graphs that are not strongly connected, hand ``A^T`` to ARPACK (``eigs(k=1, which='LR',
+    maxiter=50, tol=0)``), take the real part, scale to unit L2 norm with a positive sum.  ARPACK starts from
+    a random vector, so even two runs of the reference differ in the last bits (~1e-16): parity for this
+    sampler is a tolerance (tests: 1e-12 against the frozen scores), not bit equality.
+    """
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as sla
+    from scipy.sparse.csgraph import connected_components
+
+    n = int(num_nodes)
+    if n == 0:
+        raise ValueError("cannot compute centrality for the null graph")
+    s_, d_ = dedup_edges(edge_index, n)
+    M = sp.csr_array((np.ones(s_.size), (s_, d_)), shape=(n, n))
+    ncomp, _ = connected_components(M, directed=True, connection="strong")
+    if ncomp != 1:
+        raise ValueError("`eigenvector_centrality_numpy` does not give consistent results for disconnected graphs")
+    _, vec = sla.eigs(M.T, k=1, which="LR", maxiter=50, tol=0)
+    largest = vec.flatten().real
+    norm = np.sign(largest.sum()) * np.linalg.norm(largest)
+    return largest / norm
+
+
+def eigenvector_centrality_anchors(edge_index, num_nodes: int, k: int) -> list:
+    return stable_top_k(eigenvector_scores(edge_index, num_nodes), k)

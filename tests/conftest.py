@@ -31,5 +31,10 @@ def golden_betweenness():
     return np.load(os.path.join(GOLDEN_DIR, "reference_betweenness.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_eigenvector():
+    return np.load(os.path.join(GOLDEN_DIR, "reference_eigenvector.npz"))
+
+
 def micro_names(golden):
     return sorted({k.split("/")[1] for k in golden.files if k.startswith("micro/")})

@@ -5,6 +5,7 @@ Run in the build container only (needs /root/reference):
     python tests/golden/generate_golden.py            # small fixtures, seconds
     python tests/golden/generate_golden.py --pubmed   # + full C1 config (~2 min, 6 workers)
     python tests/golden/generate_golden.py --betweenness   # ONLY reference_betweenness.npz (seconds)
+    python tests/golden/generate_golden.py --eigenvector   # ONLY reference_eigenvector.npz (seconds)
 
 The reference has no tests or golden vectors of its own, so these
 files ARE the parity pins: every value below is produced by
@@ -73,14 +74,53 @@ def betweenness_fixture(utils):
     print("wrote reference_betweenness.npz; non-zero scores:", int((out["scores"] > 0).sum()))
 
 
+def strongly_connected_graph(n_target=800, seed=51):
+    """Giant component of a heavy-tailed symmetric graph, relabelled 0..m-1, plus random one-way edges
+    (adding edges keeps it strongly connected; they make in- and out-neighbourhoods differ)."""
+    import networkx as nx
+
+    ei = synth.chung_lu_symmetric(n_target, 6 * n_target, 2.2, seed=seed)
+    G = nx.Graph()
+    G.add_nodes_from(range(n_target))
+    G.add_edges_from(zip(ei[0].tolist(), ei[1].tolist()))
+    giant = sorted(max(nx.connected_components(G), key=len))
+    relabel = {v: i for i, v in enumerate(giant)}
+    keep = [(relabel[u], relabel[v]) for u, v in zip(ei[0].tolist(), ei[1].tolist()) if u in relabel and v in relabel]
+    m = len(giant)
+    extra = synth.random_digraph(m, m // 4, seed=seed + 1)
+    out = np.concatenate([np.asarray(keep, dtype=np.int64).T, extra], axis=1)
+    return np.ascontiguousarray(out), m
+
+
+def eigenvector_fixture(utils):
+    """reference_eigenvector.npz: utils.sample_anchor_nodes(..., 'eigenvector_centrality') (utils.py:44-48) and
+    the nx.eigenvector_centrality_numpy scores it ranks, on a strongly connected digraph (networkx >= 3.2
+    refuses anything else)."""
+    import networkx as nx
+
+    ei, n = strongly_connected_graph()
+    data = RefData(torch.tensor(ei), n)
+    out = {"n": np.int64(n), "edge_index": ei}
+    for k in (1, 16, 64, 256):
+        out[f"anchors/{k}"] = np.asarray(utils.sample_anchor_nodes(data, k, "eigenvector_centrality"), dtype=np.int64)
+    ev = nx.eigenvector_centrality_numpy(utils.to_networkx(data))
+    out["scores"] = np.asarray([ev[i] for i in range(n)], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "reference_eigenvector.npz"), **out)
+    print("wrote reference_eigenvector.npz; n =", n, "min score", float(out["scores"].min()))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pubmed", action="store_true")
     ap.add_argument("--betweenness", action="store_true")
+    ap.add_argument("--eigenvector", action="store_true")
     args = ap.parse_args()
     utils = load_reference_utils()
-    if args.betweenness:
-        betweenness_fixture(utils)
+    if args.betweenness or args.eigenvector:
+        if args.betweenness:
+            betweenness_fixture(utils)
+        if args.eigenvector:
+            eigenvector_fixture(utils)
         return
     out = {}
 

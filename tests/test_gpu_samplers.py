@@ -200,3 +200,28 @@ def test_betweenness_matches_oracle_on_hard_graphs(dev, case, spl, monkeypatch):
     want = s.betweenness_scores(ei, n)
     assert np.array_equal(got == 0, want == 0)
     assert np.allclose(got, want, rtol=1e-10, atol=0)
+
+
+def test_eigenvector_scores_and_anchor_lists(dev, golden_eigenvector):
+    """nx.eigenvector_centrality_numpy (utils.py:44-48) by float64 power iteration on A^T + I."""
+    import networkx as nx
+
+    from graphpope_b200 import utils
+    g = golden_eigenvector
+    ei, n = g["edge_index"], int(g["n"])
+    csr = dev.DeviceCsr(n, ei.shape[1]).build(torch.as_tensor(ei).cuda())
+    got, iters = csr.eigenvector()
+    got = got.cpu().numpy()
+    assert 1 <= iters < 20000
+    assert abs(np.linalg.norm(got) - 1.0) < 1e-14 and (got > 0).all()
+    assert np.allclose(got, g["scores"], rtol=1e-9, atol=1e-12)  # tolerance of this sampler (ARPACK vs power iteration)
+    for k in (1, 16, 64, 256):
+        _assert_same_ranking(got, g["scores"], k, rtol=1e-9)
+    assert utils.sample_anchor_nodes(Data(ei, n), 16, "eigenvector_centrality") == g["anchors/16"].tolist()
+    # a directed cycle (period 5: every eigenvalue has modulus 1, the shift makes the Perron root dominant)
+    cyc = np.array([[0, 1, 2, 3, 4], [1, 2, 3, 4, 0]])
+    x, _ = dev.DeviceCsr(5, 5).build(torch.as_tensor(cyc).cuda()).eigenvector()
+    assert np.allclose(x.cpu().numpy(), 1 / np.sqrt(5), rtol=0, atol=1e-12)
+    # not strongly connected: the reference (networkx >= 3.2) raises AmbiguousSolution, and so does the mirror
+    with pytest.raises(nx.AmbiguousSolution):
+        utils.sample_anchor_nodes(Data(np.array([[0, 1, 2], [1, 0, 1]]), 4), 2, "eigenvector_centrality")

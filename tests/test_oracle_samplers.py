@@ -78,3 +78,16 @@ def test_betweenness_device_summation_order_stays_within_a_few_ulp():
     got = s.betweenness_levelsync_scores(ei, n)
     assert np.array_equal(got == 0, want == 0)  # exact zeros (nodes on no shortest path) stay exact
     assert np.allclose(got, want, rtol=1e-13, atol=0)
+
+
+def test_eigenvector_matches_reference(golden_eigenvector):
+    import pytest
+    g = golden_eigenvector
+    ei, n = g["edge_index"], int(g["n"])
+    x = s.eigenvector_scores(ei, n)
+    # ARPACK starts from a random vector: the reference itself reproduces these scores only to ~1e-16
+    assert np.allclose(x, g["scores"], rtol=0, atol=1e-12)
+    for k in (1, 16, 64, 256):
+        assert s.stable_top_k(x, k) == g[f"anchors/{k}"].tolist()
+    with pytest.raises(ValueError):  # networkx >= 3.2 raises AmbiguousSolution on a disconnected graph
+        s.eigenvector_scores(np.array([[0, 1], [1, 0]]), 3)
