@@ -73,6 +73,48 @@ __device__ __forceinline__ float decode_one(const GpDecodeParams &p, Valid va, l
     return inv_hops(hops_one(p, va, w, bit));
 }
 
+// concat_into_features' copy of one x row (utils.py:133-134) by a warp: out[0:F] = x[0:F].  The loads of a
+// chunk are all issued before its stores — written as `o4[i] = x4[i]` the compiler must assume the two rows
+// alias and keeps ONE 512-byte load in flight per warp, which left the epilogue at 65 % of the HBM peak.
+// Streaming loads / stores: both rows are touched once.
+__device__ __forceinline__ void copy_x_row(const float *xrow, float *orow, int f, int lane, int vec_x)
+{
+    constexpr int T = 4;  // float4 loads in flight per lane
+    if (vec_x) {
+        const float4 *x4 = reinterpret_cast<const float4 *>(xrow);
+        float4 *o4 = reinterpret_cast<float4 *>(orow);
+        const int q = f >> 2;
+        for (int i0 = 0; i0 < q; i0 += 32 * T) {
+            float4 v[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int i = i0 + lane + 32 * t;
+                if (i < q) v[t] = __ldcs(x4 + i);
+            }
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int i = i0 + lane + 32 * t;
+                if (i < q) __stcs(o4 + i, v[t]);
+            }
+        }
+        for (int i = (q << 2) + lane; i < f; i += 32) orow[i] = __ldcs(xrow + i);
+    } else {
+        for (int i0 = 0; i0 < f; i0 += 32 * T) {
+            float v[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int i = i0 + lane + 32 * t;
+                if (i < f) v[t] = __ldcs(xrow + i);
+            }
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int i = i0 + lane + 32 * t;
+                if (i < f) __stcs(orow + i, v[t]);
+            }
+        }
+    }
+}
+
 // One warp per output row.
 __global__ void __launch_bounds__(256) decode_features_kernel(GpDecodeParams p, long long k_total, int vec_x,
                                                               int vec_f)
@@ -83,18 +125,7 @@ __global__ void __launch_bounds__(256) decode_features_kernel(GpDecodeParams p, 
     const Valid va = valid_arrays(p);
     for (long long u = warp; u < p.n; u += nwarps) {
         float *orow = p.out + (size_t)u * p.ld_out;
-        if (p.x != nullptr) {
-            const float *xrow = p.x + (size_t)u * p.ld_x;
-            if (vec_x) {
-                const float4 *x4 = reinterpret_cast<const float4 *>(xrow);
-                float4 *o4 = reinterpret_cast<float4 *>(orow);
-                const int q = (int)(p.num_features >> 2);
-                for (int i = lane; i < q; i += 32) o4[i] = __ldg(x4 + i);
-                for (long long i = ((long long)q << 2) + lane; i < p.num_features; i += 32) orow[i] = __ldg(xrow + i);
-            } else {
-                for (long long i = lane; i < p.num_features; i += 32) orow[i] = __ldg(xrow + i);
-            }
-        }
+        if (p.x != nullptr) copy_x_row(p.x + (size_t)u * p.ld_x, orow, (int)p.num_features, lane, vec_x);
         float *frow = orow + p.col_offset;
         if (vec_f) {
             // groups of 4 columns never straddle a lane word or a rank (anchors_per_rank % 4 == 0)
@@ -172,7 +203,7 @@ __global__ void __launch_bounds__(256) concat_x_kernel(const float *__restrict__
 // 8 consecutive anchor columns = ONE BYTE of every mask array, so the 32 lanes read one 32-byte row
 // sector per array with a single coalesced byte load, bit-slice the hop index of their 8 columns and
 // store two float4.  x is streamed into columns [0, F) by the same warp.
-__global__ void __launch_bounds__(256) decode_features_bytes_kernel(GpDecodeParams p, int vec_x)
+__global__ void __launch_bounds__(256, 4) decode_features_bytes_kernel(GpDecodeParams p, int vec_x)
 {
     __shared__ float s_inv[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_inv[i] = inv_hops((u32)i);
@@ -187,18 +218,7 @@ __global__ void __launch_bounds__(256) decode_features_bytes_kernel(GpDecodePara
     const size_t plane_bytes = (size_t)p.plane_stride * 8;
     for (long long u = warp; u < p.n; u += nwarps) {
         float *orow = p.out + (size_t)u * p.ld_out;
-        if (p.x != nullptr) {
-            const float *xrow = p.x + (size_t)u * p.ld_x;
-            if (vec_x) {
-                const float4 *x4 = reinterpret_cast<const float4 *>(xrow);
-                float4 *o4 = reinterpret_cast<float4 *>(orow);
-                const int q = (int)(p.num_features >> 2);
-                for (int i = lane; i < q; i += 32) o4[i] = __ldg(x4 + i);
-                for (int i = (q << 2) + lane; i < (int)p.num_features; i += 32) orow[i] = __ldg(xrow + i);
-            } else {
-                for (int i = lane; i < (int)p.num_features; i += 32) orow[i] = __ldg(xrow + i);
-            }
-        }
+        if (p.x != nullptr) copy_x_row(p.x + (size_t)u * p.ld_x, orow, (int)p.num_features, lane, vec_x);
         for (int r = 0; r < p.num_ranks; ++r) {
             const unsigned char *blk = reinterpret_cast<const unsigned char *>(p.planes0 + (size_t)r * p.rank_stride);
             for (int b = 0; b < batches; ++b) {
@@ -240,8 +260,8 @@ __global__ void __launch_bounds__(256) decode_features_bytes_kernel(GpDecodePara
                     }
                 }
                 float4 *dst = reinterpret_cast<float4 *>(orow + p.col_offset + (size_t)r * kr + col0);
-                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                __stcs(dst, make_float4(v[0], v[1], v[2], v[3]));
+                __stcs(dst + 1, make_float4(v[4], v[5], v[6], v[7]));
             }
         }
     }
@@ -289,24 +309,13 @@ __global__ void __launch_bounds__(256) decode_features_peers_kernel(GpDecodePara
                         v[c] = ((reach >> c) & 1u) ? s_inv[d] : 0.0f;
                     }
                     float4 *dst = reinterpret_cast<float4 *>(orow + p.col_offset + (size_t)r * kr + col0);
-                    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-                    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    __stcs(dst, make_float4(v[0], v[1], v[2], v[3]));
+                    __stcs(dst + 1, make_float4(v[4], v[5], v[6], v[7]));
                 }
             }
         }
         // x is streamed into columns [0, F) while the peer loads are in flight
-        if (p.x != nullptr) {
-            const float *xrow = p.x + (size_t)u * p.ld_x;
-            if (vec_x) {
-                const float4 *x4 = reinterpret_cast<const float4 *>(xrow);
-                float4 *o4 = reinterpret_cast<float4 *>(orow);
-                const int q = (int)(p.num_features >> 2);
-                for (int i = lane; i < q; i += 32) o4[i] = __ldg(x4 + i);
-                for (int i = (q << 2) + lane; i < (int)p.num_features; i += 32) orow[i] = __ldg(xrow + i);
-            } else {
-                for (int i = lane; i < (int)p.num_features; i += 32) orow[i] = __ldg(xrow + i);
-            }
-        }
+        if (p.x != nullptr) copy_x_row(p.x + (size_t)u * p.ld_x, orow, (int)p.num_features, lane, vec_x);
     }
 }
 
@@ -388,8 +397,11 @@ int gp_launch_decode_features(const GpDecodeParams &p, cudaStream_t stream)
                       (p.anchors_per_rank % 4 == 0 || p.num_ranks == 1);
     if (vec_f && p.anchors_per_rank % 8 == 0 && p.anchors_per_rank > 0 && p.packed)
         GP_LAUNCH(decode_features_peers_kernel, grid_for(p.n, 8), 256, 0, stream, p, vec_x);
-    else if (vec_f && p.anchors_per_rank % 8 == 0 && p.anchors_per_rank > 0)
-        GP_LAUNCH(decode_features_bytes_kernel, grid_for(p.n, 8), 256, 0, stream, p, vec_x);
+    else if (vec_f && p.anchors_per_rank % 8 == 0 && p.anchors_per_rank > 0) {
+        // one resident wave: 4 CTAs per SM (launch bound), rows dealt round-robin to the warps
+        const int wave = gp_sm_count() * 4, want = grid_for(p.n, 8);
+        GP_LAUNCH(decode_features_bytes_kernel, want < wave ? want : wave, 256, 0, stream, p, vec_x);
+    }
     else
         GP_LAUNCH(decode_features_kernel, grid_for(p.n, 8), 256, 0, stream, p, k_total, vec_x, vec_f);
     GP_CUDA_CHECK(cudaGetLastError());
