@@ -330,7 +330,8 @@ int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t 
     // chain of small latency-bound kernels that leaves HBM idle.  GP_XCOPY_OVERLAP selects where the copy runs:
     //   0  inside the epilogue kernel (one pass over the [N, F+K] rows);
     //   1  one strided device-to-device transfer (copy engine) on a side stream, joined before the epilogue;
-    //   2  a copy kernel on a side stream beside the csr build, joined before the cooperative MS-BFS launch.
+    //   2  a copy kernel on a side stream beside the csr build, joined before the cooperative MS-BFS launch;
+    //   3  the same kernel, joined before the epilogue only.
     // The side stream is a parallel branch of the captured graph.
     static int overlap = -1;
     if (overlap < 0) {
@@ -356,9 +357,9 @@ int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t 
         GP_CUDA_CHECK(cudaEventRecord(sc.join, sc.stream));
     }
     int rc = gp_csr_build(csr, d_ei, e, s);
-    if (side_copy && overlap != 1) GP_CUDA_CHECK(cudaStreamWaitEvent(s, sc.join, 0));
+    if (side_copy && overlap == 2) GP_CUDA_CHECK(cudaStreamWaitEvent(s, sc.join, 0));
     if (rc == GP_OK) rc = gp_msbfs_run(bfs, d_anchors, k, s);
-    if (side_copy && overlap == 1) GP_CUDA_CHECK(cudaStreamWaitEvent(s, sc.join, 0));  // a capture must not end forked
+    if (side_copy && overlap != 2) GP_CUDA_CHECK(cudaStreamWaitEvent(s, sc.join, 0));  // a capture must not end forked
     GP_TRY(rc);
     if (d_out != nullptr) GP_TRY(gp_msbfs_features(bfs, side_copy ? nullptr : d_x, f, ldx, d_out, ldo, coff, s));
     else GP_TRY(gp_msbfs_pack(bfs, (int32_t)coff, nullptr, nullptr, nullptr, nullptr, nullptr, s));  // coff = slot

@@ -176,27 +176,48 @@ __global__ void __launch_bounds__(256) decode_features_kernel(GpDecodeParams p, 
     }
 }
 
-// concat_into_features' copy of x alone (utils.py:133-134): out[:, 0:F] = x, one warp per row.  Launched on a
-// side stream beside the latency-bound csr build kernels (gp_api.cu), which leave HBM idle.
+// concat_into_features' copy of x alone (utils.py:133-134): out[:, 0:F] = x, one warp per row, two rows in
+// flight per warp.  Launched on a side stream beside the latency-bound csr build kernels (gp_api.cu,
+// GP_XCOPY_OVERLAP=2), which leave HBM idle; it takes half of an SM's thread slots so those kernels fit beside it.
 __global__ void __launch_bounds__(256) concat_x_kernel(const float *__restrict__ x, long long n, int f, long long ld_x,
                                                        float *__restrict__ out, long long ld_out, int vec)
 {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long u = warp; u < n; u += nwarps) {
-        const float *xrow = x + (size_t)u * ld_x;
-        float *orow = out + (size_t)u * ld_out;
-        if (vec) {
-            const float4 *x4 = reinterpret_cast<const float4 *>(xrow);
-            float4 *o4 = reinterpret_cast<float4 *>(orow);
-            const int q = f >> 2;
-            for (int i = lane; i < q; i += 32) __stcs(o4 + i, __ldcs(x4 + i));
-            for (int i = (q << 2) + lane; i < f; i += 32) orow[i] = xrow[i];
-        } else {
-            for (int i = lane; i < f; i += 32) orow[i] = xrow[i];
+    const int q = f >> 2;
+    if (vec && q <= 128) {
+        for (long long u = warp; u < n; u += 2 * nwarps) {
+            const long long u2 = u + nwarps;
+            const float4 *xa = reinterpret_cast<const float4 *>(x + (size_t)u * ld_x);
+            const float4 *xb = reinterpret_cast<const float4 *>(x + (size_t)(u2 < n ? u2 : u) * ld_x);
+            float4 *oa = reinterpret_cast<float4 *>(out + (size_t)u * ld_out);
+            float4 *ob = reinterpret_cast<float4 *>(out + (size_t)(u2 < n ? u2 : u) * ld_out);
+            float4 va[4], vb[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = lane + 32 * t;
+                if (i < q) {
+                    va[t] = __ldcs(xa + i);
+                    vb[t] = __ldcs(xb + i);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = lane + 32 * t;
+                if (i < q) {
+                    __stcs(oa + i, va[t]);
+                    if (u2 < n) __stcs(ob + i, vb[t]);
+                }
+            }
+            for (int i = (q << 2) + lane; i < f; i += 32) {
+                out[(size_t)u * ld_out + i] = x[(size_t)u * ld_x + i];
+                if (u2 < n) out[(size_t)u2 * ld_out + i] = x[(size_t)u2 * ld_x + i];
+            }
         }
+        return;
     }
+    for (long long u = warp; u < n; u += nwarps) copy_x_row(x + (size_t)u * ld_x, out + (size_t)u * ld_out, f, lane, vec);
 }
 
 // Fast path (anchors_per_rank % 8 == 0, 16-byte aligned rows): one warp per output row; a lane owns
