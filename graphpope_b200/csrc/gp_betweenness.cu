@@ -29,7 +29,7 @@
 namespace {
 
 constexpr int BC_CHUNK = 64;    // edges per work item
-constexpr int BC_TILE = 4;      // items per ticket; their descriptors, row states and columns are fetched together
+constexpr int BC_TILE = 4;      // items per ticket (lane k of the warp holds the descriptor of item k)
 constexpr int BC_THREADS = 256;
 constexpr int BC_MINB = 3;
 constexpr int BC_UNROLL = 8;    // neighbour hop-count loads in flight per lane
@@ -89,11 +89,16 @@ __device__ __forceinline__ void st_state(void *p, u64 v)
     else *reinterpret_cast<unsigned long long *>(p) = v;
 }
 
-// One sweep over a work list.  FWD: settle level `lvl + 1` from level `lvl`.  !FWD: finalise level `lvl`
+// One sweep over a work list.  fwd: settle level `lvl + 1` from level `lvl`.  !fwd: finalise level `lvl`
 // from level `lvl + 1` (`maxl` = deepest level of the batch, whose rows have delta = 0).
 // A lane owns S sources: its S hop counts of a row are one word, its S sigma / coeff values one 8*S-byte run.
-template <typename DT, int S, bool FWD>
-__device__ __forceinline__ void bc_sweep(const BcParams &p, const BcList &L, int lvl, int maxl, u32 *ticket, u32 *flag)
+// ONE copy of this code serves both directions and every item of a tile (the direction is a uniform run-time
+// flag, the item loop is rolled with the next item's row state and columns prefetched): unrolled four items
+// deep and instantiated per direction it was 105 KB of SASS and the kernel stalled on instruction fetch
+// (ncu: stalled_no_instruction 8.7 per issue, the same as the first cdist kernel).
+template <typename DT, int S>
+__device__ __forceinline__ void bc_sweep(const BcParams &p, const BcList &L, bool fwd, int lvl, int maxl, u32 *ticket,
+                                         u32 *flag)
 {
     constexpr DT INF = (DT)~(DT)0;
     constexpr int BYTES = S * (int)sizeof(DT);
@@ -101,9 +106,10 @@ __device__ __forceinline__ void bc_sweep(const BcParams &p, const BcList &L, int
     constexpr int W = 32 * S;  // sources per batch
     const int lane = threadIdx.x & 31;
     char *dist = reinterpret_cast<char *>(p.dist);
-    const DT want = (DT)(FWD ? lvl : lvl + 1);   // hop count a contributing neighbour must have
-    const DT own = (DT)(FWD ? INF : (DT)lvl);     // hop count of the (row, source) pairs this sweep finalises
-    const bool leaf = !FWD && (lvl + 1 == maxl);  // neighbours at the deepest level: coeff = 1 / sigma
+    const DT want = (DT)(fwd ? lvl : lvl + 1);    // hop count a contributing neighbour must have
+    const DT own = fwd ? INF : (DT)lvl;           // hop count of the (row, source) pairs this sweep finalises
+    const bool leaf = !fwd && (lvl + 1 == maxl);  // neighbours at the deepest level: coeff = 1 / sigma
+    const double *nbr_val = (fwd || leaf) ? p.sigma : p.coeff;  // what is read per contributing neighbour
     bool found_any = false;
     const int tiles = (L.num_items + BC_TILE - 1) / BC_TILE;
     // first tile of a warp: its own index (no atomic); further tiles are drawn from the ticket counter, each
@@ -115,133 +121,145 @@ __device__ __forceinline__ void bc_sweep(const BcParams &p, const BcList &L, int
         if (t >= (u32)tiles) break;
         if (lane == 0) next = nwarps + atomicAdd(ticket, 1u);
         const int i0 = (int)t * BC_TILE;
+        const int nit = min(BC_TILE, L.num_items - i0);
         // round trip 1: the tile's descriptors (lane k holds item k); round trip 2: every item's row state and
-        // first 32 columns, issued together
+        // first 32 columns, issued together, so that items with nothing to do this sweep cost no round trip each
         int4 mine_it = make_int4(0, 0, 0, -1);
-        if (lane < BC_TILE && i0 + lane < L.num_items) mine_it = __ldg(L.items + i0 + lane);
-        u64 rowraw[BC_TILE];
-        int col0[BC_TILE];
+        if (lane < nit) mine_it = __ldg(L.items + i0 + lane);
+        u64 raw_t[BC_TILE];
+        int col_t[BC_TILE];
 #pragma unroll
         for (int k = 0; k < BC_TILE; ++k) {
-            const int row = __shfl_sync(FULL_MASK, mine_it.x, k), beg = __shfl_sync(FULL_MASK, mine_it.y, k);
-            const int cnt = __shfl_sync(FULL_MASK, mine_it.z, k) & 0xFF;
-            rowraw[k] = ld_state<BYTES>(dist + ((size_t)row * 32 + lane) * BYTES);
-            col0[k] = lane < cnt ? __ldg(L.col + beg + lane) : row;
+            const int r = __shfl_sync(FULL_MASK, mine_it.x, k), b = __shfl_sync(FULL_MASK, mine_it.y, k);
+            const int c = __shfl_sync(FULL_MASK, mine_it.z, k) & 0xFF;
+            raw_t[k] = ld_state<BYTES>(dist + ((size_t)r * 32 + lane) * BYTES);
+            col_t[k] = lane < c ? __ldg(L.col + b + lane) : r;
         }
-#pragma unroll
-        for (int k = 0; k < BC_TILE; ++k) {
-            if (i0 + k >= L.num_items) break;
+#pragma unroll 1
+        for (int k = 0; k < nit; ++k) {
             const int row = __shfl_sync(FULL_MASK, mine_it.x, k), beg = __shfl_sync(FULL_MASK, mine_it.y, k);
             const int z = __shfl_sync(FULL_MASK, mine_it.z, k), hub = __shfl_sync(FULL_MASK, mine_it.w, k);
-            const int cnt = z & 0xFF, chunk = z >> 8;
-            u32 mine = 0;  // bit s: source s of this lane is finalised by this sweep
+            u64 rowraw = raw_t[0];
+            int col0 = col_t[0];
 #pragma unroll
-            for (int s = 0; s < S; ++s) mine |= ((DT)(rowraw[k] >> (s * BITS)) == own ? 1u : 0u) << s;
-            if (!__any_sync(FULL_MASK, mine != 0)) continue;
-            const size_t rbase = ((size_t)row * 32 + lane) * S;
-            double sv[S], acc[S];
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-                acc[s] = 0.0;
-                sv[s] = (!FWD && ((mine >> s) & 1u)) ? __ldcg(p.sigma + rbase + s) : 0.0;
+            for (int q = 1; q < BC_TILE; ++q) {  // k is warp-uniform: a select chain, not a local-memory array
+                if (k == q) {
+                    rowraw = raw_t[q];
+                    col0 = col_t[q];
+                }
             }
-            for (int base = 0; base < cnt; base += 32) {
-                int c = col0[k];
-                if (base > 0) c = (base + lane < cnt) ? __ldg(L.col + beg + base + lane) : row;
-                const int m = min(32, cnt - base);
-                for (int j0 = 0; j0 < m; j0 += BC_UNROLL) {
-                    int v[BC_UNROLL];
-                    u64 dv[BC_UNROLL];
+            do {
+                const int cnt = z & 0xFF, chunk = z >> 8;
+                u32 mine = 0;  // bit s: source s of this lane is finalised by this sweep
 #pragma unroll
-                    for (int q = 0; q < BC_UNROLL; ++q) {
-                        // padding slots re-read the row itself, whose own hop counts never equal `want`
-                        v[q] = __shfl_sync(FULL_MASK, c, (j0 + q) & 31);
-                        if (j0 + q >= m) v[q] = row;
-                    }
+                for (int s = 0; s < S; ++s) mine |= ((DT)(rowraw >> (s * BITS)) == own ? 1u : 0u) << s;
+                if (!__any_sync(FULL_MASK, mine != 0)) break;
+                const size_t rbase = ((size_t)row * 32 + lane) * S;
+                double sv[S], acc[S];
 #pragma unroll
-                    for (int q = 0; q < BC_UNROLL; ++q) dv[q] = ld_state<BYTES>(dist + ((size_t)v[q] * 32 + lane) * BYTES);
+                for (int s = 0; s < S; ++s) {
+                    acc[s] = 0.0;
+                    sv[s] = (!fwd && ((mine >> s) & 1u)) ? __ldcg(p.sigma + rbase + s) : 1.0;
+                }
+                for (int base = 0; base < cnt; base += 32) {
+                    int c = col0;
+                    if (base > 0) c = (base + lane < cnt) ? __ldg(L.col + beg + base + lane) : row;
+                    const int m = min(32, cnt - base);
+                    for (int j0 = 0; j0 < m; j0 += BC_UNROLL) {
+                        int v[BC_UNROLL];
+                        u64 dv[BC_UNROLL];
 #pragma unroll
-                    for (int q = 0; q < BC_UNROLL; ++q) {
-                        const size_t vb = ((size_t)v[q] * 32 + lane) * S;
+                        for (int q = 0; q < BC_UNROLL; ++q) {
+                            // padding slots re-read the row itself, whose own hop counts never equal `want`
+                            v[q] = __shfl_sync(FULL_MASK, c, (j0 + q) & 31);
+                            if (j0 + q >= m) v[q] = row;
+                        }
 #pragma unroll
-                        for (int s = 0; s < S; ++s) {
-                            if (((mine >> s) & 1u) && (DT)(dv[q] >> (s * BITS)) == want) {
-                                if (FWD) {
-                                    acc[s] = __dadd_rn(acc[s], __ldcg(p.sigma + vb + s));
-                                } else {
-                                    const double cw = leaf ? __ddiv_rn(1.0, __ldcg(p.sigma + vb + s)) : __ldcg(p.coeff + vb + s);
-                                    acc[s] = __dadd_rn(acc[s], __dmul_rn(sv[s], cw));
+                        for (int q = 0; q < BC_UNROLL; ++q)
+                            dv[q] = ld_state<BYTES>(dist + ((size_t)v[q] * 32 + lane) * BYTES);
+#pragma unroll
+                        for (int q = 0; q < BC_UNROLL; ++q) {
+                            const size_t vb = ((size_t)v[q] * 32 + lane) * S;
+#pragma unroll
+                            for (int s = 0; s < S; ++s) {
+                                if (((mine >> s) & 1u) && (DT)(dv[q] >> (s * BITS)) == want) {
+                                    // forward: + sigma[v]; backward: + sigma[row] * coeff[v] (a leaf's coeff is
+                                    // 1 / sigma[v]); sv is 1.0 forward and x * 1.0 is exact
+                                    double cw = __ldcg(nbr_val + vb + s);
+                                    if (leaf) cw = __ddiv_rn(1.0, cw);
+                                    acc[s] = __dadd_rn(acc[s], fwd ? cw : __dmul_rn(sv[s], cw));
                                 }
                             }
                         }
                     }
                 }
-            }
-            if (hub >= 0) {
-                // chunk of a long row: park the partial sums; the warp that arrives last adds them in chunk order
-                const int chunks = __ldg(L.hub_chunks + hub), first = __ldg(L.hub_first + hub);
-                double *slot = p.partial + ((size_t)first + chunk) * W + (size_t)lane * S;
+                if (hub >= 0) {
+                    // chunk of a long row: park the partial sums; the warp that arrives last adds them in chunk order
+                    const int chunks = __ldg(L.hub_chunks + hub), first = __ldg(L.hub_first + hub);
+                    double *slot = p.partial + ((size_t)first + chunk) * W + (size_t)lane * S;
 #pragma unroll
-                for (int s = 0; s < S; ++s) slot[s] = acc[s];
-                __syncwarp();
-                u32 old = 0;
-                if (lane == 0) {
-                    __threadfence();  // the warp's partial sums before the arrival
-                    old = atomicAdd(p.arrive + hub, 1u);
+                    for (int s = 0; s < S; ++s) slot[s] = acc[s];
+                    __syncwarp();
+                    u32 old = 0;
+                    if (lane == 0) {
+                        __threadfence();  // the warp's partial sums before the arrival
+                        old = atomicAdd(p.arrive + hub, 1u);
+                    }
+                    old = __shfl_sync(FULL_MASK, old, 0);
+                    if (old != (u32)(chunks - 1)) break;
+                    __threadfence();
+                    if (lane == 0) p.arrive[hub] = 0;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) acc[s] = 0.0;
+                    const double *part = p.partial + (size_t)first * W + (size_t)lane * S;
+                    constexpr int PB = 16 / S;  // 16 loads in flight, added in chunk order
+                    for (int ch0 = 0; ch0 < chunks; ch0 += PB) {
+                        double pv[PB][S];
+#pragma unroll
+                        for (int q = 0; q < PB; ++q)
+#pragma unroll
+                            for (int s = 0; s < S; ++s)
+                                pv[q][s] = ch0 + q < chunks ? __ldcg(part + (size_t)(ch0 + q) * W + s) : 0.0;
+#pragma unroll
+                        for (int q = 0; q < PB; ++q)
+                            if (ch0 + q < chunks) {
+#pragma unroll
+                                for (int s = 0; s < S; ++s) acc[s] = __dadd_rn(acc[s], pv[q][s]);
+                            }
+                    }
                 }
-                old = __shfl_sync(FULL_MASK, old, 0);
-                if (old != (u32)(chunks - 1)) continue;
-                __threadfence();
-                if (lane == 0) p.arrive[hub] = 0;
+                if (fwd) {
+                    u64 raw = rowraw;
+                    bool changed = false;
 #pragma unroll
-                for (int s = 0; s < S; ++s) acc[s] = 0.0;
-                const double *part = p.partial + (size_t)first * W + (size_t)lane * S;
-                for (int ch0 = 0; ch0 < chunks; ch0 += 4) {  // 4 * S loads in flight, added in chunk order
-                    double pv[4][S];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-#pragma unroll
-                        for (int s = 0; s < S; ++s)
-                            pv[q][s] = ch0 + q < chunks ? __ldcg(part + (size_t)(ch0 + q) * W + s) : 0.0;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (ch0 + q < chunks) {
-#pragma unroll
-                            for (int s = 0; s < S; ++s) acc[s] = __dadd_rn(acc[s], pv[q][s]);
+                    for (int s = 0; s < S; ++s) {
+                        // sigma >= 1 for every settled node, so a non-zero sum means "has a parent at level lvl"
+                        if (((mine >> s) & 1u) && acc[s] != 0.0) {
+                            p.sigma[rbase + s] = acc[s];
+                            raw = (raw & ~((u64)INF << (s * BITS))) | ((u64)(DT)(lvl + 1) << (s * BITS));
+                            changed = true;
                         }
-                }
-            }
-            if (FWD) {
-                u64 raw = rowraw[k];
-                bool changed = false;
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    // sigma >= 1 for every settled node, so a non-zero sum means "has a parent at level lvl"
-                    if (((mine >> s) & 1u) && acc[s] != 0.0) {
-                        p.sigma[rbase + s] = acc[s];
-                        raw = (raw & ~((u64)INF << (s * BITS))) | ((u64)(DT)(lvl + 1) << (s * BITS));
-                        changed = true;
                     }
-                }
-                if (changed) {  // the lane owns the whole word: readers see the old or the new hop counts
-                    st_state<BYTES>(dist + ((size_t)row * 32 + lane) * BYTES, raw);
-                    found_any = true;
-                }
-            } else {
-                double mysum = 0.0;
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    if ((mine >> s) & 1u) {
-                        p.coeff[rbase + s] = __ddiv_rn(__dadd_rn(1.0, acc[s]), sv[s]);
-                        mysum = __dadd_rn(mysum, acc[s]);
+                    if (changed) {  // the lane owns the whole word: readers see the old or the new hop counts
+                        st_state<BYTES>(dist + ((size_t)row * 32 + lane) * BYTES, raw);
+                        found_any = true;
                     }
+                } else {
+                    double mysum = 0.0;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        if ((mine >> s) & 1u) {
+                            p.coeff[rbase + s] = __ddiv_rn(__dadd_rn(1.0, acc[s]), sv[s]);
+                            mysum = __dadd_rn(mysum, acc[s]);
+                        }
+                    }
+                    const double tot = warp_sum_f64(mysum);
+                    if (lane == 0) p.bc[row] = __dadd_rn(__ldcg(p.bc + row), tot);  // the row has one owner per sweep
                 }
-                const double tot = warp_sum_f64(mysum);
-                if (lane == 0) p.bc[row] = __dadd_rn(__ldcg(p.bc + row), tot);  // the row has one owner per sweep
-            }
+            } while (0);
         }
     }
-    if (FWD && __any_sync(FULL_MASK, found_any) && lane == 0) st_relaxed_u32(flag, 1u);
+    if (fwd && __any_sync(FULL_MASK, found_any) && lane == 0) st_relaxed_u32(flag, 1u);
 }
 
 template <typename DT, int S>
@@ -270,9 +288,13 @@ __global__ void __launch_bounds__(BC_THREADS, (S == 4 ? 2 : BC_MINB)) bc_kernel(
             st_state<BYTES>(dist + ((size_t)w * 32 + lane) * BYTES, raw);
         }
         grid_barrier(p.sync + BC_SYNC_BARRIER, target, gridDim.x);
-        int lvl = 0;
+        // forward sweeps lvl = 0, 1, ... until one settles nothing (maxl = deepest level), then backward sweeps
+        // lvl = maxl - 1 ... 1 (rows at maxl have delta = 0, the sources at level 0 are not scored)
+        bool fwd = true;
+        int lvl = 0, maxl = 0;
         for (;;) {
-            bc_sweep<DT, S, true>(p, p.fwd, lvl, 0, p.sync + BC_SYNC_TICKET + 32 * (pass % 3), p.sync + BC_SYNC_FLAG + 32 * (pass % 3));
+            bc_sweep<DT, S>(p, fwd ? p.fwd : p.bwd, fwd, lvl, maxl, p.sync + BC_SYNC_TICKET + 32 * (pass % 3),
+                            p.sync + BC_SYNC_FLAG + 32 * (pass % 3));
             if (blockIdx.x == 0 && threadIdx.x == 0) {
                 // counter / flag of the NEXT sweep: last touched two sweeps ago, i.e. before the previous barrier
                 p.sync[BC_SYNC_TICKET + 32 * ((pass + 1) % 3)] = 0;
@@ -281,27 +303,21 @@ __global__ void __launch_bounds__(BC_THREADS, (S == 4 ? 2 : BC_MINB)) bc_kernel(
             grid_barrier(p.sync + BC_SYNC_BARRIER, target, gridDim.x);
             const u32 found = ld_relaxed_u32(p.sync + BC_SYNC_FLAG + 32 * (pass % 3));
             ++pass;
-            if (!found) break;
-            ++lvl;
-            if (lvl + 1 >= (int)INF) {  // the next level could not be told from "not reached"
-                overflow = true;
-                break;
+            if (fwd) {
+                if (found) {
+                    ++lvl;
+                    if (lvl + 1 >= (int)INF) {  // the next level could not be told from "not reached"
+                        overflow = true;
+                        break;
+                    }
+                    continue;
+                }
+                maxl = lvl;  // levels 0..maxl exist
+                fwd = false;
             }
+            if (--lvl < 1) break;
         }
-        if (overflow) {
-            if (blockIdx.x == 0 && threadIdx.x == 0) p.sync[BC_SYNC_OVERFLOW] = 1;
-            break;
-        }
-        const int maxl = lvl;  // levels 0..maxl exist; rows at maxl have delta = 0 and contribute nothing
-        for (int l = maxl - 1; l >= 1; --l) {
-            bc_sweep<DT, S, false>(p, p.bwd, l, maxl, p.sync + BC_SYNC_TICKET + 32 * (pass % 3), nullptr);
-            if (blockIdx.x == 0 && threadIdx.x == 0) {
-                p.sync[BC_SYNC_TICKET + 32 * ((pass + 1) % 3)] = 0;
-                p.sync[BC_SYNC_FLAG + 32 * ((pass + 1) % 3)] = 0;
-            }
-            grid_barrier(p.sync + BC_SYNC_BARRIER, target, gridDim.x);
-            ++pass;
-        }
+        if (overflow && blockIdx.x == 0 && threadIdx.x == 0) p.sync[BC_SYNC_OVERFLOW] = 1;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) p.sync[BC_SYNC_SWEEPS] = pass;  // sweeps of this launch (diagnostics)
 }
@@ -325,9 +341,13 @@ void build_list(const std::vector<int> &first, const std::vector<int> &count, bo
 {
     const size_t n = count.size();
     out.items.reserve(n + n / 8);
+    // chunked (long) rows first: their chunks are spread over many warps and the row is finalised by whichever
+    // arrives last, so started late they would be the tail every other CTA waits for at the level barrier
+    for (int pass = 0; pass < 2; ++pass)
     for (size_t r = 0; r < n; ++r) {
         const int d = count[r];
         if (d == 0 && !keep_empty) continue;
+        if ((d > BC_CHUNK) != (pass == 0)) continue;
         if (d <= BC_CHUNK) {
             out.items.push_back(make_int4((int)r, first[r], d, -1));
             continue;
@@ -460,7 +480,7 @@ extern "C" int gp_betweenness(const gp_csr_t *csr_, double *d_score, gp_stream_t
 
     // sources per lane (1, 2 or 4 -> 32, 64 or 128 sources per batch): more sources per batch amortise the
     // per-level barrier and list scan; the work per source stays the same (the sweeps are bound by instruction
-    // issue), so the gain flattens: Flickr-shape 3.8 / 3.0 / 3.7 s for 1 / 2 / 4.  GP_BC_SOURCES overrides.
+    // issue), so the gain flattens: Flickr-shape 2.8 s for 1, 2 and 4.  GP_BC_SOURCES overrides.
     int spl = n >= 512 ? 2 : 1;
     if (const char *e = getenv("GP_BC_SOURCES")) {
         const int v = atoi(e);
