@@ -811,10 +811,26 @@ extern "C" int gp_csr_create(int64_t num_nodes, int64_t edge_capacity, uint32_t 
     return GP_OK;
 }
 
+int gp_csr_scratch(gp_csr *c, int slot, size_t bytes, void **out)
+{
+    GP_REQUIRE(c != nullptr && out != nullptr && slot >= 0 && slot < 16, GP_ERR_INVALID, "gp_csr_scratch: bad argument");
+    if (bytes == 0) bytes = 16;
+    if (c->scratch_bytes[slot] < bytes) {
+        if (c->scratch[slot]) cudaFree(c->scratch[slot]);
+        c->scratch[slot] = nullptr;
+        c->scratch_bytes[slot] = 0;
+        GP_CUDA_CHECK(cudaMalloc(&c->scratch[slot], bytes));
+        c->scratch_bytes[slot] = bytes;
+    }
+    *out = c->scratch[slot];
+    return GP_OK;
+}
+
 extern "C" int gp_csr_free(gp_csr_t *c)
 {
     if (!c) return GP_OK;
     gp_drop_graphs(c);
+    for (int i = 0; i < 16; ++i) cudaFree(c->scratch[i]);
     cudaFree(c->deg);
     cudaFree(c->row_start);
     cudaFree(c->cursor);

@@ -57,10 +57,16 @@ struct gp_csr {
     int *scan_status = nullptr; // look-back words of the chained scans + ticket counters in the last 8 words
     size_t scan_status_words = 0;
     size_t scan_b_offset = 0;   // first status word of the second scan of a build
+    // grow-only device scratch owned by the handle (gp_csr_scratch), freed by gp_csr_free: samplers that run for
+    // seconds (betweenness) keep their workspace here instead of paying cudaMalloc / cudaFree on every call
+    void *scratch[16] = {};
+    size_t scratch_bytes[16] = {};
     int bitmap_words = 0;       // ceil(N / 32) if the long-row sort may use a node bitmap in shared memory, else 0
     int big_smem_bytes = 0;     // dynamic shared memory of rowsort_big_kernel
 };
 
+// Device scratch slot `slot` of at least `bytes` bytes (contents undefined; re-allocated only when it must grow).
+int gp_csr_scratch(gp_csr *csr, int slot, size_t bytes, void **out);
 // Makes sure the in-edge CSR exists (transpose sort unless symmetric).  Async.
 int gp_csr_ensure_in(gp_csr *csr, cudaStream_t stream);
 // out[:, 0:F] = x as a stand-alone copy kernel (gp_epilogue.cu).  Async.
