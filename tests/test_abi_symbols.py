@@ -48,6 +48,11 @@ def test_no_compute_without_gpu_but_clean_errors():
             _lib.require_cuda()
         assert lib.gp_device_info(None, None, None, None, 0) == _lib.GP_ERR_NO_DEVICE
         assert b"no CUDA device" in lib.gp_last_error()
+    # argument checks come before any CUDA call
+    assert lib.gp_betweenness(None, None, None) == _lib.GP_ERR_INVALID
+    assert lib.gp_eigenvector(None, 1e-15, 10, None, None, None) == _lib.GP_ERR_INVALID
+    assert lib.gp_concat_x(None, 4, 4, 2, None, 8, None) == _lib.GP_ERR_INVALID  # ld_x < F
+    assert lib.gp_concat_x(None, 0, 4, 4, None, 8, None) == _lib.GP_OK            # nothing to copy
 
 
 def test_product_never_imports_the_oracle():

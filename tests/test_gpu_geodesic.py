@@ -342,3 +342,35 @@ def test_device_resident_output_equals_host_output(dev, monkeypatch):
     assert torch.equal(devout.cpu(), host)
     n_id = torch.tensor([5, 0, 2999, 17], device="cuda")
     assert torch.equal(devout[n_id].cpu(), host[n_id.cpu()])
+
+
+@pytest.mark.parametrize("n,f,pad", [(1, 1, 0), (37, 5, 3), (1000, 500, 256), (513, 129, 2)])
+def test_concat_x_matches_torch_slicing(dev, n, f, pad):
+    """gp_concat_x: the x half of concat_into_features (utils.py:133-134) as one strided device-to-device copy."""
+    from ctypes import c_void_p
+
+    from graphpope_b200 import _lib
+    lib = _lib.load()
+    x = torch.randn(n, f, device="cuda")
+    out = torch.full((n, f + pad), float("nan"), device="cuda")
+    _lib.check(lib.gp_concat_x(c_void_p(x.data_ptr()), n, f, f, c_void_p(out.data_ptr()), f + pad,
+                               c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert torch.equal(out[:, :f], x)
+    assert bool(torch.isnan(out[:, f:]).all())
+    assert lib.gp_concat_x(None, n, f, f, c_void_p(out.data_ptr()), f + pad, None) == _lib.GP_ERR_INVALID
+    assert lib.gp_concat_x(c_void_p(x.data_ptr()), n, f, f - 1, c_void_p(out.data_ptr()), f + pad, None) == \
+        _lib.GP_ERR_INVALID
+
+
+def test_wide_feature_rows_take_the_chunked_x_copy(dev):
+    """F > 512 floats: the epilogue's x-row copy runs more than one batch of loads per lane; odd F: scalar tail."""
+    from oracle import cbfs, geodesic
+    n, k = 300, 16
+    ei = synth.random_digraph(n, 900, seed=3)
+    anchors = np.random.default_rng(1).integers(0, n, k)
+    for f in (517, 1030, 2052):
+        x = np.random.default_rng(f).standard_normal((n, f)).astype(np.float32)
+        _, feats, _ = _gpu_hops_and_features(dev, ei, n, anchors, x)
+        want = geodesic.concat_features(x, cbfs.geodesic_features(ei, n, anchors))
+        assert np.array_equal(feats.view(np.uint32), want.view(np.uint32)), f
