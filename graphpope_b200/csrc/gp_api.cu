@@ -326,19 +326,17 @@ int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t 
                        int64_t k, const float *d_x, int64_t f, int64_t ldx, float *d_out, int64_t ldo,
                        int64_t coff, cudaStream_t s)
 {
-    // concat_into_features' copy of x (utils.py:133-134) does not depend on the traversal, and the csr build is a
-    // chain of small latency-bound kernels that leaves HBM idle.  GP_XCOPY_OVERLAP selects where the copy runs:
-    //   0  inside the epilogue kernel (one pass over the [N, F+K] rows);
-    //   1  one strided device-to-device transfer (copy engine) on a side stream, joined before the epilogue;
-    //   2  a copy kernel on a side stream beside the csr build, joined before the cooperative MS-BFS launch;
-    //   3  the same kernel, joined before the epilogue only.
-    // The side stream is a parallel branch of the captured graph.
+    // concat_into_features' copy of x (utils.py:133-134) does not depend on the traversal, and the csr build and
+    // the MS-BFS are latency-bound and leave HBM idle, so the copy could run beside them on a side stream (a
+    // parallel branch of the captured graph).  Measured on B200 it never paid (profiles/r01p_notes.md: copy
+    // engine 0.323 ms, copy kernels of three shapes 0.265-0.301 ms, against 0.246 ms with the copy fused into the
+    // epilogue), so the fused copy is the default; GP_XCOPY_OVERLAP=1 keeps the copy-engine variant selectable.
     static int overlap = -1;
     if (overlap < 0) {
         const char *ev = getenv("GP_XCOPY_OVERLAP");
         overlap = ev ? atoi(ev) : 0;
     }
-    const bool side_copy = overlap > 0 && d_out != nullptr && d_x != nullptr && f > 0 && csr->num_nodes > 0;
+    const bool side_copy = overlap == 1 && d_out != nullptr && d_x != nullptr && f > 0 && csr->num_nodes > 0;
     SideCopy &sc = side_copy_state();
     if (side_copy) {
         if (sc.stream == nullptr) {
@@ -348,18 +346,14 @@ int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t 
         }
         GP_CUDA_CHECK(cudaEventRecord(sc.fork, s));
         GP_CUDA_CHECK(cudaStreamWaitEvent(sc.stream, sc.fork, 0));
-        if (overlap == 1)
-            GP_CUDA_CHECK(cudaMemcpy2DAsync(d_out, (size_t)ldo * sizeof(float), d_x, (size_t)ldx * sizeof(float),
-                                            (size_t)f * sizeof(float), (size_t)csr->num_nodes,
-                                            cudaMemcpyDeviceToDevice, sc.stream));
-        else
-            GP_TRY(gp_launch_concat_x(d_x, csr->num_nodes, f, ldx, d_out, ldo, sc.stream));
+        GP_CUDA_CHECK(cudaMemcpy2DAsync(d_out, (size_t)ldo * sizeof(float), d_x, (size_t)ldx * sizeof(float),
+                                        (size_t)f * sizeof(float), (size_t)csr->num_nodes,
+                                        cudaMemcpyDeviceToDevice, sc.stream));
         GP_CUDA_CHECK(cudaEventRecord(sc.join, sc.stream));
     }
     int rc = gp_csr_build(csr, d_ei, e, s);
-    if (side_copy && overlap == 2) GP_CUDA_CHECK(cudaStreamWaitEvent(s, sc.join, 0));
     if (rc == GP_OK) rc = gp_msbfs_run(bfs, d_anchors, k, s);
-    if (side_copy && overlap != 2) GP_CUDA_CHECK(cudaStreamWaitEvent(s, sc.join, 0));  // a capture must not end forked
+    if (side_copy) GP_CUDA_CHECK(cudaStreamWaitEvent(s, sc.join, 0));  // always re-join: a capture must not end forked
     GP_TRY(rc);
     if (d_out != nullptr) GP_TRY(gp_msbfs_features(bfs, side_copy ? nullptr : d_x, f, ldx, d_out, ldo, coff, s));
     else GP_TRY(gp_msbfs_pack(bfs, (int32_t)coff, nullptr, nullptr, nullptr, nullptr, nullptr, s));  // coff = slot

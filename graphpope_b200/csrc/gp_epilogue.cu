@@ -176,50 +176,6 @@ __global__ void __launch_bounds__(256) decode_features_kernel(GpDecodeParams p, 
     }
 }
 
-// concat_into_features' copy of x alone (utils.py:133-134): out[:, 0:F] = x, one warp per row, two rows in
-// flight per warp.  Launched on a side stream beside the latency-bound csr build kernels (gp_api.cu,
-// GP_XCOPY_OVERLAP=2), which leave HBM idle; it takes half of an SM's thread slots so those kernels fit beside it.
-__global__ void __launch_bounds__(256) concat_x_kernel(const float *__restrict__ x, long long n, int f, long long ld_x,
-                                                       float *__restrict__ out, long long ld_out, int vec)
-{
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const int q = f >> 2;
-    if (vec && q <= 128) {
-        for (long long u = warp; u < n; u += 2 * nwarps) {
-            const long long u2 = u + nwarps;
-            const float4 *xa = reinterpret_cast<const float4 *>(x + (size_t)u * ld_x);
-            const float4 *xb = reinterpret_cast<const float4 *>(x + (size_t)(u2 < n ? u2 : u) * ld_x);
-            float4 *oa = reinterpret_cast<float4 *>(out + (size_t)u * ld_out);
-            float4 *ob = reinterpret_cast<float4 *>(out + (size_t)(u2 < n ? u2 : u) * ld_out);
-            float4 va[4], vb[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int i = lane + 32 * t;
-                if (i < q) {
-                    va[t] = __ldcs(xa + i);
-                    vb[t] = __ldcs(xb + i);
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int i = lane + 32 * t;
-                if (i < q) {
-                    __stcs(oa + i, va[t]);
-                    if (u2 < n) __stcs(ob + i, vb[t]);
-                }
-            }
-            for (int i = (q << 2) + lane; i < f; i += 32) {
-                out[(size_t)u * ld_out + i] = x[(size_t)u * ld_x + i];
-                if (u2 < n) out[(size_t)u2 * ld_out + i] = x[(size_t)u2 * ld_x + i];
-            }
-        }
-        return;
-    }
-    for (long long u = warp; u < n; u += nwarps) copy_x_row(x + (size_t)u * ld_x, out + (size_t)u * ld_out, f, lane, vec);
-}
-
 // Fast path (anchors_per_rank % 8 == 0, 16-byte aligned rows): one warp per output row; a lane owns
 // 8 consecutive anchor columns = ONE BYTE of every mask array, so the 32 lanes read one 32-byte row
 // sector per array with a single coalesced byte load, bit-slice the hop index of their 8 columns and
@@ -425,18 +381,6 @@ int gp_launch_decode_features(const GpDecodeParams &p, cudaStream_t stream)
     }
     else
         GP_LAUNCH(decode_features_kernel, grid_for(p.n, 8), 256, 0, stream, p, k_total, vec_x, vec_f);
-    GP_CUDA_CHECK(cudaGetLastError());
-    return GP_OK;
-}
-
-int gp_launch_concat_x(const float *d_x, long long n, long long f, long long ld_x, float *d_out, long long ld_out,
-                       cudaStream_t stream)
-{
-    if (n == 0 || f == 0) return GP_OK;
-    const int vec = aligned16(d_x) && aligned16(d_out) && (ld_x % 4 == 0) && (ld_out % 4 == 0);
-    long long blocks = (long long)gp_sm_count() * 4;  // half of an SM's thread slots: the csr kernels fit beside it
-    if (blocks > (n + 7) / 8) blocks = (n + 7) / 8;
-    GP_LAUNCH(concat_x_kernel, (unsigned)blocks, 256, 0, stream, d_x, n, (int)f, ld_x, d_out, ld_out, vec);
     GP_CUDA_CHECK(cudaGetLastError());
     return GP_OK;
 }

@@ -69,6 +69,3 @@ struct gp_csr {
 int gp_csr_scratch(gp_csr *csr, int slot, size_t bytes, void **out);
 // Makes sure the in-edge CSR exists (transpose sort unless symmetric).  Async.
 int gp_csr_ensure_in(gp_csr *csr, cudaStream_t stream);
-// out[:, 0:F] = x as a stand-alone copy kernel (gp_epilogue.cu).  Async.
-int gp_launch_concat_x(const float *d_x, long long n, long long f, long long ld_x, float *d_out, long long ld_out,
-                       cudaStream_t stream);

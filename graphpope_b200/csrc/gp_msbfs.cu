@@ -612,7 +612,8 @@ int launch_bfs_cfg(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int cfg
 {
     const size_t want_map = (size_t)p.map_stride * sizeof(u32);
     const bool fits = bfs_cache_bytes<WB, NT, MINB>() + want_map <= 200 * 1024 / (size_t)MINB;
-    if (!fits && cfg_id == GP_BFS_DEFAULT_CFG && getenv("GP_BFS_NO_MAP") == nullptr)
+    static const bool force_global = getenv("GP_BFS_MAPG") != nullptr;  // experiment: never stage the maps
+    if ((!fits || force_global) && cfg_id == GP_BFS_DEFAULT_CFG && getenv("GP_BFS_NO_MAP") == nullptr)
         return launch_bfs_variant<WB, NT, MINB, true>(h, p, stream, cfg_id);
     return launch_bfs_variant<WB, NT, MINB, false>(h, p, stream, cfg_id);
 }

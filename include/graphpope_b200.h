@@ -145,7 +145,8 @@ int gp_geodesic_run(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_edge_index,
  * device-to-device transfer, for callers that already hold x in place or want the copy on their own stream;
  * follow with gp_msbfs_features / gp_decode_peers called with d_x == NULL.  gp_geodesic_run keeps the copy
  * inside the epilogue kernel by default: running it beside the csr build and the MS-BFS measured slower on
- * B200 (GP_XCOPY_OVERLAP=1 copy engine 0.323 ms, =2 copy kernel 0.276 ms, against 0.265 ms per step).      */
+ * B200 (copy engine 0.323 ms, copy kernels 0.265-0.301 ms, against 0.246 ms per step; GP_XCOPY_OVERLAP=1
+ * selects the copy-engine variant).                                                                    */
 int gp_concat_x(const float *d_x, int64_t num_nodes, int64_t num_features, int64_t ld_x, float *d_out,
                 int64_t ld_out, gp_stream_t stream);
 
