@@ -261,14 +261,20 @@ def main():
     barrier()
     for i in range(args.steps):
         flush_l2(i)  # untimed: evict the previous step's lines from the 126 MB L2
-        if world > 1:
-            dist.barrier()
+        # no per-step barrier: a NCCL barrier blocks the HOST, so every step would start on an empty queue and
+        # the timed region would include the launch latency of its five host calls (0.365 -> 0.29 ms at N=2);
+        # the ranks stay in lockstep through the step's own all-reduce, and the K steps as a whole are bracketed
+        # by barrier + synchronize on both sides
         starts[i].record()
         step()
         stops[i].record()
         bfs_ms.append(engine.bfs.kernel_ms())
     barrier()
     launches = dev.launch_count() - launches0
+    if peer is not None and peer.trace_events and rank == 0:
+        peer.trace_events = peer.trace_events[-args.steps:]
+        print("peer step phases (median ms): csr+bfs+pack %.4f, flag all-reduce %.4f, peer decode %.4f"
+              % tuple(peer.trace_summary()), file=sys.stderr, flush=True)
     if world > 1 and int(deep_flags[-1].item()) != 0:
         raise RuntimeError("a shard had hops > 15: the packed exchange is invalid for this graph; use "
                            "distributed.sharded_geodesic_features (all-gather path)")

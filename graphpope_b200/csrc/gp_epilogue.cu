@@ -246,8 +246,14 @@ __global__ void __launch_bounds__(256, 4) decode_features_bytes_kernel(GpDecodeP
 
 // Peer assembly (packed exchange format, gp_decode_peers): same row / lane mapping as the kernel above,
 // but the five bytes of EVERY rank's shard are requested up front, so the NVLink round trips of all
-// peers overlap (one dependent round trip per row instead of two per peer).
-__global__ void __launch_bounds__(256) decode_features_peers_kernel(GpDecodeParams p, int vec_x)
+// peers overlap (one dependent round trip per row instead of two per peer).  Per row a warp is bound by
+// that round trip (~3 us over NVLink), so what matters is rows in flight: the kernel is instantiated for
+// 2, 4 and 8 ranks (the mask registers of absent ranks cost occupancy: 114 registers and 2 CTAs per SM
+// for everyone made the 2-GPU epilogue run at half the HBM rate), and the first 2 KB of the x row are
+// requested together with the masks instead of after the columns have been stored.
+template <int R>
+__global__ void __launch_bounds__(256, R <= 2 ? 3 : 2)
+decode_features_peers_kernel(GpDecodeParams p, int vec_x)
 {
     __shared__ float s_inv[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_inv[i] = inv_hops((u32)i);
@@ -259,23 +265,42 @@ __global__ void __launch_bounds__(256) decode_features_peers_kernel(GpDecodePara
     const int kr = (int)p.anchors_per_rank;
     const int batches = (kr + 64 * p.wb - 1) / (64 * p.wb);
     const size_t plane_bytes = (size_t)p.plane_stride * 8;
+    const int f = (int)p.num_features, q = f >> 2;
+    const bool fast_x = p.x != nullptr && vec_x;
     for (long long u = warp; u < p.n; u += nwarps) {
         float *orow = p.out + (size_t)u * p.ld_out;
+        const float *xrow = p.x != nullptr ? p.x + (size_t)u * p.ld_x : nullptr;
+        float4 xv[4];
+        if (fast_x) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = lane + 32 * t;
+                if (i < q) xv[t] = __ldcs(reinterpret_cast<const float4 *>(xrow) + i);
+            }
+        }
         for (int b = 0; b < batches; ++b) {
             const int col0 = b * 64 * p.wb + lane * 8;  // first of this lane's 8 columns inside the rank
-            if (lane >= row_bytes || col0 >= kr) continue;
+            const bool act = lane < row_bytes && col0 < kr;
             const size_t roff = ((size_t)b * p.n + (size_t)u) * row_bytes + lane;
-            u32 m[GP_MAX_RANKS][GP_PACKED_ARRAYS];
+            u32 m[R][GP_PACKED_ARRAYS];
 #pragma unroll
-            for (int r = 0; r < GP_MAX_RANKS; ++r) {
-                if (r < p.num_ranks) {
+            for (int r = 0; r < R; ++r) {
+                if (act && r < p.num_ranks) {
                     const unsigned char *rowp = reinterpret_cast<const unsigned char *>(p.rank_ptr[r]) + roff;
 #pragma unroll
                     for (int a = 0; a < GP_PACKED_ARRAYS; ++a) m[r][a] = rowp[(size_t)a * plane_bytes];
                 }
             }
+            if (b == 0 && fast_x) {  // the x row goes out while the peer bytes are still in flight
 #pragma unroll
-            for (int r = 0; r < GP_MAX_RANKS; ++r) {
+                for (int t = 0; t < 4; ++t) {
+                    const int i = lane + 32 * t;
+                    if (i < q) __stcs(reinterpret_cast<float4 *>(orow) + i, xv[t]);
+                }
+            }
+            if (!act) continue;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
                 if (r < p.num_ranks) {
                     const u32 reach = m[r][0];
                     float v[8];
@@ -291,8 +316,14 @@ __global__ void __launch_bounds__(256) decode_features_peers_kernel(GpDecodePara
                 }
             }
         }
-        // x is streamed into columns [0, F) while the peer loads are in flight
-        if (p.x != nullptr) copy_x_row(p.x + (size_t)u * p.ld_x, orow, (int)p.num_features, lane, vec_x);
+        // the rest of x: rows longer than 128 float4, the scalar tail, or unaligned rows
+        if (fast_x) {
+            if (q > 128) copy_x_row(xrow + 512, orow + 512, f - 512, lane, 1);
+            else
+                for (int i = (q << 2) + lane; i < f; i += 32) orow[i] = __ldcs(xrow + i);
+        } else if (xrow != nullptr) {
+            copy_x_row(xrow, orow, f, lane, 0);
+        }
     }
 }
 
@@ -373,7 +404,11 @@ int gp_launch_decode_features(const GpDecodeParams &p, cudaStream_t stream)
     const int vec_f = aligned16(p.out) && (p.ld_out % 4 == 0) && (p.col_offset % 4 == 0) &&
                       (p.anchors_per_rank % 4 == 0 || p.num_ranks == 1);
     if (vec_f && p.anchors_per_rank % 8 == 0 && p.anchors_per_rank > 0 && p.packed)
-        GP_LAUNCH(decode_features_peers_kernel, grid_for(p.n, 8), 256, 0, stream, p, vec_x);
+    {
+        if (p.num_ranks <= 2) GP_LAUNCH(decode_features_peers_kernel<2>, grid_for(p.n, 8), 256, 0, stream, p, vec_x);
+        else if (p.num_ranks <= 4) GP_LAUNCH(decode_features_peers_kernel<4>, grid_for(p.n, 8), 256, 0, stream, p, vec_x);
+        else GP_LAUNCH(decode_features_peers_kernel<8>, grid_for(p.n, 8), 256, 0, stream, p, vec_x);
+    }
     else if (vec_f && p.anchors_per_rank % 8 == 0 && p.anchors_per_rank > 0) {
         // one resident wave: 4 CTAs per SM (launch bound), rows dealt round-robin to the warps
         const int wave = gp_sm_count() * 4, want = grid_for(p.n, 8);

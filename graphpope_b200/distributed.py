@@ -187,6 +187,7 @@ class PeerAssembly:
             self.base.append(ptr.value)
             self._opened.append(ptr.value)
         self.step = 0
+        self.trace_events = []
         self._side = None
         self.flag = torch.zeros(1, dtype=torch.int32, device="cuda")
 
@@ -230,8 +231,14 @@ class PeerAssembly:
                                        out.stride(0) if n > 1 else f + k, c_void_p(side.cuda_stream)))
             x.record_stream(side)
             out.record_stream(side)
+        trace = os.environ.get("GP_PEER_TRACE") is not None  # diagnostics: device time of the three phases
+        if trace:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
         check(self.lib.gp_geodesic_run_packed(eng.csr._h, eng.bfs._h, _ptr(edge_index), edge_index.size(1),
                                               _ptr(self._shard), hi - lo, slot, _stream()))
+        if trace:
+            ev[1].record()
         packed, stride = ctypes.c_void_p(), ctypes.c_int64()
         batches, wb, deep = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_void_p()
         check(self.lib.gp_msbfs_packed_info(eng.bfs._h, slot, ctypes.byref(packed), ctypes.byref(stride),
@@ -240,6 +247,8 @@ class PeerAssembly:
         # every rank's pack and every rank's decode
         self.flag.copy_(_wrap_device_words_i32(deep.value), non_blocking=True)
         dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.group)
+        if trace:
+            ev[2].record()
         ptrs = (ctypes.c_void_p * self.world)()
         for r in range(self.world):
             base = packed.value - slot * self.slot_stride_words * 8 if r == self.rank else self.base[r]
@@ -250,7 +259,17 @@ class PeerAssembly:
         check(self.lib.gp_decode_peers(ptrs, self.world, n, hi - lo, batches.value, wb.value, stride.value, _ptr(x), f,
                                        x.stride(0) if x is not None and n > 1 else f, _ptr(out),
                                        out.stride(0) if n > 1 else f + k, f, _stream()))
+        if trace:
+            ev[3].record()
+            self.trace_events.append(ev)
         return out, self.flag
+
+    def trace_summary(self):
+        """Median device milliseconds of (csr + bfs + pack, flag all-reduce, peer decode) over the traced steps."""
+        import statistics
+        torch.cuda.synchronize()
+        cols = [[e[i].elapsed_time(e[i + 1]) for e in self.trace_events] for i in range(3)]
+        return [statistics.median(c) for c in cols] if self.trace_events else None
 
 
 def _wrap_device_words_i32(ptr: int) -> torch.Tensor:
