@@ -374,3 +374,42 @@ def test_wide_feature_rows_take_the_chunked_x_copy(dev):
         _, feats, _ = _gpu_hops_and_features(dev, ei, n, anchors, x)
         want = geodesic.concat_features(x, cbfs.geodesic_features(ei, n, anchors))
         assert np.array_equal(feats.view(np.uint32), want.view(np.uint32)), f
+
+
+@pytest.mark.parametrize("k,f", [(64, 20), (256, 500), (24, 7)])
+def test_peer_decode_variants_on_one_gpu(dev, k, f):
+    """gp_msbfs_pack + gp_decode_peers (the multi-GPU epilogue) with the SAME local shard passed as 1..8 ranks:
+    every rank's column block must equal the single-GPU feature block and x must land in columns [0, F).
+    Covers the 2-, 4- and 8-rank instantiations of the peer kernel without needing peers."""
+    import ctypes
+    from ctypes import c_void_p
+
+    from graphpope_b200 import _lib
+    lib = _lib.load()
+    n = 3000
+    ei = synth.chung_lu_symmetric(n, 18000, 2.2, seed=5)
+    ei = np.concatenate([ei, synth.random_digraph(n, 700, seed=6)], axis=1)
+    anchors = np.random.default_rng(2).integers(0, n, k)
+    eng = dev.GeodesicEngine(n, ei.shape[1], k)
+    ei_d = torch.as_tensor(ei).cuda()
+    a_d = torch.as_tensor(anchors).cuda()
+    x = torch.randn(n, f, device="cuda")
+    want = eng.run(ei_d, a_d, x).clone()  # [n, f + k]
+    stream = c_void_p(torch.cuda.current_stream().cuda_stream)
+    packed, stride = c_void_p(), ctypes.c_int64()
+    batches, wb, deep = ctypes.c_int32(), ctypes.c_int32(), c_void_p()
+    _lib.check(lib.gp_msbfs_pack(eng.bfs._h, 0, ctypes.byref(packed), ctypes.byref(stride), ctypes.byref(batches),
+                                 ctypes.byref(wb), ctypes.byref(deep), stream))
+    for ranks in (1, 2, 3, 4, 5, 8):
+        ptrs = (c_void_p * ranks)(*([packed.value] * ranks))
+        out = torch.full((n, f + k * ranks), float("nan"), device="cuda")
+        rc = lib.gp_decode_peers(ptrs, ranks, n, k, batches.value, wb.value, stride.value, c_void_p(x.data_ptr()), f, f,
+                                 c_void_p(out.data_ptr()), f + k * ranks, f, stream)
+        if k % 8 or (f + k * ranks) % 4 or f % 4:
+            assert rc == _lib.GP_ERR_INVALID  # the packed path needs 8-column lanes and 16-byte aligned rows
+            continue
+        _lib.check(rc)
+        torch.cuda.synchronize()
+        assert torch.equal(out[:, :f], x), ranks
+        for r in range(ranks):
+            assert torch.equal(out[:, f + r * k: f + (r + 1) * k], want[:, f:]), (ranks, r)
