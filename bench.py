@@ -261,10 +261,10 @@ def main():
     barrier()
     for i in range(args.steps):
         flush_l2(i)  # untimed: evict the previous step's lines from the 126 MB L2
-        # no per-step barrier: a NCCL barrier blocks the HOST, so every step would start on an empty queue and
-        # the timed region would include the launch latency of its five host calls (0.365 -> 0.29 ms at N=2);
-        # the ranks stay in lockstep through the step's own all-reduce, and the K steps as a whole are bracketed
-        # by barrier + synchronize on both sides
+        # untimed alignment: without it the ranks drift apart during the flush and the wait for the slowest
+        # one inside the step's all-reduce lands in the timed region of the others (N=4: 0.439 -> 0.465 ms)
+        if world > 1:
+            dist.barrier()
         starts[i].record()
         step()
         stops[i].record()
