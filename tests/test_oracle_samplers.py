@@ -91,3 +91,40 @@ def test_eigenvector_matches_reference(golden_eigenvector):
         assert s.stable_top_k(x, k) == g[f"anchors/{k}"].tolist()
     with pytest.raises(ValueError):  # networkx >= 3.2 raises AmbiguousSolution on a disconnected graph
         s.eigenvector_scores(np.array([[0, 1], [1, 0]]), 3)
+
+
+def _random_small_digraph(seed, n, m):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, n, size=(2, m)).astype(np.int64)
+
+
+def test_betweenness_restatements_against_networkx_on_random_multigraphs():
+    """Self-loops, parallel edges, isolated nodes, unreachable pairs: the queue-order restatement is bit-equal to
+    networkx, the level-synchronous order (what the device kernel sums) within a few ulp with the same zeros."""
+    import networkx as nx
+    for seed in range(12):
+        n = 5 + 3 * seed
+        ei = _random_small_digraph(seed, n, 2 * n + seed)
+        G = nx.DiGraph()
+        G.add_nodes_from(range(n))
+        G.add_edges_from(zip(ei[0].tolist(), ei[1].tolist()))
+        want = nx.betweenness_centrality(G)
+        want = np.asarray([want[i] for i in range(n)])
+        assert np.array_equal(s.betweenness_scores(ei, n), want), seed
+        lv = s.betweenness_levelsync_scores(ei, n)
+        assert np.array_equal(lv == 0, want == 0), seed
+        assert np.allclose(lv, want, rtol=1e-13, atol=0), seed
+
+
+def test_eigenvector_restatement_against_networkx_on_strongly_connected_graphs():
+    import networkx as nx
+    for seed in range(6):
+        n = 12 + 5 * seed
+        ring = np.stack([np.arange(n), (np.arange(n) + 1) % n])  # a directed cycle keeps it strongly connected
+        ei = np.concatenate([ring, _random_small_digraph(100 + seed, n, 3 * n)], axis=1)
+        G = nx.DiGraph()
+        G.add_nodes_from(range(n))
+        G.add_edges_from(zip(ei[0].tolist(), ei[1].tolist()))
+        want = nx.eigenvector_centrality_numpy(G)
+        want = np.asarray([want[i] for i in range(n)])
+        assert np.allclose(s.eigenvector_scores(ei, n), want, rtol=0, atol=1e-12), seed
