@@ -97,7 +97,9 @@ def _store_block(path, block):
     torch.save(block.detach().cpu().contiguous(), tmp)
     os.replace(tmp, path)  # atomic: DDP ranks may race to write the same key
 
-_HOST_CENTRALITIES = ("betweenness_centrality", "eigenvector_centrality", "clustering_coefficient")  # clustering: large graphs only
+# reached only through GRAPHPOPE_BETWEENNESS=networkx / GRAPHPOPE_EIGENVECTOR=networkx, or (clustering) for graphs whose
+# node bitmaps do not fit in shared memory: the reference's own networkx call
+_HOST_CENTRALITIES = ("betweenness_centrality", "eigenvector_centrality", "clustering_coefficient")
 
 last_stats: dict = {}  # stats of the most recent MS-BFS (levels, edges examined, ...)
 

@@ -257,7 +257,8 @@ int gp_clustering(const gp_csr_t *csr, double *d_score, gp_stream_t stream);
  * endpoints, on the DiGraph): 32 sources per batch, one warp lane per source, level-synchronous pull sweeps in
  * one persistent kernel (gp_betweenness.cu).  Path counts are exact; the float64 dependency sums have a fixed
  * order that differs from networkx's queue order, so scores agree to a few ulp, not bit for bit.  syncs.
- * d_score float64[N].                                                                                  */
+ * d_score float64[N].  The workspace (~1.1 KB per node) lives in the csr handle and is reused by later calls:
+ * one gp_betweenness call at a time per handle.                                                        */
 int gp_betweenness(const gp_csr_t *csr, double *d_score, gp_stream_t stream);
 /* eigenvector_centrality (utils.py:44-48 -> nx.eigenvector_centrality_numpy: eigenvector of A^T for the
  * largest real eigenvalue, unit L2 norm, positive): float64 power iteration on (A^T + I) until the L1 change
