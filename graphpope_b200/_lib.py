@@ -131,7 +131,9 @@ def load():
     return _lib
 
 
-def check(status: int):
+def check(status: int, iterations: int | None = None):
+    """Raise the Python exception the reference would have raised for ``status``.  ``iterations`` is the
+    iteration budget of a power-iteration call (reported by PowerIterationFailedConvergence)."""
     if status == GP_OK:
         return
     msg = (load().gp_last_error() or b"").decode("utf-8", "replace")
@@ -144,7 +146,7 @@ def check(status: int):
     if status == GP_ERR_NOT_CONVERGED:
         try:
             import networkx as nx
-            raise nx.PowerIterationFailedConvergence(100)  # what utils.py:28 raises
+            raise nx.PowerIterationFailedConvergence(100 if iterations is None else int(iterations))  # utils.py:28
         except ImportError:
             pass
     raise GraphpopeError(status, msg)

@@ -84,7 +84,7 @@ class DeviceCsr:
         """networkx ``pagerank_scipy`` defaults (utils.py:26-30).  Returns (x float64[N], iterations)."""
         x = torch.empty(self.num_nodes, dtype=torch.float64, device="cuda")
         it = c_int32()
-        check(self._lib.gp_pagerank(self._h, alpha, tol, max_iter, _ptr(x), byref(it), _stream()))
+        check(self._lib.gp_pagerank(self._h, alpha, tol, max_iter, _ptr(x), byref(it), _stream()), iterations=max_iter)
         return x, it.value
 
     def closeness(self) -> torch.Tensor:
@@ -111,7 +111,7 @@ class DeviceCsr:
         (float64[N] unit-norm positive vector, iterations).  Agrees with ARPACK to rounding, not bit for bit."""
         x = torch.empty(self.num_nodes, dtype=torch.float64, device="cuda")
         it = c_int32(0)
-        check(self._lib.gp_eigenvector(self._h, tol, max_iter, _ptr(x), byref(it), _stream()))
+        check(self._lib.gp_eigenvector(self._h, tol, max_iter, _ptr(x), byref(it), _stream()), iterations=max_iter)
         return x, it.value
 
     def close(self):

@@ -22,11 +22,30 @@ import torch.distributed as dist
 
 
 def shard_bounds(num_anchors: int, world_size: int, rank: int) -> tuple[int, int]:
-    """Contiguous, equal anchor shards; K must divide evenly so every shard has the same lane layout."""
-    if num_anchors % world_size:
-        raise ValueError(f"num_anchor_nodes={num_anchors} must be divisible by the world size {world_size}")
-    per = num_anchors // world_size
-    return rank * per, (rank + 1) * per
+    """Contiguous anchor shards of ``ceil(K / G)`` columns; when G does not divide K the last ranks hold fewer
+    (possibly zero) anchors.  The reference accepts any K (utils.py:24, main.py:37: the default is 2)."""
+    per = -(-int(num_anchors) // int(world_size))
+    return min(num_anchors, rank * per), min(num_anchors, (rank + 1) * per)
+
+
+def pad_anchors(anchors, world_size: int, multiple: int = 8):
+    """The device exchange needs every rank to own the same number of lanes, a multiple of ``multiple`` (a decode
+    lane owns 8 columns).  Returns ``(padded anchors, anchors per rank)``: K is padded up to ``G * per`` by repeating
+    the last anchor — duplicate anchors are legal (sampling is with replacement, utils.py:24) and the padded columns
+    are dropped by the caller."""
+    k = len(anchors)
+    per = -(-max(k, 1) // world_size)
+    per = -(-per // multiple) * multiple
+    pad = world_size * per - k
+    if pad == 0:
+        return anchors, per
+    if torch.is_tensor(anchors):
+        fill = anchors[-1:].expand(pad) if k else torch.zeros(pad, dtype=anchors.dtype, device=anchors.device)
+        return torch.cat([anchors, fill]), per
+    import numpy as np
+
+    a = np.asarray(anchors, dtype=np.int64)
+    return np.concatenate([a, np.full(pad, a[-1] if k else 0, dtype=np.int64)]), per
 
 
 def agree_num_planes(local_num_planes: int, group=None, device="cpu") -> int:

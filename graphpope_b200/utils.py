@@ -83,8 +83,13 @@ def _cached_block(data):
     key = block_cache_key(_edge_index_of(data), data.num_nodes, data.anchor_nodes, SYMMETRIZE)
     path = osp.join(d, key + ".pt")
     if osp.exists(path):
-        blk = torch.load(path, map_location="cpu")
-        if tuple(blk.shape) == (int(data.num_nodes), len(data.anchor_nodes)) and blk.dtype == torch.float32:
+        try:
+            # weights_only: the cache directory may be shared between users / DDP ranks; never unpickle code
+            blk = torch.load(path, map_location="cpu", weights_only=True)
+        except Exception:
+            return None, path  # unreadable or foreign file: a cache miss, recomputed and overwritten
+        if (torch.is_tensor(blk) and tuple(blk.shape) == (int(data.num_nodes), len(data.anchor_nodes))
+                and blk.dtype == torch.float32):
             return blk, path
     return None, path
 
@@ -176,15 +181,22 @@ def sample_anchor_nodes(data, num_anchor_nodes, sampling_method):
         if n == 0:
             raise nx.NetworkXPointlessConcept("cannot compute centrality for the null graph")
         ei = _edge_index_of(data)
-        # eigenvector_centrality_numpy refuses graphs that are not strongly connected (networkx >= 3.2):
-        # node 0 must reach, and be reached by, every node — two single-anchor sweeps of the MS-BFS
+        # The power iteration has a unique limit only on a strongly connected graph: node 0 must reach, and be
+        # reached by, every node — two single-anchor sweeps of the MS-BFS.  Anything else is handed to the
+        # reference's own networkx call below, which decides for the installed networkx (>= 3.2 raises
+        # AmbiguousSolution, older versions return ARPACK's vector for such graphs).
+        connected = True
         for e in (ei, ei.flip(0)):
             _, hops, _ = _dev.geodesic_embed_host(e.contiguous(), n, [0], None, False, want_hops=True)
             if bool((hops.numpy() == _lib.GP_UNREACHABLE_U16).any()):
-                raise nx.AmbiguousSolution(
-                    "`eigenvector_centrality_numpy` does not give consistent results for disconnected graphs")
-        score, _ = _device_csr(data).eigenvector()
-        return _dev.topk_stable(score, num_anchor_nodes).cpu().tolist()
+                connected = False
+                break
+        if connected:
+            try:
+                score, _ = _device_csr(data).eigenvector()
+                return _dev.topk_stable(score, num_anchor_nodes).cpu().tolist()
+            except nx.PowerIterationFailedConvergence:
+                pass  # tiny spectral gap (e.g. long paths): ARPACK below does not depend on it
 
     if sampling_method in _HOST_CENTRALITIES:
         # Not re-implemented (north_star): the reference's own networkx call, same top-k rule.
@@ -214,22 +226,32 @@ def _graph_to_edge_index(G):
     return torch.from_numpy(np.ascontiguousarray(edges.T)), n
 
 
-def shortest_path_length(G, anchor_nodes, partition_length):
-    """utils.py:64-81: ``{node: [1/len(path) per anchor]}`` with ``0`` where there is no path.
-
-    ``G`` is the networkx graph ``to_networkx`` built; distances come from one device MS-BFS.
-    Values are Python floats ``1/(d+1)`` and the int ``0``, exactly as the reference appends them.
-    """
+def _hops_of_graph(G, anchor_nodes):
+    """uint16 hop matrix [N, K] of a networkx graph (nodes 0..N-1) from one device MS-BFS."""
     ei, n = _graph_to_edge_index(G)
     anchors = [int(a) for a in anchor_nodes]
     _, hops, stats = _dev.geodesic_embed_host(ei, n, anchors, None, False, want_hops=True)
     last_stats.update(stats)
-    h = hops.numpy()
+    return hops.numpy()
+
+
+def _rows_as_reference_lists(h, nodes):
+    """utils.py:69-78: per node a list of Python floats ``1/len(path)`` = ``1/(hops+1)`` and the *int* ``0``
+    where there is no path (utils.py:76 appends a literal 0)."""
     out = {}
-    for node in partition_length:
-        row = h[node]
-        out[node] = [0 if d == _lib.GP_UNREACHABLE_U16 else 1 / (int(d) + 1) for d in row]
+    for node in nodes:
+        out[node] = [0 if d == _lib.GP_UNREACHABLE_U16 else 1 / (int(d) + 1) for d in h[node].tolist()]
     return out
+
+
+def shortest_path_length(G, anchor_nodes, partition_length):
+    """utils.py:64-81: ``{node: [1/len(path) per anchor]}`` with ``0`` where there is no path, keys in the
+    order of ``partition_length``.
+
+    ``G`` is the networkx graph ``to_networkx`` built; distances come from one device MS-BFS.
+    Values are Python floats ``1/(d+1)`` and the int ``0``, exactly as the reference appends them.
+    """
+    return _rows_as_reference_lists(_hops_of_graph(G, anchor_nodes), partition_length)
 
 
 def merge_dicts(dicts):
@@ -241,8 +263,14 @@ def merge_dicts(dicts):
 
 
 def all_pairs_shortest_path_length_parallel(G, anchor_nodes, num_workers):
-    """utils.py:92-114.  ``num_workers`` sized a CPU pool there; one GPU sweep replaces it."""
-    return shortest_path_length(G, anchor_nodes, list(G.nodes))
+    """utils.py:92-114.  ``num_workers`` sized a CPU pool there; one GPU sweep replaces the pool, but the node
+    slices ``nodes[int(N/w*i):int(N/w*(i+1))]`` (utils.py:100, float arithmetic) and their ordered merge are
+    kept, so the returned dict has the reference's keys in the reference's order."""
+    nodes = list(G.nodes)
+    h = _hops_of_graph(G, anchor_nodes)
+    parts = [_rows_as_reference_lists(h, nodes[int(len(nodes) / num_workers * i):int(len(nodes) / num_workers * (i + 1))])
+             for i in range(num_workers)]
+    return merge_dicts(parts)
 
 
 def get_geodesic_distance_vector(data, num_workers):

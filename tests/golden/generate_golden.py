@@ -6,6 +6,7 @@ Run in the build container only (needs /root/reference):
     python tests/golden/generate_golden.py --pubmed   # + full C1 config (~2 min, 6 workers)
     python tests/golden/generate_golden.py --betweenness   # ONLY reference_betweenness.npz (seconds)
     python tests/golden/generate_golden.py --eigenvector   # ONLY reference_eigenvector.npz (seconds)
+    python tests/golden/generate_golden.py --shims         # ONLY reference_shims.npz (seconds)
 
 The reference has no tests or golden vectors of its own, so these
 files ARE the parity pins: every value below is produced by
@@ -109,13 +110,41 @@ def eigenvector_fixture(utils):
     print("wrote reference_eigenvector.npz; n =", n, "min score", float(out["scores"].min()))
 
 
+def shims_fixture(utils):
+    """reference_shims.npz: what utils.shortest_path_length (utils.py:64-81) and
+    utils.all_pairs_shortest_path_length_parallel (utils.py:92-114) return as Python objects — key order,
+    the Python type of every entry (float 1/len(path) vs the int 0 appended at utils.py:76) and the rows of a
+    partition that is a permuted subset of the nodes."""
+    out = {}
+    for name, (n, edges, anchors) in micro_graphs().items():
+        ei = torch.tensor(np.asarray(edges, dtype=np.int64).reshape(-1, 2).T.copy())
+        G = utils.to_networkx(RefData(ei, n))
+        part = list(range(n))[::-2]  # descending, every other node
+        rows = utils.shortest_path_length(G, anchors, part)
+        out[f"{name}/partition"] = np.asarray(list(rows.keys()), dtype=np.int64)
+        out[f"{name}/partition_rows"] = np.asarray([rows[k] for k in rows], dtype=np.float64)
+        out[f"{name}/partition_is_int"] = np.asarray([[isinstance(v, int) for v in rows[k]] for k in rows], dtype=bool)
+        for w in (1, 2, 3):
+            full = utils.all_pairs_shortest_path_length_parallel(G, anchors, w)
+            out[f"{name}/all_pairs_keys/{w}"] = np.asarray(list(full.keys()), dtype=np.int64)
+            out[f"{name}/all_pairs_rows/{w}"] = np.asarray([full[k] for k in full], dtype=np.float64)
+            out[f"{name}/all_pairs_is_int/{w}"] = np.asarray([[isinstance(v, int) for v in full[k]] for k in full],
+                                                             dtype=bool)
+    np.savez_compressed(os.path.join(HERE, "reference_shims.npz"), **out)
+    print("wrote reference_shims.npz with", len(out), "arrays")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pubmed", action="store_true")
     ap.add_argument("--betweenness", action="store_true")
     ap.add_argument("--eigenvector", action="store_true")
+    ap.add_argument("--shims", action="store_true")
     args = ap.parse_args()
     utils = load_reference_utils()
+    if args.shims:
+        shims_fixture(utils)
+        return
     if args.betweenness or args.eigenvector:
         if args.betweenness:
             betweenness_fixture(utils)

@@ -82,5 +82,10 @@ def test_anchor_sharding_world_size_2(k_total):
 
 def test_shard_bounds():
     assert [gpd.shard_bounds(1024, 8, r) for r in (0, 7)] == [(0, 128), (896, 1024)]
-    with pytest.raises(ValueError):
-        gpd.shard_bounds(10, 4, 0)
+    # ragged: ceil(K / G) per rank, the tail ranks hold fewer (the reference accepts any K)
+    assert [gpd.shard_bounds(10, 4, r) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert [gpd.shard_bounds(2, 4, r) for r in range(4)] == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    padded, per = gpd.pad_anchors(np.arange(10), 4)
+    assert per == 8 and len(padded) == 32 and padded[:10].tolist() == list(range(10)) and set(padded[10:]) == {9}
+    padded, per = gpd.pad_anchors(torch.arange(1024), 8)
+    assert per == 128 and padded.numel() == 1024
