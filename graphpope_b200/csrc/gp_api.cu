@@ -5,7 +5,6 @@
 
 #include <algorithm>
 #include <atomic>
-#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -16,6 +15,9 @@
 #include <vector>
 
 bool gp_is_capturing();
+bool gp_xcopy_tma_ok(const float *d_x, int64_t num_features, int64_t ld_x, const float *d_out, int64_t ld_out);
+int gp_launch_xcopy_tma(const float *d_x, int64_t num_nodes, int64_t num_features, int64_t ld_x, float *d_out,
+                        int64_t ld_out, cudaStream_t stream);
 static bool g_capturing_flag_for_count() { return gp_is_capturing(); }
 void gp_count_launches(int n);
 
@@ -326,17 +328,23 @@ int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t 
                        int64_t k, const float *d_x, int64_t f, int64_t ldx, float *d_out, int64_t ldo,
                        int64_t coff, cudaStream_t s)
 {
-    // concat_into_features' copy of x (utils.py:133-134) does not depend on the traversal, and the csr build and
-    // the MS-BFS are latency-bound and leave HBM idle, so the copy could run beside them on a side stream (a
-    // parallel branch of the captured graph).  Measured on B200 it never paid (profiles/r01p_notes.md: copy
-    // engine 0.323 ms, copy kernels of three shapes 0.265-0.301 ms, against 0.246 ms with the copy fused into the
-    // epilogue), so the fused copy is the default; GP_XCOPY_OVERLAP=1 keeps the copy-engine variant selectable.
+    // concat_into_features' copy of x (utils.py:133-134) depends on neither the csr build nor the traversal, which
+    // are latency-bound and leave HBM idle, so it could run beside them on a side stream (a parallel branch of the
+    // captured graph).  Measured on B200 it never pays: whatever moves the rows — the copy engine (round 1), copy
+    // kernels of three shapes (round 1), or the bulk-copy-engine pipeline of gp_xcopy.cu (round 2: 4.9 TB/s alone,
+    // one thread and 64 KB of shared memory per SM, resident next to the cooperative MS-BFS grid) — the latency-bound
+    // neighbours slow down by about the time the copy takes (csr build 94 -> 153-170 us, msbfs_kernel 86 -> 117-241 us
+    // while rows stream through the L2, even throttled to 3.6 TB/s; profiles/r02_notes.md), so the copy stays fused
+    // in the epilogue kernel (GP_XCOPY_OVERLAP=0, default).  1 = one strided cudaMemcpy2DAsync on the copy engine,
+    // 2 = the bulk-copy kernel on the side branch.
     static int overlap = -1;
     if (overlap < 0) {
         const char *ev = getenv("GP_XCOPY_OVERLAP");
         overlap = ev ? atoi(ev) : 0;
     }
-    const bool side_copy = overlap == 1 && d_out != nullptr && d_x != nullptr && f > 0 && csr->num_nodes > 0;
+    const bool have_copy = d_out != nullptr && d_x != nullptr && f > 0 && csr->num_nodes > 0;
+    const bool tma_copy = have_copy && overlap == 2 && gp_xcopy_tma_ok(d_x, f, ldx, d_out, ldo);
+    const bool side_copy = have_copy && (overlap == 1 || tma_copy);
     SideCopy &sc = side_copy_state();
     if (side_copy) {
         if (sc.stream == nullptr) {
@@ -346,10 +354,20 @@ int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t 
         }
         GP_CUDA_CHECK(cudaEventRecord(sc.fork, s));
         GP_CUDA_CHECK(cudaStreamWaitEvent(sc.stream, sc.fork, 0));
-        GP_CUDA_CHECK(cudaMemcpy2DAsync(d_out, (size_t)ldo * sizeof(float), d_x, (size_t)ldx * sizeof(float),
-                                        (size_t)f * sizeof(float), (size_t)csr->num_nodes,
-                                        cudaMemcpyDeviceToDevice, sc.stream));
-        GP_CUDA_CHECK(cudaEventRecord(sc.join, sc.stream));
+        int crc = GP_OK;
+        if (tma_copy) {
+            crc = gp_launch_xcopy_tma(d_x, csr->num_nodes, f, ldx, d_out, ldo, sc.stream);
+        } else if (cudaMemcpy2DAsync(d_out, (size_t)ldo * sizeof(float), d_x, (size_t)ldx * sizeof(float),
+                                     (size_t)f * sizeof(float), (size_t)csr->num_nodes, cudaMemcpyDeviceToDevice,
+                                     sc.stream) != cudaSuccess) {
+            gp_set_error("cudaMemcpy2DAsync of x failed");
+            crc = GP_ERR_CUDA;
+        }
+        GP_CUDA_CHECK(cudaEventRecord(sc.join, sc.stream));  // always re-join: a capture must not end forked
+        if (crc != GP_OK) {
+            cudaStreamWaitEvent(s, sc.join, 0);
+            return crc;
+        }
     }
     int rc = gp_csr_build(csr, d_ei, e, s);
     if (rc == GP_OK) rc = gp_msbfs_run(bfs, d_anchors, k, s);
@@ -452,6 +470,8 @@ extern "C" int gp_concat_x(const float *d_x, int64_t num_nodes, int64_t num_feat
                "gp_concat_x: inconsistent sizes");
     if (num_nodes == 0 || num_features == 0) return GP_OK;
     GP_REQUIRE(d_x != nullptr && d_out != nullptr, GP_ERR_INVALID, "gp_concat_x: NULL argument");
+    if (gp_xcopy_tma_ok(d_x, num_features, ld_x, d_out, ld_out))
+        return gp_launch_xcopy_tma(d_x, num_nodes, num_features, ld_x, d_out, ld_out, (cudaStream_t)stream);
     GP_CUDA_CHECK(cudaMemcpy2DAsync(d_out, (size_t)ld_out * sizeof(float), d_x, (size_t)ld_x * sizeof(float),
                                     (size_t)num_features * sizeof(float), (size_t)num_nodes,
                                     cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
