@@ -27,7 +27,7 @@ int g_sm_count = 0;
 std::atomic<long long> g_launches{0};
 }  // namespace
 
-static int g_capture_count = 0;  // kernels recorded into the graph being captured
+static thread_local int g_capture_count = 0;  // kernels this thread recorded into the graph it is capturing
 void gp_count_launch()
 {
     if (g_capturing_flag_for_count()) ++g_capture_count;
@@ -311,7 +311,7 @@ std::vector<PipeEntry> g_pipes;
 std::mutex g_pipe_mutex;
 cudaStream_t g_capture_stream = nullptr;
 uint64_t g_pipe_clock = 0;
-bool g_capturing = false;
+thread_local bool g_capturing = false;  // a capture belongs to the thread that runs it
 
 struct SideCopy {
     cudaStream_t stream = nullptr;
@@ -369,12 +369,17 @@ int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t 
             return crc;
         }
     }
+    // stage clocks of the step (gp_pipeline_stage_ms): inside a capture these become event-record nodes
+    const unsigned ev_flags = gp_is_capturing() ? cudaEventRecordExternal : cudaEventRecordDefault;
+    GP_CUDA_CHECK(cudaEventRecordWithFlags(bfs->ev_pipe0, s, ev_flags));
     int rc = gp_csr_build(csr, d_ei, e, s);
     if (rc == GP_OK) rc = gp_msbfs_run(bfs, d_anchors, k, s);
     if (side_copy) GP_CUDA_CHECK(cudaStreamWaitEvent(s, sc.join, 0));  // always re-join: a capture must not end forked
     GP_TRY(rc);
     if (d_out != nullptr) GP_TRY(gp_msbfs_features(bfs, side_copy ? nullptr : d_x, f, ldx, d_out, ldo, coff, s));
     else GP_TRY(gp_msbfs_pack(bfs, (int32_t)coff, nullptr, nullptr, nullptr, nullptr, nullptr, s));  // coff = slot
+    GP_CUDA_CHECK(cudaEventRecordWithFlags(bfs->ev_pipe1, s, ev_flags));
+    bfs->pipe_timed = true;
     return GP_OK;
 }
 
@@ -455,6 +460,10 @@ extern "C" int gp_geodesic_run(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_
     if (ent->exec != nullptr) {
         csr->in_built = false;  // the replay rebuilds the out-edge CSR from the (possibly changed) edge buffer
         csr->num_input_edges = num_edges;
+        csr->built = true;
+        gp_msbfs_layout(bfs, num_anchors);  // the handle may have run another anchor count since the capture
+        bfs->ran = true;
+        bfs->pipe_timed = true;
         gp_count_launches(ent->kernels);  // kernels inside the graph
         GP_CUDA_CHECK(cudaGraphLaunch(ent->exec, stream));
         return GP_OK;

@@ -649,6 +649,22 @@ static void bfs_config(int64_t k, int *wb, int *batches)
     *batches = (int)gp_ceil_div(k > 0 ? k : 1, 64 * (*wb));
 }
 
+// Host view of a run with `num_anchors` anchors: lane layout and the array pointers inside lane_buf.  Also called
+// when a captured pipeline is replayed, so the decode entry points see the layout of the run they follow.
+void gp_msbfs_layout(gp_msbfs *h, int64_t num_anchors)
+{
+    int wb, batches;
+    bfs_config(num_anchors, &wb, &batches);
+    h->wb = wb;
+    h->batches = batches;
+    h->num_anchors = num_anchors;
+    const size_t words = (size_t)wb * batches * (size_t)h->num_nodes;
+    h->seeds = h->lane_buf;
+    h->seen = h->lane_buf + words;  // R[0]; R[l] = seen + l * words
+    h->fr_a = h->seen + (size_t)GP_BFS_RESULT_ARRAYS * words;
+    h->fr_b = h->fr_a + words;
+}
+
 extern "C" int gp_msbfs_create(const gp_csr_t *csr, int64_t max_anchors, gp_msbfs_t **out)
 {
     GP_REQUIRE(out != nullptr, GP_ERR_INVALID, "gp_msbfs_create: out is NULL");
@@ -697,7 +713,8 @@ extern "C" int gp_msbfs_create(const gp_csr_t *csr, int64_t max_anchors, gp_msbf
         h->nzmap = reinterpret_cast<u32 *>(h->status + 16);
     }
     if (getenv("GP_BFS_TRACE")) alloc((void **)&h->trace, GP_BFS_TRACE_WORDS * sizeof(u64));
-    if (rc == GP_OK && (cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess)) {
+    if (rc == GP_OK && (cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess ||
+                        cudaEventCreate(&h->ev_pipe0) != cudaSuccess || cudaEventCreate(&h->ev_pipe1) != cudaSuccess)) {
         gp_set_error("gp_msbfs_create: cudaEventCreate failed");
         rc = GP_ERR_CUDA;
     }
@@ -722,6 +739,8 @@ extern "C" int gp_msbfs_free(gp_msbfs_t *h)
     cudaFree(h->trace);
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     if (h->ev_stop) cudaEventDestroy(h->ev_stop);
+    if (h->ev_pipe0) cudaEventDestroy(h->ev_pipe0);
+    if (h->ev_pipe1) cudaEventDestroy(h->ev_pipe1);
     delete h;
     return GP_OK;
 }
@@ -736,18 +755,11 @@ extern "C" int gp_msbfs_run(gp_msbfs_t *h, const int64_t *d_anchors, int64_t num
                "gp_msbfs_run: %lld anchors exceed max_anchors %lld", (long long)num_anchors,
                (long long)h->max_anchors);
     GP_REQUIRE(num_anchors == 0 || d_anchors != nullptr, GP_ERR_INVALID, "gp_msbfs_run: anchors is NULL");
-    int wb, batches;
-    bfs_config(num_anchors, &wb, &batches);
-    h->wb = wb;
-    h->batches = batches;
-    h->num_anchors = num_anchors;
+    gp_msbfs_layout(h, num_anchors);
     h->ran = false;
+    const int wb = h->wb, batches = h->batches;
     const int64_t n = h->num_nodes;
     const size_t words = (size_t)wb * batches * (size_t)n;
-    h->seeds = h->lane_buf;
-    h->seen = h->lane_buf + words;  // R[0]; R[l] = seen + l * words
-    h->fr_a = h->seen + (size_t)GP_BFS_RESULT_ARRAYS * words;
-    h->fr_b = h->fr_a + words;
     const int map_stride = (int)(((int64_t)batches * h->nzwords + 3) / 4 * 4);
     const size_t run_scratch = (size_t)((char *)h->nzmap - (char *)h->scratch) + 3 * (size_t)map_stride * sizeof(u32);
     GP_CUDA_CHECK(cudaMemsetAsync(h->scratch, 0, run_scratch, stream));  // live, bar, counters, status, maps
@@ -846,6 +858,19 @@ extern "C" int gp_msbfs_kernel_ms(gp_msbfs_t *h, float *ms)
     if (h->num_nodes == 0 || h->num_anchors == 0) return GP_OK;
     GP_CUDA_CHECK(cudaEventSynchronize(h->ev_stop));
     GP_CUDA_CHECK(cudaEventElapsedTime(ms, h->ev_start, h->ev_stop));
+    return GP_OK;
+}
+
+extern "C" int gp_pipeline_stage_ms(gp_msbfs_t *h, float *ms3)
+{
+    GP_REQUIRE(h != nullptr && ms3 != nullptr, GP_ERR_INVALID, "gp_pipeline_stage_ms: NULL argument");
+    GP_REQUIRE(h->ran && h->pipe_timed, GP_ERR_INVALID, "gp_pipeline_stage_ms: gp_geodesic_run has not been called");
+    ms3[0] = ms3[1] = ms3[2] = 0.0f;
+    if (h->num_nodes == 0 || h->num_anchors == 0) return GP_OK;
+    GP_CUDA_CHECK(cudaEventSynchronize(h->ev_pipe1));
+    GP_CUDA_CHECK(cudaEventElapsedTime(ms3 + 0, h->ev_pipe0, h->ev_start));
+    GP_CUDA_CHECK(cudaEventElapsedTime(ms3 + 1, h->ev_start, h->ev_stop));
+    GP_CUDA_CHECK(cudaEventElapsedTime(ms3 + 2, h->ev_stop, h->ev_pipe1));
     return GP_OK;
 }
 

@@ -60,7 +60,11 @@ struct gp_msbfs {
     int grid_cfg = -1;
     int block_threads = 512;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;  // bracket the persistent kernel alone
+    cudaEvent_t ev_pipe0 = nullptr, ev_pipe1 = nullptr;  // first / last node of the last gp_geodesic_run pipeline
+    bool pipe_timed = false;
 };
+
+void gp_msbfs_layout(gp_msbfs *h, int64_t num_anchors);
 
 // Fused decode + concat epilogue over `num_ranks` plane sets (1 = local result).
 struct GpDecodeParams {

@@ -200,6 +200,13 @@ class MsBfs:
         check(self._lib.gp_msbfs_kernel_ms(self._h, byref(ms)))
         return float(ms.value)
 
+    def pipeline_stage_ms(self):
+        """(csr build, MS-BFS kernel, epilogue) device milliseconds of the last fused run on this handle,
+        from event nodes inside the replayed CUDA graph."""
+        ms = (ctypes.c_float * 3)()
+        check(self._lib.gp_pipeline_stage_ms(self._h, ms))
+        return float(ms[0]), float(ms[1]), float(ms[2])
+
     def planes(self):
         """(uint64 view [num_planes, words], meta dict) of the bit-sliced result, for the gather."""
         ptr, stride = c_void_p(), c_int64()

@@ -163,6 +163,132 @@ def sharded_geodesic_embed_host(engine, edge_index: torch.Tensor, anchors, x: to
     return out
 
 
+class SharedHostMatrix:
+    """One float32 ``[rows, cols]`` matrix in POSIX shared memory per node, page-locked in every rank.
+
+    The reference runs ``Graphpope`` in every DDP rank (main.py:88-98) and afterwards only indexes ``data.x[n_id]``
+    (main.py:120,177), so all ranks of a node hold identical ``[N, F+K]`` host matrices.  Here there is ONE: rank 0
+    creates ``/dev/shm/<name>``, every rank maps the same pages, registers them with CUDA (``cudaHostRegister``) so
+    device-to-host DMAs can land in it directly, and wraps the mapping as a torch tensor.  Rank r then writes only
+    its own column block (and its row range of ``x``), a barrier later every rank sees the whole matrix.
+    """
+
+    def __init__(self, rows: int, cols: int, group=None, name: str | None = None, register: bool = True):
+        import mmap
+        import uuid
+
+        import numpy as np
+
+        self.rows, self.cols, self.group = int(rows), int(cols), group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        nbytes = max(4 * self.rows * self.cols, mmap.PAGESIZE)
+        self.nbytes = -(-nbytes // mmap.PAGESIZE) * mmap.PAGESIZE
+        box = [name or "graphpope_%s" % uuid.uuid4().hex]
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=0, group=group)
+        self.path = os.path.join("/dev/shm", box[0])
+        if self.rank == 0:
+            fd = os.open(self.path, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
+            os.ftruncate(fd, self.nbytes)
+        if self.world > 1:
+            dist.barrier(group=group)
+        if self.rank != 0:
+            fd = os.open(self.path, os.O_RDWR)
+        self._mm = mmap.mmap(fd, self.nbytes, mmap.MAP_SHARED, mmap.PROT_READ | mmap.PROT_WRITE)
+        os.close(fd)
+        if self.world > 1:
+            dist.barrier(group=group)
+        if self.rank == 0:
+            os.unlink(self.path)  # every rank holds its mapping; the name is no longer needed
+        arr = np.frombuffer(self._mm, dtype=np.float32, count=self.rows * self.cols).reshape(self.rows, self.cols)
+        self.tensor = torch.from_numpy(arr)
+        self._registered = False
+        if register and torch.cuda.is_available():
+            rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), self.nbytes, 0)
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister of the shared matrix failed with error {int(rc)}")
+            self._registered = True
+
+    def barrier(self):
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def close(self):
+        if self._registered:
+            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            self._registered = False
+        self.tensor = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def row_slice(num_rows: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Rank r's share of a row-partitioned host copy (``x`` into columns ``[0, F)``)."""
+    per = -(-int(num_rows) // int(world_size))
+    return min(num_rows, rank * per), min(num_rows, (rank + 1) * per)
+
+
+def sharded_embed_host_shared(engine, edge_index: torch.Tensor, anchors, x: torch.Tensor | None,
+                              shared: "SharedHostMatrix", staging: dict) -> torch.Tensor:
+    """Host contract of the geodesic path for the ranks of one node WITHOUT assembling anything on the device
+    (SURVEY §8 f3): HOST ``edge_index`` / ``x`` in, the node-shared HOST ``[N, F + K]`` matrix out.
+
+    Rank r runs the MS-BFS for its anchor shard only, decodes its own ``[N, K/G]`` block and DMAs it straight
+    into columns ``[F + lo, F + hi)`` of the shared matrix; the copy of ``x`` (concat_into_features,
+    utils.py:129-135) is split by row range across the ranks; one barrier, then every rank returns the same
+    tensor.  Per rank and step: H2D = edge_index + its anchors, D2H = N * K/G floats (1/G of what the
+    replicated assembly moved), host copy = N/G rows of x.  Bit-equal to the 1-GPU result.
+    """
+    from . import _lib
+    from ._lib import check
+    from .device import _ptr
+
+    import numpy as np
+
+    n = engine.csr.num_nodes
+    a = torch.as_tensor(np.asarray(anchors, dtype=np.int64))
+    k = a.numel()
+    f = 0 if x is None else x.size(1)
+    out = shared.tensor
+    if tuple(out.shape) != (n, f + k):
+        raise ValueError(f"shared matrix is {tuple(out.shape)}, expected {(n, f + k)}")
+    rank, world = shared.rank, shared.world
+    lo, hi = shard_bounds(k, world, rank)
+    kr = hi - lo
+    key = (n, kr, edge_index.size(1))
+    if staging.get("shape") != key:
+        staging.clear()
+        staging["shape"] = key
+        staging["ei"] = torch.empty_like(edge_index, device="cuda")
+        staging["anchors"] = torch.empty(max(kr, 1), dtype=torch.int64, device="cuda")
+        staging["block_d"] = torch.empty((n, max(kr, 1)), dtype=torch.float32, device="cuda")
+        staging["a_pin"] = torch.empty(max(kr, 1), dtype=torch.int64).pin_memory()
+    lib = _lib.load()
+    stream = c_void_p(torch.cuda.current_stream().cuda_stream)
+    if kr > 0:
+        staging["ei"].copy_(edge_index, non_blocking=True)
+        staging["a_pin"][:kr].copy_(a[lo:hi])
+        staging["anchors"][:kr].copy_(staging["a_pin"][:kr], non_blocking=True)
+        engine.run(staging["ei"], staging["anchors"][:kr], None, staging["block_d"][:, :kr])
+        check(lib.gp_block_to_host(_ptr(staging["block_d"]), n, kr, _ptr(out), out.stride(0), f + lo, stream))
+    if x is not None and f > 0:
+        if not x.is_contiguous():
+            x = x.contiguous()
+        r0, r1 = row_slice(n, world, rank)
+        if r1 > r0:  # this rank's rows of x, on the host while the GPU works
+            check(lib.gp_host_concat(c_void_p(x.data_ptr() + 4 * r0 * x.stride(0)), f, None, 0, r1 - r0,
+                                     c_void_p(out.data_ptr() + 4 * r0 * out.stride(0)), out.stride(0)))
+    torch.cuda.current_stream().synchronize()
+    engine.bfs.stats() if kr > 0 else None  # surfaces latched device errors (bad index, uint16 overflow)
+    shared.barrier()
+    return out
+
+
 class PeerAssembly:
     """NVLink peer-to-peer assembly of the sharded result (the B200-native form of the exchange step).
 

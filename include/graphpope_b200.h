@@ -141,6 +141,12 @@ int gp_geodesic_run(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_edge_index,
                     const int64_t *d_anchors, int64_t num_anchors, const float *d_x, int64_t num_features,
                     int64_t ld_x, float *d_out, int64_t ld_out, int64_t col_offset, gp_stream_t stream);
 
+/* syncs on the pipeline's own events.  Device time of the three stages of the last gp_geodesic_run /
+ * gp_geodesic_run_packed on this handle, in milliseconds: ms3[0] = csr build (+ the MS-BFS state memsets),
+ * ms3[1] = the persistent MS-BFS kernel, ms3[2] = epilogue (decode + concat, or pack).  The events are nodes of
+ * the replayed CUDA graph, so these are the times inside the timed step, not of stages launched on their own. */
+int gp_pipeline_stage_ms(gp_msbfs_t *bfs, float *ms3);
+
 /* async.  The x half of concat_into_features (utils.py:133-134) alone: d_out[:, 0:F] = d_x as ONE strided
  * device-to-device transfer, for callers that already hold x in place or want the copy on their own stream;
  * follow with gp_msbfs_features / gp_decode_peers called with d_x == NULL.  gp_geodesic_run keeps the copy
