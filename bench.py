@@ -321,11 +321,12 @@ def timed_steps(fn, barrier, dist, world, reps, flush=None):
     """Device time per call: events around each call, L2 flushed in between (untimed), max over ranks."""
     import torch
     total = 0.0
+    align = torch.zeros(1, device="cuda")
     for i in range(reps):
         if flush is not None:
             flush(i)
         if world > 1:
-            dist.barrier()
+            dist.all_reduce(align)  # device-side alignment of the ranks, not waited for by the host
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize()
         total += a.elapsed_time(b)
@@ -598,19 +599,25 @@ def main():
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stage_ms = []
     launches0 = dev.launch_count()
+    align_t = torch.zeros(1, device="cuda")
     barrier()
     for i in range(args.steps):
         flush_l2(i)  # untimed: evict the previous step's lines from the 126 MB L2
-        # untimed alignment: without it the ranks drift apart during the flush and the wait for the slowest
-        # one inside the step's exchange lands in the timed region of the others
+        # untimed alignment ON THE DEVICE: a tiny all-reduce that the host does not wait for.  Its kernel ends at
+        # the same moment on every rank and the step is already queued behind it, so the ranks enter the timed
+        # region together.  (dist.barrier() blocks the host, and the ranks' launch jitter after it — tens of
+        # microseconds — then shows up inside the step as waiting for the last rank's flag.)
         if world > 1:
-            dist.barrier()
+            dist.all_reduce(align_t)
         starts[i].record()
         step()
         stops[i].record()
         stage_ms.append(engine.bfs.pipeline_stage_ms())  # event nodes of the replayed graph (syncs on the last one)
     barrier()
     launches = dev.launch_count() - launches0
+    if peer is not None and hasattr(peer, "trace"):
+        tr = peer.trace()
+        print(f"rank {rank} exchange kernel phases (us from its start): {tr}", file=sys.stderr, flush=True)
     if peer is not None and peer.trace_events and rank == 0:
         peer.trace_events = peer.trace_events[-args.steps:]
         print("peer step phases (median ms): csr+bfs+pack %.4f, flag all-reduce %.4f, peer decode %.4f"
@@ -705,7 +712,7 @@ def main():
         b_epi = bytes_epilogue(n, k_total, f)
         st = np.asarray(stage_ms)  # [steps, 3] csr, bfs kernel, epilogue
         csr_ms, bfs_avg_ms, epi_ms = [float(v) for v in st.mean(axis=0)]
-        if world > 1:  # the graph of a sharded step ends at the pack; exchange + decode follow it
+        if world > 1 and not hasattr(peer, "trace"):  # pull path: the graph ends at the pack, exchange + decode follow it
             epi_ms = max(ms_per_step - csr_ms - bfs_avg_ms, 1e-6)
         achieved = b_bfs / (bfs_avg_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None

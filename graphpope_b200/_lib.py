@@ -88,6 +88,16 @@ SIGNATURES = {
     "gp_ipc_close": (c_int, [c_void_p]),
     "gp_decode_peers": (c_int, [c_void_p, c_int32, c_int64, c_int64, c_int32, c_int32, c_int64, c_void_p, c_int64,
                                 c_int64, c_void_p, c_int64, c_int64, c_void_p]),
+    "gp_exchange_create": (c_int, [c_void_p, c_int32, c_int32, POINTER(c_void_p)]),
+    "gp_exchange_ipc_export": (c_int, [c_void_p, c_void_p]),
+    "gp_exchange_local_ptr": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "gp_exchange_set_peer": (c_int, [c_void_p, c_int32, c_void_p]),
+    "gp_geodesic_run_exchange": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                         c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p]),
+    "gp_exchange_run": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p]),
+    "gp_exchange_status": (c_int, [c_void_p, POINTER(c_int32), c_void_p]),
+    "gp_exchange_trace": (c_int, [c_void_p, c_void_p]),
+    "gp_exchange_free": (c_int, [c_void_p]),
     "gp_normalize_into": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p]),
     "gp_geodesic_embed_host": (c_int, [c_void_p, c_int64, c_int64, c_uint32, c_void_p, c_int64, c_void_p,
                                        c_int64, c_void_p, c_int64, c_int64, c_void_p, POINTER(MsbfsStats)]),

@@ -18,6 +18,10 @@ bool gp_is_capturing();
 bool gp_xcopy_tma_ok(const float *d_x, int64_t num_features, int64_t ld_x, const float *d_out, int64_t ld_out);
 int gp_launch_xcopy_tma(const float *d_x, int64_t num_nodes, int64_t num_features, int64_t ld_x, float *d_out,
                         int64_t ld_out, cudaStream_t stream);
+struct gp_exchange;
+int gp_exchange_launch(gp_exchange *x, int parity, const float *d_x, int64_t f, int64_t ldx, float *d_out, int64_t ldo,
+                       int64_t coff, cudaStream_t stream);
+int gp_exchange_next_parity(gp_exchange *x);
 static bool g_capturing_flag_for_count() { return gp_is_capturing(); }
 void gp_count_launches(int n);
 
@@ -294,8 +298,8 @@ void copy_rows_parallel(const float *src, int64_t ld_src, float *dst, int64_t ld
 namespace {
 
 struct PipeKey {
-    const void *csr, *bfs, *ei, *anchors, *x, *out;
-    int64_t e, k, f, ldx, ldo, coff;
+    const void *csr, *bfs, *ei, *anchors, *x, *out, *xchg;
+    int64_t e, k, f, ldx, ldo, coff, parity;
     bool operator==(const PipeKey &o) const { return memcmp(this, &o, sizeof(PipeKey)) == 0; }
 };
 
@@ -326,7 +330,7 @@ SideCopy &side_copy_state()
 
 int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t e, const int64_t *d_anchors,
                        int64_t k, const float *d_x, int64_t f, int64_t ldx, float *d_out, int64_t ldo,
-                       int64_t coff, cudaStream_t s)
+                       int64_t coff, cudaStream_t s, gp_exchange *xchg = nullptr, int parity = 0)
 {
     // concat_into_features' copy of x (utils.py:133-134) depends on neither the csr build nor the traversal, which
     // are latency-bound and leave HBM idle, so it could run beside them on a side stream (a parallel branch of the
@@ -342,7 +346,7 @@ int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t 
         const char *ev = getenv("GP_XCOPY_OVERLAP");
         overlap = ev ? atoi(ev) : 0;
     }
-    const bool have_copy = d_out != nullptr && d_x != nullptr && f > 0 && csr->num_nodes > 0;
+    const bool have_copy = d_out != nullptr && d_x != nullptr && f > 0 && csr->num_nodes > 0 && xchg == nullptr;
     const bool tma_copy = have_copy && overlap == 2 && gp_xcopy_tma_ok(d_x, f, ldx, d_out, ldo);
     const bool side_copy = have_copy && (overlap == 1 || tma_copy);
     SideCopy &sc = side_copy_state();
@@ -376,7 +380,8 @@ int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t 
     if (rc == GP_OK) rc = gp_msbfs_run(bfs, d_anchors, k, s);
     if (side_copy) GP_CUDA_CHECK(cudaStreamWaitEvent(s, sc.join, 0));  // always re-join: a capture must not end forked
     GP_TRY(rc);
-    if (d_out != nullptr) GP_TRY(gp_msbfs_features(bfs, side_copy ? nullptr : d_x, f, ldx, d_out, ldo, coff, s));
+    if (xchg != nullptr) GP_TRY(gp_exchange_launch(xchg, parity, d_x, f, ldx, d_out, ldo, coff, s));
+    else if (d_out != nullptr) GP_TRY(gp_msbfs_features(bfs, side_copy ? nullptr : d_x, f, ldx, d_out, ldo, coff, s));
     else GP_TRY(gp_msbfs_pack(bfs, (int32_t)coff, nullptr, nullptr, nullptr, nullptr, nullptr, s));  // coff = slot
     GP_CUDA_CHECK(cudaEventRecordWithFlags(bfs->ev_pipe1, s, ev_flags));
     bfs->pipe_timed = true;
@@ -391,7 +396,7 @@ void gp_drop_graphs(const void *handle)
 {
     std::lock_guard<std::mutex> lock(g_pipe_mutex);
     for (size_t i = 0; i < g_pipes.size();) {
-        if (g_pipes[i].key.csr == handle || g_pipes[i].key.bfs == handle) {
+        if (g_pipes[i].key.csr == handle || g_pipes[i].key.bfs == handle || g_pipes[i].key.xchg == handle) {
             if (g_pipes[i].exec) cudaGraphExecDestroy(g_pipes[i].exec);
             g_pipes.erase(g_pipes.begin() + i);
         } else {
@@ -400,10 +405,10 @@ void gp_drop_graphs(const void *handle)
     }
 }
 
-extern "C" int gp_geodesic_run(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_edge_index, int64_t num_edges,
-                               const int64_t *d_anchors, int64_t num_anchors, const float *d_x,
-                               int64_t num_features, int64_t ld_x, float *d_out, int64_t ld_out,
-                               int64_t col_offset, gp_stream_t stream_)
+static int geodesic_run_impl(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_edge_index, int64_t num_edges,
+                             const int64_t *d_anchors, int64_t num_anchors, const float *d_x,
+                             int64_t num_features, int64_t ld_x, float *d_out, int64_t ld_out,
+                             int64_t col_offset, gp_stream_t stream_, gp_exchange *xchg, int parity)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     GP_REQUIRE(csr != nullptr && bfs != nullptr, GP_ERR_INVALID, "gp_geodesic_run: NULL handle");
@@ -414,12 +419,13 @@ extern "C" int gp_geodesic_run(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_
     }
     if (!use_graph || csr->num_nodes == 0 || num_anchors == 0)
         return run_pipeline_eager(csr, bfs, d_edge_index, num_edges, d_anchors, num_anchors, d_x, num_features, ld_x,
-                                  d_out, ld_out, col_offset, stream);
+                                  d_out, ld_out, col_offset, stream, xchg, parity);
     std::lock_guard<std::mutex> lock(g_pipe_mutex);
     PipeKey key;
     memset(&key, 0, sizeof(key));
     key.csr = csr; key.bfs = bfs; key.ei = d_edge_index; key.anchors = d_anchors; key.x = d_x; key.out = d_out;
     key.e = num_edges; key.k = num_anchors; key.f = num_features; key.ldx = ld_x; key.ldo = ld_out; key.coff = col_offset;
+    key.xchg = xchg; key.parity = parity;
     PipeEntry *ent = nullptr;
     for (auto &p : g_pipes)
         if (p.key == key) ent = &p;
@@ -445,7 +451,8 @@ extern "C" int gp_geodesic_run(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_
             g_capturing = true;
             g_capture_count = 0;
             const int rc = run_pipeline_eager(csr, bfs, d_edge_index, num_edges, d_anchors, num_anchors, d_x,
-                                              num_features, ld_x, d_out, ld_out, col_offset, g_capture_stream);
+                                              num_features, ld_x, d_out, ld_out, col_offset, g_capture_stream, xchg,
+                                              parity);
             g_capturing = false;
             ent->kernels = g_capture_count;
             const cudaError_t ce = cudaStreamEndCapture(g_capture_stream, &graph);
@@ -469,7 +476,30 @@ extern "C" int gp_geodesic_run(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_
         return GP_OK;
     }
     return run_pipeline_eager(csr, bfs, d_edge_index, num_edges, d_anchors, num_anchors, d_x, num_features, ld_x,
-                              d_out, ld_out, col_offset, stream);
+                              d_out, ld_out, col_offset, stream, xchg, parity);
+}
+
+extern "C" int gp_geodesic_run(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_edge_index, int64_t num_edges,
+                               const int64_t *d_anchors, int64_t num_anchors, const float *d_x,
+                               int64_t num_features, int64_t ld_x, float *d_out, int64_t ld_out,
+                               int64_t col_offset, gp_stream_t stream_)
+{
+    return geodesic_run_impl(csr, bfs, d_edge_index, num_edges, d_anchors, num_anchors, d_x, num_features, ld_x, d_out,
+                             ld_out, col_offset, stream_, nullptr, 0);
+}
+
+// Sharded step as one call: csr build + MS-BFS of this rank's anchors + the fused push exchange / decode kernel
+// (gp_exchange.cu), graph-replayed per step parity.  Collective: every rank of the exchange calls it once per step.
+extern "C" int gp_geodesic_run_exchange(gp_csr_t *csr, gp_msbfs_t *bfs, gp_exchange_t *xchg, const int64_t *d_edge_index,
+                                        int64_t num_edges, const int64_t *d_anchors, int64_t num_anchors,
+                                        const float *d_x, int64_t num_features, int64_t ld_x, float *d_out,
+                                        int64_t ld_out, int64_t col_offset, gp_stream_t stream_)
+{
+    GP_REQUIRE(xchg != nullptr && d_out != nullptr, GP_ERR_INVALID, "gp_geodesic_run_exchange: NULL argument");
+    GP_REQUIRE(csr != nullptr && csr->num_nodes > 0 && num_anchors > 0, GP_ERR_INVALID,
+               "gp_geodesic_run_exchange: empty graph or shard");
+    return geodesic_run_impl(csr, bfs, d_edge_index, num_edges, d_anchors, num_anchors, d_x, num_features, ld_x, d_out,
+                             ld_out, col_offset, stream_, xchg, gp_exchange_next_parity(xchg));
 }
 
 extern "C" int gp_concat_x(const float *d_x, int64_t num_nodes, int64_t num_features, int64_t ld_x, float *d_out,

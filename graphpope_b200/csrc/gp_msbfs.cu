@@ -55,8 +55,9 @@ struct BfsParams {
     const long long *__restrict__ anchors;
     u64 *result;                    // R[0..31], see the layout note above
     u64 *seeds;                     // level-0 frontier (the anchors)
-    u64 *fr_a;                      // ping-pong frontiers for hops >= 16
+    u64 *fr_a;                      // three rotating frontiers for hops >= 16 (hop l lives in buffer l % 3)
     u64 *fr_b;
+    u64 *fr_c;
     long long plane_stride;         // words per array = batches * n * wb
     u64 *live;                      // [3][GP_BFS_MAX_LANE_WORDS]
     u64 *hub_acc;                   // [batches][hub_capacity][wb] partial ORs of hub rows
@@ -168,12 +169,12 @@ struct LevelCtx {
     u64 *planes;   // R[16]: deep-hop bit planes
     long long plane_stride;
     int level;
-    int zero_first, zero_count;  // bit planes [zero_first, zero_first + zero_count) are cleared during this sweep
     u32 *map_w;    // non-zero-row bitmap of the frontier being written (this batch), or nullptr
 };
 
-// Owner-side update of one row's VW lane words.  Returns true if the row can still gain lanes
-// (some lane that is live this level has not reached it yet).
+// Owner-side update of one row's VW lane words.  The frontier array being written was zeroed one level ahead
+// (see the level prologue), so a row with nothing new writes nothing at all.  Returns true if the row can still
+// gain lanes (some lane that is live this level has not reached it yet).
 template <int VW>
 __device__ __forceinline__ bool finalize_row(const LevelCtx<VW> &c, size_t off, int row, const u64 (&acc)[VW],
                                              u64 (&seenv)[VW], u64 (&live_acc)[VW], const u64 (&lv)[VW], int &nzrows)
@@ -185,16 +186,8 @@ __device__ __forceinline__ bool finalize_row(const LevelCtx<VW> &c, size_t off, 
         nw[i] = acc[i] & ~seenv[i];
         any |= nw[i] != 0;
     }
-    vstore<VW>(c.nxt + off, nw);  // for level <= 15 this IS the record "first reached at hop level"
-    if (c.zero_count > 0) {
-        u64 z[VW];
-#pragma unroll
-        for (int i = 0; i < VW; ++i) z[i] = 0;
-#pragma unroll 1  // rare (hop 15 of a deep graph): keep it out of the way of the hot path's registers
-        for (int q = c.zero_first; q < c.zero_first + c.zero_count; ++q)
-            vstore<VW>(c.planes + (size_t)q * c.plane_stride + off, z);
-    }
     if (any) {
+        vstore<VW>(c.nxt + off, nw);  // for level <= 15 this IS the record "first reached at hop level"
 #pragma unroll
         for (int i = 0; i < VW; ++i) {
             seenv[i] |= nw[i];
@@ -264,7 +257,8 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
     int4 *s_lead = reinterpret_cast<int4 *>(s_dyn);                 // [JT][32]
     int4 *s_cols = s_lead + JT * 32;                                // [JT][32]
     unsigned char *s_done = reinterpret_cast<unsigned char *>(s_cols + JT * 32);  // [DONE_B][JT][32]
-    u32 *s_map = reinterpret_cast<u32 *>(s_done + GP_BFS_DONE_BATCHES * JT * 32);  // [batches][nzwords] or absent
+    unsigned char *s_tdone = s_done + GP_BFS_DONE_BATCHES * JT * 32;               // [DONE_B][JT] whole tile finished
+    u32 *s_map = reinterpret_cast<u32 *>(s_tdone + GP_BFS_DONE_BATCHES * JT);      // [batches][nzwords] or absent
     __shared__ u32 s_live32[GP_BFS_MAX_LANE_WORDS * 2];
     __shared__ int s_ent_base[GP_NUM_CLASSES + 1];
     __shared__ int s_slot_base[GP_NUM_CLASSES + 1];
@@ -324,6 +318,7 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
         s_cols[j * 32 + lane] = cols;
         for (int b = 0; b < GP_BFS_DONE_BATCHES; ++b) s_done[(b * JT + j) * 32 + lane] = lead.x < 0 ? 1 : 0;
     }
+    for (int i = tid; i < GP_BFS_DONE_BATCHES * JT; i += NT) s_tdone[i] = 0;
     grid_barrier_flags(p.bar + 0, gridDim.x, false, false, &s_bcast, &s_any, &s_notdone, &s_nzrows, s_queue, p.batches);
 
     int level = 1, max_level = 0;
@@ -334,7 +329,7 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
         auto frontier = [&](int l) -> u64 * {
             if (l == 0) return p.seeds;
             if (l <= GP_BFS_LEVEL_ARRAYS) return p.result + (size_t)l * p.plane_stride;
-            return (l & 1) ? p.fr_a : p.fr_b;
+            return l % 3 == 0 ? p.fr_a : (l % 3 == 1 ? p.fr_b : p.fr_c);
         };
         c.cur = frontier(level - 1);
         c.nxt = frontier(level);
@@ -342,10 +337,17 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
         c.planes = p.result + (size_t)(1 + GP_BFS_LEVEL_ARRAYS) * p.plane_stride;
         c.plane_stride = p.plane_stride;
         c.level = level;
-        // the deep-hop bit planes are first needed at hop 16: every row clears all of them one level ahead
-        // (deep graphs only; clearing them lazily left the high planes of a shallower run undefined)
-        c.zero_first = 0;
-        c.zero_count = level == GP_BFS_LEVEL_ARRAYS ? GP_BFS_PLANES : 0;
+        // Rows write their next-frontier words only when a lane is new, so every frontier array is cleared one
+        // level AHEAD of its use, by the whole grid with coalesced stores that nobody waits for (the host clears
+        // the arrays of hops 0 and 1).  The deep-hop bit planes, first needed at hop 16, are cleared at hop 15.
+        {
+            u64 *z = frontier(level + 1);
+            for (long long i = gtid; i < p.plane_stride; i += gthreads) z[i] = 0;
+            if (level == GP_BFS_LEVEL_ARRAYS) {
+                u64 *pl = c.planes;
+                for (long long i = gtid; i < (long long)GP_BFS_PLANES * p.plane_stride; i += gthreads) pl[i] = 0;
+            }
+        }
         const u64 *live_r = p.live + (level % 3) * GP_BFS_MAX_LANE_WORDS;
         u64 *live_w = p.live + ((level + 1) % 3) * GP_BFS_MAX_LANE_WORDS;
         u64 *live_z = p.live + ((level + 2) % 3) * GP_BFS_MAX_LANE_WORDS;
@@ -388,6 +390,8 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
             for (int j = warp; j < tiles_cta; j = __shfl_sync(FULL_MASK, j_next, 0)) {
                 if (lane == 0) j_next = atomicAdd(&s_queue[b], 1) + WARPS;
 
+            unsigned char *tdone = (j < JT && b < GP_BFS_DONE_BATCHES) ? s_tdone + b * JT + j : nullptr;
+            if (tdone != nullptr && *tdone) continue;  // every row of the tile holds all live lanes: nothing to do
             int4 lead, cols;
             unsigned char *dflag = nullptr;
             if (j < JT) {
@@ -401,7 +405,6 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
             const int sub = lane & ((1 << gsh) - 1);
             const bool leader = sub == 0 && lead.x >= 0;
             const int nch = (lead.y >> 8) & 0x3FFFFF;
-            const bool writes_empty = nch == 0 || ((lead.y >> 30) & 1);  // chunked rows: the first chunk writes the empty frontier
             const size_t off = ((size_t)b * n + (size_t)(lead.x >= 0 ? lead.x : 0)) * WB;
             // a row is "done" once every still-live lane has reached it: it never needs gathering again
             const bool done = dflag != nullptr ? dflag[lane - sub] != 0 : lead.x < 0;
@@ -412,8 +415,7 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
                 acc[i] = 0;
             }
             if (__all_sync(FULL_MASK, done)) {
-                // whole tile finished: only the empty next-frontier rows have to be written
-                if (leader && writes_empty) finalize_row<VW>(c, off, lead.x, acc, seenv, live_acc, lv, nzrows);
+                if (tdone != nullptr && lane == 0) *tdone = 1;
                 continue;
             }
             const int v[GP_SLOT_EDGES] = {cols.x, cols.y, cols.z, cols.w};
@@ -457,13 +459,8 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
             }
             if (!leader) continue;
             if (!eval) {
-                // done, or not done but no neighbour has anything new: the row's next frontier is empty
+                // done, or not done but no neighbour has anything new: the row's next frontier stays empty
                 if (!done) s_notdone = 1;  // flags are set as soon as a row completes, so this row still lacks lanes
-                if (writes_empty) {
-#pragma unroll
-                    for (int i = 0; i < VW; ++i) acc[i] = 0;
-                    finalize_row<VW>(c, off, lead.x, acc, seenv, live_acc, lv, nzrows);
-                }
                 continue;
             }
             bool need_row = false;
@@ -473,11 +470,6 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
                 // nothing left to reach here (monotone: seen grows, live shrinks): remember it
                 if (dflag != nullptr) dflag[lane] = 1;
                 else s_notdone = 1;  // untracked rows cannot prove the end of the search
-                if (writes_empty) {
-#pragma unroll
-                    for (int i = 0; i < VW; ++i) acc[i] = 0;
-                    finalize_row<VW>(c, off, lead.x, acc, seenv, live_acc, lv, nzrows);
-                }
             } else if (nch == 0) {
                 if (finalize_row<VW>(c, off, lead.x, acc, seenv, live_acc, lv, nzrows) || dflag == nullptr) s_notdone = 1;
                 else dflag[lane] = 1;
@@ -555,7 +547,8 @@ template <int WB, int NT, int MINB>
 constexpr size_t bfs_cache_bytes()
 {
     constexpr int tiles = bfs_cache_iters(NT, MINB) * (NT / 32);
-    return (size_t)tiles * 32 * (2 * sizeof(int4) + GP_BFS_DONE_BATCHES);
+    static_assert((tiles * GP_BFS_DONE_BATCHES) % 16 == 0, "the staged bitmaps that follow are read as uint4");
+    return (size_t)tiles * 32 * (2 * sizeof(int4) + GP_BFS_DONE_BATCHES) + (size_t)tiles * GP_BFS_DONE_BATCHES;
 }
 
 template <int WB, int NT, int MINB, bool MAPG>
@@ -663,6 +656,7 @@ void gp_msbfs_layout(gp_msbfs *h, int64_t num_anchors)
     h->seen = h->lane_buf + words;  // R[0]; R[l] = seen + l * words
     h->fr_a = h->seen + (size_t)GP_BFS_RESULT_ARRAYS * words;
     h->fr_b = h->fr_a + words;
+    h->fr_c = h->fr_b + words;
 }
 
 extern "C" int gp_msbfs_create(const gp_csr_t *csr, int64_t max_anchors, gp_msbfs_t **out)
@@ -693,9 +687,9 @@ extern "C" int gp_msbfs_create(const gp_csr_t *csr, int64_t max_anchors, gp_msbf
         }
     };
     // lane state, one allocation: seed frontier, then the result block R[0..31] (reached mask, 15
-    // first-reached-at-hop arrays, 16 deep-hop bit planes), then the ping-pong pair.  The seed frontier
-    // sits right before R[0] so one memset clears both.
-    alloc((void **)&h->lane_buf, (size_t)(1 + GP_BFS_RESULT_ARRAYS + 2) * words * sizeof(u64));
+    // first-reached-at-hop arrays, 16 deep-hop bit planes), then three rotating frontiers for hops >= 16.  The
+    // seed frontier sits right before R[0] and R[1] so one memset clears the three arrays a run starts from.
+    alloc((void **)&h->lane_buf, (size_t)(1 + GP_BFS_RESULT_ARRAYS + 3) * words * sizeof(u64));
     h->hub_capacity = csr->hub_capacity;
     alloc((void **)&h->hub_acc, (size_t)h->hub_capacity * (size_t)h->cap_words_per_node * sizeof(u64));
     alloc((void **)&h->hub_cnt, (size_t)h->hub_capacity * (size_t)h->cap_words_per_node * sizeof(u32));
@@ -767,7 +761,9 @@ extern "C" int gp_msbfs_run(gp_msbfs_t *h, const int64_t *d_anchors, int64_t num
         h->ran = true;
         return GP_OK;
     }
-    GP_CUDA_CHECK(cudaMemsetAsync(h->lane_buf, 0, 2 * words * sizeof(u64), stream));  // seeds + reached mask
+    // seeds, reached mask and the hop-1 frontier; every later frontier array is cleared by the kernel one level
+    // before it is written
+    GP_CUDA_CHECK(cudaMemsetAsync(h->lane_buf, 0, 3 * words * sizeof(u64), stream));
     if (!h->hub_zeroed) {
         // the kernel leaves these zeroed again (the finalising chunk resets its row's words)
         GP_CUDA_CHECK(cudaMemsetAsync(h->hub_acc, 0, (size_t)h->hub_capacity * h->cap_words_per_node * sizeof(u64), stream));
@@ -794,6 +790,7 @@ extern "C" int gp_msbfs_run(gp_msbfs_t *h, const int64_t *d_anchors, int64_t num
     p.seeds = h->seeds;
     p.fr_a = h->fr_a;
     p.fr_b = h->fr_b;
+    p.fr_c = h->fr_c;
     p.plane_stride = (long long)words;
     p.live = h->live;
     p.status = h->status;

@@ -34,12 +34,13 @@ struct gp_msbfs {
     int batches = 0;   // independent 64*wb-anchor batches
     bool ran = false;
 
-    u64 *lane_buf = nullptr; // one allocation: seeds | R[0..31] | ping | pong (pointers below are set per run)
+    u64 *lane_buf = nullptr; // one allocation: seeds | R[0..31] | 3 deep frontiers (pointers below are set per run)
     void *scratch = nullptr; // one allocation: live | bar | counters | status | nzmap (cleared by one memset per run)
     size_t scratch_bytes = 0;
     u64 *seen = nullptr;     // result block R[0..31], each [batches][N][wb]; R[0] = reached mask (gp_msbfs.cu)
-    u64 *fr_a = nullptr;     // frontier ping (hops >= 16)
-    u64 *fr_b = nullptr;     // frontier pong
+    u64 *fr_a = nullptr;     // three rotating frontiers for hops >= 16
+    u64 *fr_b = nullptr;
+    u64 *fr_c = nullptr;
     u64 *seeds = nullptr;    // hop-0 frontier
     u64 *live = nullptr;     // [3][GP_BFS_MAX_LANE_WORDS]
     u64 *hub_acc = nullptr;  // [batches][hub_capacity][wb] partial ORs of hub rows (zero between levels)

@@ -11,55 +11,12 @@
 // duration while the rows stream through the memory system (profiles/r02_notes.md), so gp_geodesic_run keeps the
 // copy fused in its epilogue kernel by default.
 #include "gp_msbfs.cuh"
+#include "gp_tma.cuh"
 
 namespace {
 
 constexpr int XC_STAGE_BYTES = 16384;
 constexpr int XC_MAX_STAGES = 8;
-
-__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(u32 bar, u32 count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-
-__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity)
-{
-    u32 done;
-    while (true) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) break;
-    }
-}
-
-__device__ __forceinline__ void bulk_load(u32 dst_smem, const void *src, u32 bytes, u32 bar, u64 policy)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
-            "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
-        : "memory");
-}
-
-__device__ __forceinline__ void bulk_store(void *dst, u32 src_smem, u32 bytes, u64 policy)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst),
-                 "r"(src_smem), "r"(bytes), "l"(policy)
-                 : "memory");
-}
 
 // One CTA per SM, one thread drives the pipeline.  Row blocks of R rows are dealt round-robin to the CTAs; block
 // i of a CTA lives in stage i % S.  Loads run S - 2 blocks ahead of the stores: before stage s is refilled the
@@ -73,8 +30,8 @@ xcopy_tma_kernel(const unsigned char *__restrict__ x, long long n, u32 row_bytes
     extern __shared__ __align__(128) unsigned char s_stage[];
     __shared__ __align__(8) u64 s_full[XC_MAX_STAGES];
     if (threadIdx.x != 0) return;
-    for (int s = 0; s < stages; ++s) mbar_init(smem_addr(&s_full[s]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < stages; ++s) gp_mbar_init(gp_smem_addr(&s_full[s]), 1);
+    gp_mbar_init_fence();
     u64 policy;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
 
@@ -83,20 +40,20 @@ xcopy_tma_kernel(const unsigned char *__restrict__ x, long long n, u32 row_bytes
     const long long first = blockIdx.x, step = gridDim.x;
     const long long cnt = nblk > first ? (nblk - first + step - 1) / step : 0;
     const bool contiguous = ldx_bytes == (long long)row_bytes;
-    const u32 stage0 = smem_addr(s_stage);
+    const u32 stage0 = gp_smem_addr(s_stage);
 
     auto load = [&](long long i) {
         const int s = (int)(i % stages);
         const long long r0 = (first + i * step) * R;
         const int rows = (int)(n - r0 < R ? n - r0 : R);
-        const u32 bar = smem_addr(&s_full[s]);
+        const u32 bar = gp_smem_addr(&s_full[s]);
         const u32 dst = stage0 + (u32)s * XC_STAGE_BYTES;
-        mbar_expect_tx(bar, (u32)rows * row_bytes);
+        gp_mbar_expect_tx(bar, (u32)rows * row_bytes);
         if (contiguous) {
-            bulk_load(dst, x + r0 * ldx_bytes, (u32)rows * row_bytes, bar, policy);
+            gp_bulk_load_hint(dst, x + r0 * ldx_bytes, (u32)rows * row_bytes, bar, policy);
         } else {
             for (int r = 0; r < rows; ++r)
-                bulk_load(dst + (u32)r * row_bytes, x + (r0 + r) * ldx_bytes, row_bytes, bar, policy);
+                gp_bulk_load_hint(dst + (u32)r * row_bytes, x + (r0 + r) * ldx_bytes, row_bytes, bar, policy);
         }
     };
 
@@ -109,11 +66,11 @@ xcopy_tma_kernel(const unsigned char *__restrict__ x, long long n, u32 row_bytes
             load(i + ahead);
         }
         const int s = (int)(i % stages);
-        mbar_wait(smem_addr(&s_full[s]), (u32)((i / stages) & 1));
+        gp_mbar_wait(gp_smem_addr(&s_full[s]), (u32)((i / stages) & 1));
         const long long r0 = (first + i * step) * R;
         const int rows = (int)(n - r0 < R ? n - r0 : R);
         const u32 src = stage0 + (u32)s * XC_STAGE_BYTES;
-        for (int r = 0; r < rows; ++r) bulk_store(out + (r0 + r) * ldo_bytes, src + (u32)r * row_bytes, row_bytes, policy);
+        for (int r = 0; r < rows; ++r) gp_bulk_store_hint(out + (r0 + r) * ldo_bytes, src + (u32)r * row_bytes, row_bytes, policy);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every row has reached global memory

@@ -289,7 +289,141 @@ def sharded_embed_host_shared(engine, edge_index: torch.Tensor, anchors, x: torc
     return out
 
 
-class PeerAssembly:
+class PushExchange:
+    """The exchange step as ONE kernel over NVLink peer memory (csrc/gp_exchange.cu): every rank packs its result
+    into its own exchange buffer and raises a flag on the peers; its row-streaming epilogue then gathers the peers'
+    packed row segments into shared memory with the bulk-copy engine, two row blocks ahead of the rows it writes.
+    No collective library call, no host round trip; the whole step (csr build + MS-BFS + exchange / decode) replays
+    from one CUDA graph.
+
+    Collective: every rank constructs it together and calls :meth:`run` once per step, in the same order.
+    Sharing one process (tests: several "ranks" on one GPU) is supported through ``peers=``.
+    """
+
+    def __init__(self, engine, group=None, world=None, rank=None):
+        import ctypes
+
+        from . import _lib
+        from ._lib import check
+
+        self.engine, self.group = engine, group
+        self.lib = _lib.load()
+        self.world = dist.get_world_size(group) if world is None else int(world)
+        self.rank = dist.get_rank(group) if rank is None else int(rank)
+        if self.world > 8:
+            raise ValueError("the push exchange covers the GPUs of one NVSwitch node (<= 8 ranks)")
+        self._h = c_void_p()
+        check(self.lib.gp_exchange_create(engine.bfs._h, self.world, self.rank, ctypes.byref(self._h)))
+        self._opened = []
+        self._pad = {}
+        if world is None and self.world > 1:  # one process per GPU: CUDA IPC mappings of the other ranks' buffers
+            handle = (ctypes.c_uint8 * 64)()
+            check(self.lib.gp_exchange_ipc_export(self._h, handle))
+            mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device="cuda")
+            every = torch.empty(self.world * 64, dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(every, mine, group=group)
+            every = every.cpu().view(self.world, 64)
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                buf = (ctypes.c_uint8 * 64)(*every[r].tolist())
+                ptr = c_void_p()
+                check(self.lib.gp_ipc_open(buf, ctypes.byref(ptr)))
+                self._opened.append(ptr.value)
+                check(self.lib.gp_exchange_set_peer(self._h, r, ptr))
+            dist.barrier(group=group)
+
+    def local_ptr(self) -> int:
+        import ctypes
+
+        from ._lib import check
+        ptr = c_void_p()
+        check(self.lib.gp_exchange_local_ptr(self._h, ctypes.byref(ptr)))
+        return ptr.value
+
+    def set_peer(self, rank: int, ptr: int):
+        from ._lib import check
+        check(self.lib.gp_exchange_set_peer(self._h, int(rank), c_void_p(ptr)))
+
+    def run(self, edge_index, anchors, x=None, out=None):
+        """Every rank returns the full float32 ``[N, F + K]`` block; this rank ran only its K/G anchors.
+        ``anchors`` holds all K anchors (identical on every rank).  Returns ``(out, self)``; ``self.item()`` is 1 if
+        some shard had hops > 15 (then redo the step with :func:`sharded_geodesic_features`)."""
+        from ._lib import check
+        from .device import _ptr, _stream
+
+        eng = self.engine
+        n = eng.csr.num_nodes
+        k = anchors.numel()
+        f = 0 if x is None else x.size(1)
+        if out is None:
+            out = torch.empty((n, f + k), dtype=torch.float32, device="cuda")
+        key = (anchors.data_ptr(), k)
+        if key not in self._pad:  # stable tensors = stable graph keys; a ragged K is padded with repeats of the last anchor
+            padded, per = pad_anchors(anchors, self.world)
+            shard = padded[self.rank * per:(self.rank + 1) * per].contiguous()
+            tmp = None if padded.numel() == k else torch.empty((n, f + padded.numel()), dtype=torch.float32, device="cuda")
+            self._pad = {key: (shard, per, tmp)}
+        shard, per, tmp = self._pad[key]
+        dst = out if tmp is None else tmp
+        edge_index = edge_index.contiguous()
+        if x is not None and x.stride(1) != 1:
+            x = x.contiguous()
+        eng.csr._edges, eng.bfs._anchors, eng.bfs.num_anchors, self._x = edge_index, shard, per, x
+        check(self.lib.gp_geodesic_run_exchange(eng.csr._h, eng.bfs._h, self._h, _ptr(edge_index), edge_index.size(1),
+                                                _ptr(shard), per, _ptr(x), f, x.stride(0) if x is not None and n > 1 else f,
+                                                _ptr(dst), dst.stride(0) if n > 1 else dst.size(1), f, _stream()))
+        if tmp is not None:
+            out.copy_(tmp[:, :f + k])
+        return out, self
+
+    def item(self) -> int:
+        """Syncs.  1 if the last step hit hops > 15 somewhere; raises if a peer's data never arrived."""
+        import ctypes
+
+        from ._lib import check
+        from .device import _stream
+        deep = ctypes.c_int32(0)
+        check(self.lib.gp_exchange_status(self._h, ctypes.byref(deep), _stream()))
+        return int(deep.value)
+
+    trace_events = ()
+
+    def trace(self):
+        """Diagnostics: microseconds from the start of the last exchange kernel (block 0) to: its share packed, every
+        peer's flag seen, and the last block leaving."""
+        import ctypes
+
+        from ._lib import check
+        st = (ctypes.c_uint64 * 8)()
+        check(self.lib.gp_exchange_trace(self._h, st))
+        t0 = st[0]
+        return {"packed_us": (st[1] - t0) / 1e3, "flags_seen_us": (st[2] - t0) / 1e3, "end_us": (st[3] - t0) / 1e3}
+
+    def close(self):
+        for p in self._opened:
+            self.lib.gp_ipc_close(c_void_p(p))
+        self._opened = []
+        if self._h:
+            self.lib.gp_exchange_free(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def PeerAssembly(engine, group=None):
+    """The device exchange of the sharded path: the push kernel (default) or round 1's pull-based peer decode
+    (``GP_EXCHANGE=pull``: pack + NCCL flag all-reduce + an epilogue that reads the peers' shards over NVLink)."""
+    if os.environ.get("GP_EXCHANGE", "push") == "pull":
+        return PullAssembly(engine, group)
+    return PushExchange(engine, group)
+
+
+class PullAssembly:
     """NVLink peer-to-peer assembly of the sharded result (the B200-native form of the exchange step).
 
     Instead of all-gathering result masks into a staging buffer and then decoding, every rank maps the

@@ -61,6 +61,7 @@ enum gp_cdist_mode {
 
 typedef struct gp_csr gp_csr_t;     /* de-duplicated digraph in CSR form          */
 typedef struct gp_msbfs gp_msbfs_t; /* multi-source BFS workspace + results       */
+typedef struct gp_exchange gp_exchange_t; /* NVLink push-exchange buffers of one rank */
 
 typedef struct gp_csr_info {
     int64_t num_nodes;
@@ -194,6 +195,40 @@ int gp_decode_peers(const uint64_t *const *h_rank_ptrs, int32_t num_ranks, int64
                     int64_t anchors_per_rank, int32_t batches, int32_t words_per_batch, int64_t plane_stride_words,
                     const float *d_x, int64_t num_features, int64_t ld_x, float *d_out, int64_t ld_out,
                     int64_t col_offset, gp_stream_t stream);
+
+/* ---- device exchange (gp_exchange.cu): pack -> gather from every rank -> decode as ONE cooperative kernel over
+ * NVLink peer memory, no collective library call.  It replaces the result hand-back of the reference's pool
+ * (utils.py:98-106) for anchor shards spread over the GPUs of one NVSwitch node: every rank packs its result into its
+ * own exchange buffer and raises a flag on the peers; the row-streaming epilogue then pulls the peers' packed row
+ * segments into shared memory with the bulk-copy engine (cp.async.bulk) two blocks ahead of the rows it writes.
+ *   gp_exchange_create      buffers of this rank: 2 step parities x 5 packed planes, plus flags.
+ *   gp_exchange_ipc_export  CUDA IPC handle of the buffer (open it in the other ranks with gp_ipc_open),
+ *   gp_exchange_local_ptr   or its plain device pointer (ranks sharing one process),
+ *   gp_exchange_set_peer    tell this rank where rank r's buffer is mapped.
+ *   gp_geodesic_run_exchange (async, COLLECTIVE: every rank calls it once per step, in the same order)
+ *                           gp_csr_build + gp_msbfs_run on this rank's `num_anchors` anchors + the fused kernel:
+ *                           d_out[:, 0:F] = x, d_out[:, col_offset + r*num_anchors + j] = feature of rank r's anchor
+ *                           j, for every rank r.  num_anchors must be the same multiple of 8 on every rank; d_out
+ *                           16-byte aligned, ld_out and col_offset multiples of 4.  Replays a CUDA graph.
+ *   gp_exchange_status      syncs.  *deep = 1 if some shard had hops > 15 in the last step (the 5-plane format
+ *                           cannot hold them: redo the step through gp_msbfs_planes / gp_decode_gathered);
+ *                           GP_ERR_CUDA if a peer's flag never arrived (bounded wait, ~3 s).                   */
+int gp_exchange_create(gp_msbfs_t *bfs, int32_t world, int32_t rank, gp_exchange_t **out);
+int gp_exchange_ipc_export(gp_exchange_t *xchg, uint8_t *handle64);
+int gp_exchange_local_ptr(gp_exchange_t *xchg, void **d_ptr);
+int gp_exchange_set_peer(gp_exchange_t *xchg, int32_t rank, void *d_ptr);
+int gp_geodesic_run_exchange(gp_csr_t *csr, gp_msbfs_t *bfs, gp_exchange_t *xchg, const int64_t *d_edge_index,
+                             int64_t num_edges, const int64_t *d_anchors, int64_t num_anchors, const float *d_x,
+                             int64_t num_features, int64_t ld_x, float *d_out, int64_t ld_out, int64_t col_offset,
+                             gp_stream_t stream);
+/* async, COLLECTIVE.  The fused exchange / decode kernel alone, after the caller's own gp_msbfs_run. */
+int gp_exchange_run(gp_exchange_t *xchg, const float *d_x, int64_t num_features, int64_t ld_x, float *d_out,
+                    int64_t ld_out, int64_t col_offset, gp_stream_t stream);
+int gp_exchange_status(gp_exchange_t *xchg, int32_t *deep, gp_stream_t stream);
+/* Diagnostics, syncs the device: globaltimer stamps (ns) of the last step: [0] block 0 starts, [1] block 0 has packed
+ * its share, [2] block 0 has seen every peer's flag, [3] the last block leaves. */
+int gp_exchange_trace(gp_exchange_t *xchg, uint64_t *h_stamps8);
+int gp_exchange_free(gp_exchange_t *xchg);
 
 /* async.  Stand-alone epilogue from a uint16 hop matrix (utils.py:73,76,125). */
 int gp_normalize_into(const uint16_t *d_dist, int64_t num_nodes, int64_t num_anchors, int64_t ld_dist,

@@ -433,3 +433,48 @@ def test_peer_decode_variants_on_one_gpu(dev, k, f):
         assert torch.equal(out[:, :f], x), ranks
         for r in range(ranks):
             assert torch.equal(out[:, f + r * k: f + (r + 1) * k], want[:, f:]), (ranks, r)
+
+
+@pytest.mark.parametrize("world,k,f", [(2, 64, 20), (4, 512, 500), (3, 48, 8), (8, 128, 4)])
+def test_push_exchange_virtual_ranks_on_one_gpu(dev, monkeypatch, world, k, f):
+    """gp_exchange.cu with `world` virtual ranks in ONE process on one GPU (plain device pointers instead of IPC
+    mappings): every rank runs its anchor shard, then the fused pack / push / decode kernels run side by side on
+    their own streams (partial grids so all of them are resident) and every rank's [N, F + K] matrix must equal the
+    single-GPU result bit for bit.  Two steps: both slot parities and the epoch protocol."""
+    from ctypes import c_void_p
+
+    from graphpope_b200 import _lib, distributed as gpd
+    monkeypatch.setenv("GP_XCHG_GRID", "24")
+    lib = _lib.load()
+    n = 3000
+    ei = synth.chung_lu_symmetric(n, 18000, 2.2, seed=5)
+    ei = np.concatenate([ei, synth.random_digraph(n, 700, seed=6)], axis=1)
+    per = k // world
+    ei_d = torch.as_tensor(ei).cuda()
+    x = torch.randn(n, f, device="cuda")
+    engines = [dev.GeodesicEngine(n, ei.shape[1], per) for _ in range(world)]
+    xch = [gpd.PushExchange(engines[r], world=world, rank=r) for r in range(world)]
+    for r in range(world):
+        for q in range(world):
+            if q != r:
+                xch[r].set_peer(q, xch[q].local_ptr())
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    for step in range(2):
+        anchors = np.random.default_rng(step).integers(0, n, k)
+        a_d = torch.as_tensor(anchors).cuda()
+        want = dev.GeodesicEngine(n, ei.shape[1], k).run(ei_d, a_d, x).clone()
+        outs = [torch.full((n, f + k), float("nan"), device="cuda") for _ in range(world)]
+        for r in range(world):
+            engines[r].csr.build(ei_d)
+            engines[r].bfs.run(a_d[r * per:(r + 1) * per].contiguous())
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                _lib.check(lib.gp_exchange_run(xch[r]._h, c_void_p(x.data_ptr()), f, f, c_void_p(outs[r].data_ptr()),
+                                               f + k, f, c_void_p(streams[r].cuda_stream)))
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert xch[r].item() == 0
+            assert torch.equal(outs[r], want), (step, r)
+    for e in xch:
+        e.close()
