@@ -119,8 +119,10 @@ struct HostCtx {
     float *d_feat = nullptr;
     uint16_t *d_hops = nullptr;
     cudaStream_t stream = nullptr;
-    void *h_stage = nullptr;  // pinned staging for pageable outputs
-    size_t h_stage_bytes = 0;
+    // pageable outputs: two pinned 8 MB ring slots; the GPU fills one while the host scatters the other into the
+    // caller's rows (no N*K*4-byte pinned allocation, no second pass over the whole block)
+    float *h_ring[2] = {nullptr, nullptr};
+    cudaEvent_t ring_ev[2] = {nullptr, nullptr};
 
     void release()
     {
@@ -597,16 +599,7 @@ extern "C" int gp_geodesic_embed_host(const int64_t *h_edge_index, int64_t num_e
                                             sizeof(float) * (size_t)num_anchors, sizeof(float) * (size_t)num_anchors,
                                             (size_t)num_nodes, cudaMemcpyDeviceToHost, s));
         } else {
-            const size_t need = sizeof(float) * (size_t)(num_nodes * num_anchors);
-            if (c.h_stage_bytes < need) {
-                if (c.h_stage) cudaFreeHost(c.h_stage);
-                c.h_stage = nullptr;
-                c.h_stage_bytes = 0;
-                GP_CUDA_CHECK(cudaMallocHost(&c.h_stage, need));
-                c.h_stage_bytes = need;
-            }
-            GP_CUDA_CHECK(cudaMemcpyAsync(c.h_stage, c.d_feat, need, cudaMemcpyDeviceToHost, s));
-            staged = true;
+            staged = true;  // ring-buffered below, after the hop matrix has been queued behind the block
         }
         if (h_hops)
             GP_CUDA_CHECK(cudaMemcpyAsync(h_hops, c.d_hops, sizeof(uint16_t) * (size_t)(num_nodes * num_anchors),
@@ -614,10 +607,36 @@ extern "C" int gp_geodesic_embed_host(const int64_t *h_edge_index, int64_t num_e
     }
     // concat_into_features (utils.py:129-135): x goes into columns [0, F) on the host, while the
     // GPU works.
-    if (h_x != nullptr) copy_rows_parallel(h_x, num_features, h_out, ld_out, num_nodes, num_features);
     if (staged) {
-        GP_CUDA_CHECK(cudaStreamSynchronize(s));
-        copy_rows_parallel((const float *)c.h_stage, num_anchors, h_out + col_offset, ld_out, num_nodes, num_anchors);
+        // Pageable h_out: rows [r0, r1) of the device block go to a pinned ring slot (one contiguous DMA), the host
+        // scatters the previous slot into the caller's rows meanwhile.  The copy of x runs after the first two DMAs
+        // have been queued, so it overlaps them as well.
+        constexpr size_t RING_BYTES = 8u << 20;
+        for (int i = 0; i < 2; ++i) {
+            if (c.h_ring[i] == nullptr) GP_CUDA_CHECK(cudaMallocHost((void **)&c.h_ring[i], RING_BYTES));
+            if (c.ring_ev[i] == nullptr) GP_CUDA_CHECK(cudaEventCreateWithFlags(&c.ring_ev[i], cudaEventDisableTiming));
+        }
+        const int64_t rows_per = std::max<int64_t>(1, (int64_t)(RING_BYTES / (sizeof(float) * (size_t)num_anchors)));
+        const int64_t chunks = gp_ceil_div(num_nodes, rows_per);
+        auto enqueue = [&](int64_t i) -> int {
+            const int64_t r0 = i * rows_per, r1 = std::min(num_nodes, r0 + rows_per);
+            GP_CUDA_CHECK(cudaMemcpyAsync(c.h_ring[i & 1], c.d_feat + r0 * num_anchors,
+                                          sizeof(float) * (size_t)((r1 - r0) * num_anchors), cudaMemcpyDeviceToHost, s));
+            GP_CUDA_CHECK(cudaEventRecord(c.ring_ev[i & 1], s));
+            return GP_OK;
+        };
+        GP_REQUIRE((size_t)num_anchors * sizeof(float) <= RING_BYTES, GP_ERR_UNSUPPORTED,
+                   "gp_geodesic_embed_host: more than %zu anchors need a pinned output buffer", RING_BYTES / sizeof(float));
+        for (int64_t i = 0; i < std::min<int64_t>(2, chunks); ++i) GP_TRY(enqueue(i));
+        if (h_x != nullptr) copy_rows_parallel(h_x, num_features, h_out, ld_out, num_nodes, num_features);
+        for (int64_t i = 0; i < chunks; ++i) {
+            const int64_t r0 = i * rows_per, r1 = std::min(num_nodes, r0 + rows_per);
+            GP_CUDA_CHECK(cudaEventSynchronize(c.ring_ev[i & 1]));
+            copy_rows_parallel(c.h_ring[i & 1], num_anchors, h_out + r0 * ld_out + col_offset, ld_out, r1 - r0, num_anchors);
+            if (i + 2 < chunks) GP_TRY(enqueue(i + 2));
+        }
+    } else if (h_x != nullptr) {
+        copy_rows_parallel(h_x, num_features, h_out, ld_out, num_nodes, num_features);
     }
     gp_msbfs_stats_t local;
     GP_TRY(gp_msbfs_stats(c.bfs, stats ? stats : &local, s));  // synchronises and reports device errors

@@ -474,6 +474,147 @@ __global__ void minmax_init_kernel(int *cmin, int *cmax, long long k)
     }
 }
 
+// ---------------------------------------------------------------- any embedding width
+// The tensor-core kernel stages operands in 64-element K chunks and is instantiated for D = 64 and 128 (the
+// reference writes 128-d tables, generate_node2vec_embedding.py:23).  utils.py:174 accepts any width, so:
+//   D < 128, D not 64  rows are zero-padded to 64 / 128 in stream-ordered scratch (zeros change neither dot products
+//                      nor norms) and take the tensor-core path;
+//   D > 128            a plain fp32 kernel (shared-memory tiles, difference form for euclidean: no cancellation).
+__global__ void pad_rows_kernel(const float *__restrict__ src, long long rows, int d, int dp, float *__restrict__ dst)
+{
+    const long long total = rows * dp;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long r = i / dp;
+        const int c = (int)(i - r * dp);
+        dst[i] = c < d ? src[r * d + c] : 0.0f;
+    }
+}
+
+constexpr int CG_TILE = 64, CG_KC = 16;
+
+__global__ void __launch_bounds__(256)
+cdist_generic_kernel(CdistParams p, int write_out, int track_minmax)
+{
+    __shared__ float s_x[CG_KC][CG_TILE + 1], s_a[CG_KC][CG_TILE + 1];
+    __shared__ int s_min[CG_TILE], s_max[CG_TILE];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // thread = 4 rows (ty) x 4 columns (tx)
+    const long long r0 = (long long)blockIdx.x * CG_TILE, c0 = (long long)blockIdx.y * CG_TILE;
+    if (threadIdx.x < CG_TILE) {
+        s_min[threadIdx.x] = f2ord(INFINITY);
+        s_max[threadIdx.x] = f2ord(-INFINITY);
+    }
+    float acc[4][4], xx[4], aa[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        xx[i] = aa[i] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    }
+    const bool euclid = p.mode == GP_CDIST_EUCLIDEAN;
+    for (long long k0 = 0; k0 < p.d; k0 += CG_KC) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < CG_TILE * CG_KC; i += 256) {
+            const int rr = i / CG_KC, kk = i % CG_KC;
+            const bool kin = k0 + kk < p.d;
+            s_x[kk][rr] = (kin && r0 + rr < p.n) ? p.emb[(size_t)(r0 + rr) * p.d + k0 + kk] : 0.0f;
+            s_a[kk][rr] = (kin && c0 + rr < p.k) ? p.anc[(size_t)(c0 + rr) * p.d + k0 + kk] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < CG_KC; ++kk) {
+            float xv[4], av[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                xv[i] = s_x[kk][ty * 4 + i];
+                av[i] = s_a[kk][tx * 4 + i];
+                xx[i] = fmaf(xv[i], xv[i], xx[i]);
+                aa[i] = fmaf(av[i], av[i], aa[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (euclid) {
+                        const float df = xv[i] - av[j];
+                        acc[i][j] = fmaf(df, df, acc[i][j]);
+                    } else {
+                        acc[i][j] = fmaf(xv[i], av[j], acc[i][j]);
+                    }
+                }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const long long c = c0 + tx * 4 + j;
+        float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long r = r0 + ty * 4 + i;
+            float v;
+            if (euclid) {
+                v = sqrtf(acc[i][j]);
+            } else {
+                const float ix = xx[i] > 0.0f ? rsqrtf(xx[i]) : 0.0f, ia = aa[j] > 0.0f ? rsqrtf(aa[j]) : 0.0f;
+                const float sim = acc[i][j] * ix * ia;
+                v = p.mode == GP_CDIST_COSINE_SIMILARITY ? sim : fminf(fmaxf(1.0f - sim, 0.0f), 2.0f);
+            }
+            if (r < p.n && c < p.k) {
+                if (write_out) p.out[(size_t)r * p.ld_out + p.col_offset + c] = v;
+                mn = fminf(mn, v);
+                mx = fmaxf(mx, v);
+            }
+        }
+        if (track_minmax && mn <= mx) {
+            atomicMin(&s_min[tx * 4 + j], f2ord(mn));
+            atomicMax(&s_max[tx * 4 + j], f2ord(mx));
+        }
+    }
+    if (track_minmax) {
+        __syncthreads();
+        if (threadIdx.x < CG_TILE && c0 + threadIdx.x < p.k && s_min[threadIdx.x] <= s_max[threadIdx.x]) {
+            atomicMin(reinterpret_cast<int *>(p.colmin) + c0 + threadIdx.x, s_min[threadIdx.x]);
+            atomicMax(reinterpret_cast<int *>(p.colmax) + c0 + threadIdx.x, s_max[threadIdx.x]);
+        }
+    }
+}
+
+// MinMaxScaler.transform in place (utils.py:176), same arithmetic as the fused path of cdist_kernel.
+__global__ void minmax_scale_kernel(CdistParams p)
+{
+    const long long total = p.n * p.k;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long r = i / p.k, c = i - r * p.k;
+        const float dmin = ord2f(reinterpret_cast<const int *>(p.colmin)[c]);
+        const float dmax = ord2f(reinterpret_cast<const int *>(p.colmax)[c]);
+        float range = dmax - dmin;
+        if (range < 10.0f * 1.1920929e-07f) range = 1.0f;
+        const float scale = __fdiv_rn(1.0f, range), shift = __fsub_rn(0.0f, __fmul_rn(dmin, scale));
+        float *o = p.out + (size_t)r * p.ld_out + p.col_offset + c;
+        *o = __fadd_rn(__fmul_rn(*o, scale), shift);
+    }
+}
+
+cudaMemPool_t cdist_pool()
+{
+    // stream-ordered scratch from a pool of our own that keeps its memory across synchronisations
+    // (the default pool hands it back to the driver at every sync, ~100 us per call)
+    static cudaMemPool_t pool = nullptr;
+    if (pool == nullptr) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) return nullptr;
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    return pool;
+}
+
 size_t cdist_smem_bytes(int d, int n_pad)
 {
     const size_t b = (size_t)(d / CD_KCHUNK) * n_pad * 128, a = (size_t)(d / CD_KCHUNK) * CD_TILE_M * 128;
@@ -494,11 +635,52 @@ extern "C" int gp_cdist_minmax(const float *d_emb, const float *d_anchor_emb, in
     if (num_nodes == 0 || num_anchors == 0) return GP_OK;
     GP_REQUIRE(d_emb != nullptr && d_anchor_emb != nullptr && d_out != nullptr, GP_ERR_INVALID,
                "gp_cdist_minmax: NULL argument");
-    GP_REQUIRE(dim == 64 || dim == 128, GP_ERR_UNSUPPORTED,
-               "gp_cdist_minmax: embedding dimension %lld not supported by this build (64 or 128; the reference "
-               "uses 128, generate_node2vec_embedding.py:23)", (long long)dim);
-    GP_REQUIRE((reinterpret_cast<uintptr_t>(d_emb) & 15u) == 0 && (reinterpret_cast<uintptr_t>(d_anchor_emb) & 15u) == 0,
-               GP_ERR_INVALID, "gp_cdist_minmax: embeddings must be 16-byte aligned");
+    cudaMemPool_t pool = cdist_pool();
+    GP_REQUIRE(pool != nullptr, GP_ERR_CUDA, "gp_cdist_minmax: cannot create the scratch memory pool");
+    if (dim != 64 && dim != 128 && dim < 128) {
+        // zero-pad the rows to the next instantiated width and take the tensor-core path
+        const int dp = dim < 64 ? 64 : 128;
+        float *emb_p = nullptr, *anc_p = nullptr;
+        GP_CUDA_CHECK(cudaMallocFromPoolAsync((void **)&emb_p, sizeof(float) * (size_t)num_nodes * dp, pool, stream));
+        GP_CUDA_CHECK(cudaMallocFromPoolAsync((void **)&anc_p, sizeof(float) * (size_t)num_anchors * dp, pool, stream));
+        GP_LAUNCH(pad_rows_kernel, gp_sm_count() * 8, 256, 0, stream, d_emb, (long long)num_nodes, (int)dim, dp, emb_p);
+        GP_LAUNCH(pad_rows_kernel, gp_sm_count() * 8, 256, 0, stream, d_anchor_emb, (long long)num_anchors, (int)dim, dp, anc_p);
+        const int rc = gp_cdist_minmax(emb_p, anc_p, num_nodes, num_anchors, dp, mode, apply_minmax, d_out, ld_out,
+                                       col_offset, stream_);
+        GP_CUDA_CHECK(cudaFreeAsync(emb_p, stream));
+        GP_CUDA_CHECK(cudaFreeAsync(anc_p, stream));
+        return rc;
+    }
+    if (dim > 128) {
+        CdistParams g;
+        g.emb = d_emb;
+        g.anc = d_anchor_emb;
+        g.n = num_nodes;
+        g.k = num_anchors;
+        g.d = dim;
+        g.mode = mode;
+        g.out = d_out;
+        g.ld_out = ld_out;
+        g.col_offset = col_offset;
+        g.colmin = g.colmax = nullptr;
+        g.best = nullptr;
+        int *mm = nullptr;
+        if (apply_minmax) {
+            GP_CUDA_CHECK(cudaMallocFromPoolAsync((void **)&mm, sizeof(int) * 2 * (size_t)num_anchors, pool, stream));
+            g.colmin = reinterpret_cast<float *>(mm);
+            g.colmax = reinterpret_cast<float *>(mm + num_anchors);
+            GP_LAUNCH(minmax_init_kernel, (unsigned)gp_ceil_div(num_anchors, 256), 256, 0, stream, mm, mm + num_anchors,
+                      num_anchors);
+        }
+        const dim3 ggrid((unsigned)gp_ceil_div(num_nodes, CG_TILE), (unsigned)gp_ceil_div(num_anchors, CG_TILE));
+        GP_LAUNCH(cdist_generic_kernel, ggrid, 256, 0, stream, g, 1, apply_minmax ? 1 : 0);
+        if (apply_minmax) {
+            GP_LAUNCH(minmax_scale_kernel, gp_sm_count() * 8, 256, 0, stream, g);
+            GP_CUDA_CHECK(cudaFreeAsync(mm, stream));
+        }
+        GP_CUDA_CHECK(cudaGetLastError());
+        return GP_OK;
+    }
     CdistParams p;
     p.emb = d_emb;
     p.anc = d_anchor_emb;
@@ -537,20 +719,6 @@ extern "C" int gp_cdist_minmax(const float *d_emb, const float *d_anchor_emb, in
         // MinMaxScaler (utils.py:175-176) without a second trip of the N x K block through HBM: pass 1
         // computes the block and keeps only the per-column min / max, pass 2 recomputes it (the node
         // table is L2 resident by then) and writes the scaled values.
-        // stream-ordered scratch from a pool of our own that keeps its memory across synchronisations
-        // (the default pool hands it back to the driver at every sync, ~100 us per call)
-        static cudaMemPool_t pool = nullptr;
-        if (pool == nullptr) {
-            int dev = 0;
-            GP_CUDA_CHECK(cudaGetDevice(&dev));
-            cudaMemPoolProps props = {};
-            props.allocType = cudaMemAllocationTypePinned;
-            props.location.type = cudaMemLocationTypeDevice;
-            props.location.id = dev;
-            GP_CUDA_CHECK(cudaMemPoolCreate(&pool, &props));
-            uint64_t keep = ~0ull;
-            GP_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        }
         int *mm = nullptr;
         GP_CUDA_CHECK(cudaMallocFromPoolAsync((void **)&mm, sizeof(int) * 2 * (size_t)num_anchors, pool, stream));
         p.colmin = reinterpret_cast<float *>(mm);

@@ -341,7 +341,13 @@ def kmeans(table: torch.Tensor, num_clusters: int, n_init: int = 10, max_iter: i
     """
     lib = _lib.require_cuda()
     x = table.to(device="cuda", dtype=torch.float32).contiguous()
-    n, d = x.shape
+    n, d_in = x.shape
+    if d_in > 128:
+        raise ValueError("device k-means covers embedding widths up to 128 (the reference writes 128-d tables)")
+    if d_in not in (64, 128):
+        # the kernels are instantiated for 64 and 128 columns: zero columns change neither distances nor means
+        x = torch.nn.functional.pad(x, (0, (64 if d_in < 64 else 128) - d_in)).contiguous()
+    d = x.size(1)
     k = int(num_clusters)
     if k <= 0 or k > n:
         raise ValueError(f"n_clusters={k} must be in [1, {n}]")
@@ -371,5 +377,5 @@ def kmeans(table: torch.Tensor, num_clusters: int, n_init: int = 10, max_iter: i
         check(lib.gp_kmeans_assign(_ptr(x), _ptr(centers), n, k, d, _ptr(best), _stream()))
         inertia = float((best >> 32).to(torch.int32).view(torch.float32).double().sum().item())
         if result is None or inertia < result[1]:
-            result = (centers.clone(), inertia, iters)
+            result = (centers[:, :d_in].clone(), inertia, iters)
     return result

@@ -354,7 +354,9 @@ def attach_node2vec(data, dataset, num_anchor_nodes, sampling_method, distance_f
     else:
         # anything but 'stochastic' means KMeans centres (utils.py:168-170).  Lloyd + k-means++ run on the
         # device (tensor-core assignment); GRAPHPOPE_KMEANS=sklearn keeps the reference's scikit-learn call.
-        if os.environ.get("GRAPHPOPE_KMEANS", "device") == "sklearn" or table.size(1) not in (64, 128):
+        # (tables wider than 128 columns keep scikit-learn for the clustering; the pairwise block below runs on the
+        # device for any width)
+        if os.environ.get("GRAPHPOPE_KMEANS", "device") == "sklearn" or table.size(1) > 128:
             from sklearn.cluster import KMeans
 
             kmeans = KMeans(n_clusters=num_anchor_nodes).fit(table.numpy())

@@ -89,3 +89,33 @@ def test_shard_bounds():
     assert per == 8 and len(padded) == 32 and padded[:10].tolist() == list(range(10)) and set(padded[10:]) == {9}
     padded, per = gpd.pad_anchors(torch.arange(1024), 8)
     assert per == 128 and padded.numel() == 1024
+
+
+def _shared_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n, f, k = 1000, 7, 10
+        shared = gpd.SharedHostMatrix(n, f + k, register=False)  # no CUDA here: the mapping alone
+        lo, hi = gpd.shard_bounds(k, world, rank)
+        r0, r1 = gpd.row_slice(n, world, rank)
+        x = torch.arange(n * f, dtype=torch.float32).view(n, f)
+        shared.tensor[:, f + lo:f + hi] = float(rank + 1)       # this rank's column block
+        shared.tensor[r0:r1, :f] = x[r0:r1]                     # this rank's rows of x
+        shared.barrier()
+        want = torch.cat([x, torch.cat([torch.full((n, gpd.shard_bounds(k, world, r)[1] - gpd.shard_bounds(k, world, r)[0]),
+                                                   float(r + 1)) for r in range(world)], 1)], 1)
+        ret[rank] = bool(torch.equal(shared.tensor, want)) and not os.path.exists(shared.path)
+        shared.barrier()
+        shared.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_node_shared_host_matrix_world_size_2():
+    """SharedHostMatrix: two processes map the same POSIX shared-memory matrix; each writes its column block and its
+    row range of x; after the barrier both see the whole [N, F + K] matrix and the name is unlinked."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ret = mp.Manager().dict()
+    mp.spawn(_shared_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert dict(ret) == {0: True, 1: True}

@@ -478,3 +478,17 @@ def test_push_exchange_virtual_ranks_on_one_gpu(dev, monkeypatch, world, k, f):
             assert torch.equal(outs[r], want), (step, r)
     for e in xch:
         e.close()
+
+
+def test_pageable_output_ring_equals_pinned_output(dev):
+    """gp_geodesic_embed_host with a PAGEABLE output goes through two pinned 8 MB ring slots (three chunks here);
+    the result must equal the strided-DMA path taken for a pinned output, x columns included."""
+    n, k, f = 70000, 64, 12
+    ei = synth.chung_lu_symmetric(n, 400000, 2.1, seed=11)
+    anchors = np.random.default_rng(3).integers(0, n, k)
+    x = torch.randn(n, f)
+    pinned = torch.empty(n, f + k).pin_memory()
+    dev.geodesic_embed_host(torch.as_tensor(ei), n, anchors, x, out=pinned)
+    pageable = torch.full((n, f + k), float("nan"))
+    dev.geodesic_embed_host(torch.as_tensor(ei), n, anchors, x, out=pageable)
+    assert torch.equal(pageable, pinned) and torch.equal(pageable[:, :f], x)

@@ -105,10 +105,14 @@ def test_attach_node2vec_end_to_end(dev, golden_small, tmp_path, monkeypatch):
         assert np.allclose(got.numpy(), want, rtol=RTOL, atol=2e-5)
 
 
-def test_unsupported_dim_is_loud(dev):
+def test_bad_arguments_are_loud(dev):
     from graphpope_b200._lib import GraphpopeError
     with pytest.raises(GraphpopeError):
-        dev.cdist_minmax(torch.zeros(10, 100), torch.zeros(2, 100), "euclidean")
+        dev.cdist_minmax(torch.zeros(10, 100), torch.zeros(2, 100), 7)  # unknown mode
+    with pytest.raises(ValueError):
+        dev.cdist_minmax(torch.zeros(10, 100), torch.zeros(2, 64), "euclidean")  # widths differ
+    with pytest.raises(ValueError):
+        dev.kmeans(torch.zeros(300, 200), 4)  # device k-means covers widths up to 128
 
 
 def test_kmeans_assign_matches_fp32_argmin():
@@ -149,3 +153,37 @@ def test_device_kmeans_inertia_close_to_sklearn():
         # the reported inertia is the objective of the returned centres
         d2 = torch.cdist(torch.as_tensor(table).double(), got_c.cpu().double()).pow(2).min(dim=1).values.sum().item()
         assert abs(d2 - got_inertia) <= 1e-3 * d2
+
+
+@pytest.mark.parametrize("fn", ["distance", "similarity", "euclidean"])
+@pytest.mark.parametrize("n,k,d", [(700, 40, 100), (513, 70, 32), (300, 33, 7), (900, 80, 200), (257, 300, 130)])
+def test_any_embedding_width(dev, fn, n, k, d):
+    """utils.py:174 accepts any embedding width: widths below 128 are zero-padded onto the tensor-core kernel,
+    wider tables take the plain fp32 kernel; raw and MinMax-scaled blocks against the sklearn restatement."""
+    from oracle import node2vec as nv
+    rng = np.random.default_rng(n + k + d)
+    emb = rng.standard_normal((n, d)).astype(np.float32)
+    idx = rng.integers(0, n, k)
+    anc = emb[idx].copy()
+    scale = float(np.sqrt(2 * d)) if fn == "euclidean" else 1.0
+    got = dev.cdist_minmax(torch.as_tensor(emb), torch.as_tensor(anc), fn, apply_minmax=False).cpu().numpy()
+    want = nv.PAIRWISE[fn](emb, anc)
+    # the dropped lo*lo term of the split-bf16 product is ~2^-16 of |x||a| whatever the width; short rows do not
+    # average it down, so the absolute floor is wider for them (the relative bar of north_star stays 1e-4)
+    floor = (1e-5 if d >= 32 else 5e-5) * scale
+    assert np.allclose(got, want, rtol=RTOL, atol=floor), np.abs(got - want).max()
+    got = dev.cdist_minmax(torch.as_tensor(emb), torch.as_tensor(anc), fn, apply_minmax=True).cpu().numpy()
+    lo, hi = want.min(axis=0), want.max(axis=0)
+    rng_ = np.where(hi - lo < 10 * np.finfo(np.float32).eps, 1.0, hi - lo)
+    assert np.allclose(got, (want - lo) / rng_, rtol=RTOL, atol=3e-5 if d >= 32 else 1e-4), np.abs(got - (want - lo) / rng_).max()
+
+
+def test_kmeans_on_a_100_column_table(dev):
+    """Device k-means pads a 100-column table to 128; centres come back 100 wide and cluster a separable table."""
+    rng = np.random.default_rng(0)
+    centres = rng.standard_normal((8, 100)).astype(np.float32) * 6
+    x = (centres[rng.integers(0, 8, 4000)] + rng.standard_normal((4000, 100)).astype(np.float32) * 0.3)
+    got, inertia, _ = dev.kmeans(torch.as_tensor(x), 8, n_init=3, seed=1)
+    assert tuple(got.shape) == (8, 100)
+    d = torch.cdist(got.cpu(), torch.as_tensor(centres))
+    assert float(d.min(dim=1).values.max()) < 0.2 and inertia < 4000 * 100 * 0.3 ** 2 * 1.2
