@@ -64,6 +64,7 @@ SIGNATURES = {
     "gp_csr_build": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "gp_csr_info": (c_int, [c_void_p, POINTER(CsrInfo), c_void_p]),
     "gp_csr_export": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "gp_csr_trace_ms": (c_int, [c_void_p, POINTER(ctypes.c_float), c_int32, POINTER(c_int32)]),
     "gp_csr_free": (c_int, [c_void_p]),
     "gp_msbfs_create": (c_int, [c_void_p, c_int64, POINTER(c_void_p)]),
     "gp_msbfs_run": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
@@ -96,11 +97,16 @@ SIGNATURES = {
                                          c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p]),
     "gp_exchange_run": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p]),
     "gp_exchange_status": (c_int, [c_void_p, POINTER(c_int32), c_void_p]),
+    "gp_exchange_set_grid": (c_int, [c_void_p, c_int32]),
     "gp_exchange_trace": (c_int, [c_void_p, c_void_p]),
     "gp_exchange_free": (c_int, [c_void_p]),
     "gp_normalize_into": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p]),
     "gp_geodesic_embed_host": (c_int, [c_void_p, c_int64, c_int64, c_uint32, c_void_p, c_int64, c_void_p,
                                        c_int64, c_void_p, c_int64, c_int64, c_void_p, POINTER(MsbfsStats)]),
+    "gp_ctx_create": (c_int, [POINTER(c_void_p)]),
+    "gp_ctx_free": (c_int, [c_void_p]),
+    "gp_geodesic_embed_host_ctx": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_uint32, c_void_p, c_int64, c_void_p,
+                                           c_int64, c_void_p, c_int64, c_int64, c_void_p, POINTER(MsbfsStats)]),
     "gp_host_concat": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64]),
     "gp_block_to_host": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p]),
     "gp_degree": (c_int, [c_void_p, c_void_p, c_void_p]),

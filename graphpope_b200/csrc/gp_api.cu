@@ -14,6 +14,9 @@
 #include <thread>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+#include <unistd.h>
+
 bool gp_is_capturing();
 bool gp_xcopy_tma_ok(const float *d_x, int64_t num_features, int64_t ld_x, const float *d_out, int64_t ld_out);
 int gp_launch_xcopy_tma(const float *d_x, int64_t num_nodes, int64_t num_features, int64_t ld_x, float *d_out,
@@ -62,6 +65,48 @@ int gp_sm_count()
     return g_sm_count;
 }
 
+const GpEnv &gp_env()
+{
+    static const GpEnv env = [] {
+        auto geti = [](const char *name, int dflt) {
+            const char *v = getenv(name);
+            return v ? atoi(v) : dflt;
+        };
+        GpEnv e;
+        e.use_graph = geti("GP_USE_GRAPH", 1);
+        e.xcopy_overlap = geti("GP_XCOPY_OVERLAP", 0);
+        e.xcopy_stages = geti("GP_XCOPY_STAGES", 4);
+        e.xcopy_grid = geti("GP_XCOPY_GRID", 0);
+        e.bfs_cfg = geti("GP_BFS_CFG", -1);
+        e.bfs_no_map = getenv("GP_BFS_NO_MAP") != nullptr;
+        e.bfs_mapg = getenv("GP_BFS_MAPG") != nullptr;
+        e.bfs_trace = getenv("GP_BFS_TRACE") != nullptr;
+        e.bfs_push = geti("GP_BFS_PUSH", 1);
+        e.xchg_grid = geti("GP_XCHG_GRID", 0);
+        e.xchg_debug = geti("GP_XCHG_DEBUG", 0);
+        e.pdl = geti("GP_PDL", 1);
+        e.csr_trace = geti("GP_CSR_TRACE", 0);
+        e.nvtx = geti("GP_NVTX", 1);
+        return e;
+    }();  // function-local static: initialised once, thread-safe
+    return env;
+}
+
+uint64_t gp_next_uid()
+{
+    static std::atomic<uint64_t> next{1};
+    return next.fetch_add(1, std::memory_order_relaxed);
+}
+
+GpRange::GpRange(const char *name) : on(gp_env().nvtx != 0)
+{
+    if (on) nvtxRangePushA(name);
+}
+GpRange::~GpRange()
+{
+    if (on) nvtxRangePop();
+}
+
 extern "C" int gp_abi_version(void) { return GP_ABI_VERSION; }
 
 extern "C" const char *gp_last_error(void) { return g_err; }
@@ -107,9 +152,11 @@ extern "C" int gp_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_
 // ------------------------------------------------------------------------------------------
 // One-call host path.  A small cache keeps the handles, device staging and the stream alive
 // between calls of the same shape so repeated calls pay no allocation.
-namespace {
-
-struct HostCtx {
+// The state of the one-call host entry lives in an explicit context the caller may own (gp_ctx_create): handles,
+// device staging, a stream and the pinned ring.  Two host threads with two contexts share nothing but the device;
+// gp_geodesic_embed_host without a context uses one process-wide default context behind a mutex.
+struct gp_ctx {
+    std::mutex mutex;
     int64_t n = -1, e_cap = -1, k_cap = -1;
     uint32_t flags = 0;
     gp_csr *csr = nullptr;
@@ -142,12 +189,18 @@ struct HostCtx {
     }
 };
 
-HostCtx g_ctx;
-std::mutex g_ctx_mutex;
+typedef gp_ctx HostCtx;
 
-int ensure_ctx(int64_t n, int64_t e, int64_t k, uint32_t flags)
+namespace {
+
+HostCtx &default_ctx()
 {
-    HostCtx &c = g_ctx;
+    static HostCtx ctx;
+    return ctx;
+}
+
+int ensure_ctx(HostCtx &c, int64_t n, int64_t e, int64_t k, uint32_t flags)
+{
     if (c.stream == nullptr) GP_CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     if (c.n == n && c.flags == flags && e <= c.e_cap && k <= c.k_cap) return GP_OK;
     c.release();
@@ -179,7 +232,14 @@ public:
     // fn(first_row, last_row) over [0, rows) in chunks, on all workers plus the caller
     void parallel_rows(int64_t rows, int64_t chunk, const std::function<void(int64_t, int64_t)> &fn)
     {
-        std::unique_lock<std::mutex> run_lock(run_mutex_);  // one job at a time
+        // The workers exist only in the process that created them: after fork() (DataLoader workers,
+        // multiprocessing) the child copies the rows itself.  A second caller does not queue behind a running
+        // job either (two contexts on two threads must not serialise): it copies on its own thread.
+        std::unique_lock<std::mutex> run_lock(run_mutex_, std::try_to_lock);
+        if (getpid() != owner_pid_ || !run_lock.owns_lock()) {
+            fn(0, rows);
+            return;
+        }
         {
             std::lock_guard<std::mutex> lk(m_);
             fn_ = &fn;
@@ -197,13 +257,17 @@ public:
     }
 
 private:
-    HostPool()
+    HostPool() : owner_pid_(getpid())
     {
         int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u) - 1;
         for (int t = 0; t < nt; ++t) workers_.emplace_back([this] { loop(); });
     }
     ~HostPool()
     {
+        if (getpid() != owner_pid_) {  // forked child: the worker threads were never copied, nothing to join
+            for (auto &t : workers_) t.detach();
+            return;
+        }
         {
             std::lock_guard<std::mutex> lk(m_);
             stop_ = true;
@@ -236,6 +300,7 @@ private:
             }
         }
     }
+    const pid_t owner_pid_;
     std::vector<std::thread> workers_;
     std::mutex m_, run_mutex_;
     std::condition_variable cv_, done_cv_;
@@ -300,7 +365,8 @@ void copy_rows_parallel(const float *src, int64_t ld_src, float *dst, int64_t ld
 namespace {
 
 struct PipeKey {
-    const void *csr, *bfs, *ei, *anchors, *x, *out, *xchg;
+    uint64_t csr, bfs, xchg;  // handle uids (addresses are reused by the allocator, uids are not)
+    const void *ei, *anchors, *x, *out;
     int64_t e, k, f, ldx, ldo, coff, parity;
     bool operator==(const PipeKey &o) const { return memcmp(this, &o, sizeof(PipeKey)) == 0; }
 };
@@ -313,10 +379,18 @@ struct PipeEntry {
     uint64_t stamp = 0;
 };
 
-std::vector<PipeEntry> g_pipes;
-std::mutex g_pipe_mutex;
-cudaStream_t g_capture_stream = nullptr;
-uint64_t g_pipe_clock = 0;
+}  // namespace
+
+// The captured pipelines of one MS-BFS handle (the handle owns them: no process-wide cache, no global lock; a
+// handle is used by one thread at a time, like a stream).
+struct gp_pipe_cache {
+    std::vector<PipeEntry> pipes;
+    cudaStream_t capture_stream = nullptr;
+    uint64_t clock = 0;
+};
+
+namespace {
+
 thread_local bool g_capturing = false;  // a capture belongs to the thread that runs it
 
 struct SideCopy {
@@ -343,11 +417,7 @@ int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t 
     // while rows stream through the L2, even throttled to 3.6 TB/s; profiles/r02_notes.md), so the copy stays fused
     // in the epilogue kernel (GP_XCOPY_OVERLAP=0, default).  1 = one strided cudaMemcpy2DAsync on the copy engine,
     // 2 = the bulk-copy kernel on the side branch.
-    static int overlap = -1;
-    if (overlap < 0) {
-        const char *ev = getenv("GP_XCOPY_OVERLAP");
-        overlap = ev ? atoi(ev) : 0;
-    }
+    const int overlap = gp_env().xcopy_overlap;
     const bool have_copy = d_out != nullptr && d_x != nullptr && f > 0 && csr->num_nodes > 0 && xchg == nullptr;
     const bool tma_copy = have_copy && overlap == 2 && gp_xcopy_tma_ok(d_x, f, ldx, d_out, ldo);
     const bool side_copy = have_copy && (overlap == 1 || tma_copy);
@@ -378,10 +448,18 @@ int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t 
     // stage clocks of the step (gp_pipeline_stage_ms): inside a capture these become event-record nodes
     const unsigned ev_flags = gp_is_capturing() ? cudaEventRecordExternal : cudaEventRecordDefault;
     GP_CUDA_CHECK(cudaEventRecordWithFlags(bfs->ev_pipe0, s, ev_flags));
-    int rc = gp_csr_build(csr, d_ei, e, s);
-    if (rc == GP_OK) rc = gp_msbfs_run(bfs, d_anchors, k, s);
+    int rc;
+    {
+        GpRange r("graphpope:csr_build");
+        rc = gp_csr_build(csr, d_ei, e, s);
+    }
+    if (rc == GP_OK) {
+        GpRange r("graphpope:msbfs");
+        rc = gp_msbfs_run(bfs, d_anchors, k, s);
+    }
     if (side_copy) GP_CUDA_CHECK(cudaStreamWaitEvent(s, sc.join, 0));  // always re-join: a capture must not end forked
     GP_TRY(rc);
+    GpRange r(xchg != nullptr ? "graphpope:exchange_decode" : "graphpope:epilogue");
     if (xchg != nullptr) GP_TRY(gp_exchange_launch(xchg, parity, d_x, f, ldx, d_out, ldo, coff, s));
     else if (d_out != nullptr) GP_TRY(gp_msbfs_features(bfs, side_copy ? nullptr : d_x, f, ldx, d_out, ldo, coff, s));
     else GP_TRY(gp_msbfs_pack(bfs, (int32_t)coff, nullptr, nullptr, nullptr, nullptr, nullptr, s));  // coff = slot
@@ -394,18 +472,18 @@ int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t 
 
 bool gp_is_capturing() { return g_capturing; }
 
-void gp_drop_graphs(const void *handle)
+// Called when an MS-BFS handle is freed: its captured pipelines go with it.  (csr / exchange handles are referred to
+// by uid, so a graph that names a freed one can never be matched again; it is dropped with its bfs handle.)
+void gp_pipe_cache_free(gp_pipe_cache *pc)
 {
-    std::lock_guard<std::mutex> lock(g_pipe_mutex);
-    for (size_t i = 0; i < g_pipes.size();) {
-        if (g_pipes[i].key.csr == handle || g_pipes[i].key.bfs == handle || g_pipes[i].key.xchg == handle) {
-            if (g_pipes[i].exec) cudaGraphExecDestroy(g_pipes[i].exec);
-            g_pipes.erase(g_pipes.begin() + i);
-        } else {
-            ++i;
-        }
-    }
+    if (pc == nullptr) return;
+    for (auto &e : pc->pipes)
+        if (e.exec) cudaGraphExecDestroy(e.exec);
+    if (pc->capture_stream) cudaStreamDestroy(pc->capture_stream);
+    delete pc;
 }
+
+uint64_t gp_exchange_uid(const gp_exchange *x);
 
 static int geodesic_run_impl(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_edge_index, int64_t num_edges,
                              const int64_t *d_anchors, int64_t num_anchors, const float *d_x,
@@ -414,50 +492,47 @@ static int geodesic_run_impl(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_ed
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     GP_REQUIRE(csr != nullptr && bfs != nullptr, GP_ERR_INVALID, "gp_geodesic_run: NULL handle");
-    static int use_graph = -1;
-    if (use_graph < 0) {
-        const char *e = getenv("GP_USE_GRAPH");
-        use_graph = e ? atoi(e) : 1;
-    }
-    if (!use_graph || csr->num_nodes == 0 || num_anchors == 0)
+    if (!gp_env().use_graph || csr->num_nodes == 0 || num_anchors == 0)
         return run_pipeline_eager(csr, bfs, d_edge_index, num_edges, d_anchors, num_anchors, d_x, num_features, ld_x,
                                   d_out, ld_out, col_offset, stream, xchg, parity);
-    std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    if (bfs->pipe_cache == nullptr) bfs->pipe_cache = new (std::nothrow) gp_pipe_cache();
+    GP_REQUIRE(bfs->pipe_cache != nullptr, GP_ERR_OOM, "gp_geodesic_run: host allocation failed");
+    gp_pipe_cache &pc = *bfs->pipe_cache;
     PipeKey key;
     memset(&key, 0, sizeof(key));
-    key.csr = csr; key.bfs = bfs; key.ei = d_edge_index; key.anchors = d_anchors; key.x = d_x; key.out = d_out;
+    key.csr = csr->uid; key.bfs = bfs->uid; key.ei = d_edge_index; key.anchors = d_anchors; key.x = d_x; key.out = d_out;
     key.e = num_edges; key.k = num_anchors; key.f = num_features; key.ldx = ld_x; key.ldo = ld_out; key.coff = col_offset;
-    key.xchg = xchg; key.parity = parity;
+    key.xchg = xchg ? gp_exchange_uid(xchg) : 0; key.parity = parity;
     PipeEntry *ent = nullptr;
-    for (auto &p : g_pipes)
+    for (auto &p : pc.pipes)
         if (p.key == key) ent = &p;
     if (ent == nullptr) {
-        if (g_pipes.size() >= 8) {  // evict the least recently used graph
+        if (pc.pipes.size() >= 8) {  // evict the least recently used graph
             size_t lru = 0;
-            for (size_t i = 1; i < g_pipes.size(); ++i)
-                if (g_pipes[i].stamp < g_pipes[lru].stamp) lru = i;
-            if (g_pipes[lru].exec) cudaGraphExecDestroy(g_pipes[lru].exec);
-            g_pipes.erase(g_pipes.begin() + lru);
+            for (size_t i = 1; i < pc.pipes.size(); ++i)
+                if (pc.pipes[i].stamp < pc.pipes[lru].stamp) lru = i;
+            if (pc.pipes[lru].exec) cudaGraphExecDestroy(pc.pipes[lru].exec);
+            pc.pipes.erase(pc.pipes.begin() + lru);
         }
-        g_pipes.emplace_back();
-        ent = &g_pipes.back();
+        pc.pipes.emplace_back();
+        ent = &pc.pipes.back();
         ent->key = key;
     }
-    ent->stamp = ++g_pipe_clock;
+    ent->stamp = ++pc.clock;
     ent->seen += 1;
     if (ent->exec == nullptr && ent->seen == 2) {
-        if (g_capture_stream == nullptr)
-            GP_CUDA_CHECK(cudaStreamCreateWithFlags(&g_capture_stream, cudaStreamNonBlocking));
+        if (pc.capture_stream == nullptr)
+            GP_CUDA_CHECK(cudaStreamCreateWithFlags(&pc.capture_stream, cudaStreamNonBlocking));
         cudaGraph_t graph = nullptr;
-        if (cudaStreamBeginCapture(g_capture_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+        if (cudaStreamBeginCapture(pc.capture_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
             g_capturing = true;
             g_capture_count = 0;
             const int rc = run_pipeline_eager(csr, bfs, d_edge_index, num_edges, d_anchors, num_anchors, d_x,
-                                              num_features, ld_x, d_out, ld_out, col_offset, g_capture_stream, xchg,
+                                              num_features, ld_x, d_out, ld_out, col_offset, pc.capture_stream, xchg,
                                               parity);
             g_capturing = false;
             ent->kernels = g_capture_count;
-            const cudaError_t ce = cudaStreamEndCapture(g_capture_stream, &graph);
+            const cudaError_t ce = cudaStreamEndCapture(pc.capture_stream, &graph);
             if (rc == GP_OK && ce == cudaSuccess && graph != nullptr) {
                 if (cudaGraphInstantiate(&ent->exec, graph, 0) != cudaSuccess) ent->exec = nullptr;
             }
@@ -474,6 +549,7 @@ static int geodesic_run_impl(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_ed
         bfs->ran = true;
         bfs->pipe_timed = true;
         gp_count_launches(ent->kernels);  // kernels inside the graph
+        GpRange r("graphpope:pipeline_graph_replay");
         GP_CUDA_CHECK(cudaGraphLaunch(ent->exec, stream));
         return GP_OK;
     }
@@ -556,11 +632,42 @@ extern "C" int gp_block_to_host(const float *d_block, int64_t num_nodes, int64_t
     return GP_OK;
 }
 
+extern "C" int gp_ctx_create(gp_ctx_t **out)
+{
+    GP_REQUIRE(out != nullptr, GP_ERR_INVALID, "gp_ctx_create: out is NULL");
+    *out = new (std::nothrow) gp_ctx();
+    GP_REQUIRE(*out != nullptr, GP_ERR_OOM, "gp_ctx_create: host allocation failed");
+    return GP_OK;
+}
+
+extern "C" int gp_ctx_free(gp_ctx_t *ctx)
+{
+    if (ctx == nullptr) return GP_OK;
+    ctx->release();
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->h_ring[i]) cudaFreeHost(ctx->h_ring[i]);
+        if (ctx->ring_ev[i]) cudaEventDestroy(ctx->ring_ev[i]);
+    }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return GP_OK;
+}
+
 extern "C" int gp_geodesic_embed_host(const int64_t *h_edge_index, int64_t num_edges, int64_t num_nodes,
                                       uint32_t csr_flags, const int64_t *h_anchors, int64_t num_anchors,
                                       const float *h_x, int64_t num_features, float *h_out, int64_t ld_out,
                                       int64_t col_offset, uint16_t *h_hops, gp_msbfs_stats_t *stats)
 {
+    return gp_geodesic_embed_host_ctx(&default_ctx(), h_edge_index, num_edges, num_nodes, csr_flags, h_anchors,
+                                      num_anchors, h_x, num_features, h_out, ld_out, col_offset, h_hops, stats);
+}
+
+extern "C" int gp_geodesic_embed_host_ctx(gp_ctx_t *ctx, const int64_t *h_edge_index, int64_t num_edges,
+                                          int64_t num_nodes, uint32_t csr_flags, const int64_t *h_anchors,
+                                          int64_t num_anchors, const float *h_x, int64_t num_features, float *h_out,
+                                          int64_t ld_out, int64_t col_offset, uint16_t *h_hops, gp_msbfs_stats_t *stats)
+{
+    GP_REQUIRE(ctx != nullptr, GP_ERR_INVALID, "gp_geodesic_embed_host_ctx: ctx is NULL");
     GP_REQUIRE(num_edges >= 0 && num_nodes >= 0 && num_anchors >= 0 && num_features >= 0, GP_ERR_INVALID,
                "gp_geodesic_embed_host: negative size");
     GP_REQUIRE(num_edges == 0 || h_edge_index != nullptr, GP_ERR_INVALID, "edge_index is NULL");
@@ -569,9 +676,10 @@ extern "C" int gp_geodesic_embed_host(const int64_t *h_edge_index, int64_t num_e
                "out is NULL");
     GP_REQUIRE(col_offset >= 0 && ld_out >= col_offset + num_anchors && (h_x == nullptr || col_offset >= num_features),
                GP_ERR_INVALID, "gp_geodesic_embed_host: inconsistent ld_out / col_offset");
-    std::lock_guard<std::mutex> lock(g_ctx_mutex);
-    GP_TRY(ensure_ctx(num_nodes, num_edges, num_anchors, csr_flags));
-    HostCtx &c = g_ctx;
+    HostCtx &c = *ctx;
+    std::lock_guard<std::mutex> lock(c.mutex);  // a context serves one call at a time; contexts are independent
+    GP_TRY(ensure_ctx(c, num_nodes, num_edges, num_anchors, csr_flags));
+    GpRange range("graphpope:embed_host");
     cudaStream_t s = c.stream;
     if (num_edges > 0)
         GP_CUDA_CHECK(cudaMemcpyAsync(c.d_edges, h_edge_index, sizeof(int64_t) * 2 * (size_t)num_edges,

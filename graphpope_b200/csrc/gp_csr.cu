@@ -53,32 +53,77 @@ int row_blocks(int64_t rows)
 }
 
 // ---------------------------------------------------------------- count / scatter
-__global__ void count_edges_kernel(const long long *__restrict__ ei, long long e, long long n, int symmetrize,
-                                   int *__restrict__ cnt, int *meta)
+// Four consecutive edges per thread, read as two 16-byte loads from each row of edge_index: one resident wave covers a
+// million edges, and every thread has its eight atomics in flight together (a thread per edge ran four waves, each a
+// dependent load -> atomic round trip).  `vec` = both rows are 16-byte aligned (E even and the base aligned).
+__device__ __forceinline__ void load_edges4(const long long *__restrict__ ei, long long e, long long i0, int vec,
+                                            long long (&s)[4], long long (&d)[4], int &cnt)
 {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    bool bad = false;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += stride) {
-        const long long s = ei[i], d = ei[e + i];
-        if (s < 0 || d < 0 || s >= n || d >= n) {
-            bad = true;
-            continue;
+    cnt = (int)(e - i0 < 4 ? e - i0 : 4);
+    if (vec && cnt == 4) {
+        const longlong2 a = __ldcs(reinterpret_cast<const longlong2 *>(ei + i0));
+        const longlong2 b = __ldcs(reinterpret_cast<const longlong2 *>(ei + i0) + 1);
+        const longlong2 c = __ldcs(reinterpret_cast<const longlong2 *>(ei + e + i0));
+        const longlong2 f = __ldcs(reinterpret_cast<const longlong2 *>(ei + e + i0) + 1);
+        s[0] = a.x; s[1] = a.y; s[2] = b.x; s[3] = b.y;
+        d[0] = c.x; d[1] = c.y; d[2] = f.x; d[3] = f.y;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            s[q] = q < cnt ? ei[i0 + q] : 0;
+            d[q] = q < cnt ? ei[e + i0 + q] : 0;
         }
-        atomicAdd(cnt + s, 1);
-        if (symmetrize) atomicAdd(cnt + d, 1);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+count_edges_kernel(const long long *__restrict__ ei, long long e, long long n, int symmetrize, int vec,
+                   int *__restrict__ cnt, int *meta)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    bool bad = false;
+    for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < e; i0 += stride) {
+        long long s[4], d[4];
+        int c;
+        load_edges4(ei, e, i0, vec, s, d, c);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (q >= c) break;
+            if (s[q] < 0 || d[q] < 0 || s[q] >= n || d[q] >= n) {
+                bad = true;
+                continue;
+            }
+            atomicAdd(cnt + s[q], 1);
+            if (symmetrize) atomicAdd(cnt + d[q], 1);
+        }
     }
     if (__any_sync(FULL_MASK, bad) && lane_id() == 0) atomicOr(&meta[GP_META_ERROR], GP_DEV_ERR_EDGE_RANGE);
 }
 
-__global__ void scatter_edges_kernel(const long long *__restrict__ ei, long long e, long long n, int symmetrize,
-                                     int *__restrict__ cursor, int *__restrict__ raw_col)
+__global__ void __launch_bounds__(256)
+scatter_edges_kernel(const long long *__restrict__ ei, long long e, long long n, int symmetrize, int vec,
+                     int *__restrict__ cursor, int *__restrict__ raw_col)
 {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += stride) {
-        const long long s = ei[i], d = ei[e + i];
-        if (s < 0 || d < 0 || s >= n || d >= n) continue;  // latched by count_edges_kernel
-        raw_col[atomicAdd(cursor + s, 1)] = (int)d;
-        if (symmetrize) raw_col[atomicAdd(cursor + d, 1)] = (int)s;
+    gp_pdl_enter();
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < e; i0 += stride) {
+        long long s[4], d[4];
+        int c, pos[4], pos2[4];
+        load_edges4(ei, e, i0, vec, s, d, c);
+        bool ok[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {  // the four returning atomics are in flight together
+            ok[q] = q < c && !(s[q] < 0 || d[q] < 0 || s[q] >= n || d[q] >= n);  // bad entries: latched by count_edges_kernel
+            pos[q] = ok[q] ? atomicAdd(cursor + s[q], 1) : 0;
+            pos2[q] = (ok[q] && symmetrize) ? atomicAdd(cursor + d[q], 1) : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (ok[q]) {
+                raw_col[pos[q]] = (int)d[q];
+                if (symmetrize) raw_col[pos2[q]] = (int)s[q];
+            }
+        }
     }
 }
 
@@ -131,14 +176,17 @@ __device__ __forceinline__ void st_release_i32(int *p, int v)
 //   __device__ void load(long long i, int (&v)[CHN]) const      contribution of element i (v arrives zeroed)
 //   __device__ void store(long long i, const int (&excl)[CHN], const int (&v)[CHN]) const
 //   __device__ void finish(const int (&total)[CHN]) const        called once, by the last tile
-template <int CHN, class IO>
+template <int CHN, class IO, int IPT = SCAN_IPT>
 __global__ void __launch_bounds__(SCAN_THREADS) chained_scan_kernel(IO io, long long count, int *status, int *ticket)
 {
     constexpr int STRIDE = ScanStatus<CHN>::STRIDE;
+    constexpr int SCAN_IPT = IPT;                         // items per thread of THIS instantiation
+    constexpr int SCAN_TILE = SCAN_THREADS * SCAN_IPT;    // (shadow the file-level defaults)
     __shared__ int s_tile;
     __shared__ int s_warp[SCAN_THREADS / 32][CHN];
     __shared__ int s_prefix[CHN];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    gp_pdl_enter();
     if (tid == 0) s_tile = atomicAdd(ticket, 1);
     __syncthreads();
     const int tile = s_tile;
@@ -489,6 +537,7 @@ rowsort_small_kernel(const int *__restrict__ ptr, const int *len_in, int *__rest
     const int lane = lane_id();
     const long long nblk = (n + 255) / 256;
     int mx = 0;
+    gp_pdl_enter();
     for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
         const long long r = blk * 256 + threadIdx.x;
         int s = 0, len = 0;
@@ -570,6 +619,7 @@ rowsort_big_kernel(const int *__restrict__ ptr, const int *len_in, int *colbuf, 
     __shared__ int s_warp[BIG_THREADS / 32];
     __shared__ int s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    gp_pdl_enter();
     const int nbig = meta[GP_META_NUM_BIG_ROWS];
     for (int q = blockIdx.x; q < nbig; q += gridDim.x) {
         const int r = biglist[q];
@@ -680,6 +730,7 @@ __global__ void desc_kernel(const int *__restrict__ row_start, const int *__rest
                             const int *__restrict__ meta, long long n, int4 *__restrict__ desc)
 {
     __shared__ int s_ent[GP_NUM_CLASSES];
+    gp_pdl_enter();
     if (threadIdx.x < GP_NUM_CLASSES) s_ent[threadIdx.x] = meta[GP_META_ENT_BASE + threadIdx.x];
     __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -743,10 +794,12 @@ int sort_rows(gp_csr *c, const int *ptr, int *len, int *colbuf, int max_word, bo
 {
     const int64_t n = c->num_nodes;
     if (reset_queue) GP_LAUNCH(set_meta_kernel, 1, 1, 0, stream, c->meta, GP_META_NUM_BIG_ROWS, 0);
-    GP_LAUNCH(rowsort_small_kernel, launch_blocks(n, 256), 256, 0, stream, ptr, len, colbuf, n, len, c->biglist,
-              c->meta, max_word);
-    GP_LAUNCH(rowsort_big_kernel, gp_sm_count() * 4, BIG_THREADS, c->big_smem_bytes, stream, ptr, len, colbuf, len,
-              c->biglist, c->meta, max_word, c->bitmap_words);
+    // programmatic launches: inside gp_csr_build they follow kernels of the same chain (after a memset or a
+    // one-thread kernel the attribute simply has no effect)
+    GP_LAUNCH_PDL(rowsort_small_kernel, launch_blocks(n, 256), 256, 0, stream, ptr, (const int *)len, colbuf, (long long)n, len,
+                  c->biglist, c->meta, max_word);
+    GP_LAUNCH_PDL(rowsort_big_kernel, gp_sm_count() * 4, BIG_THREADS, (size_t)c->big_smem_bytes, stream, ptr,
+                  (const int *)len, colbuf, len, (const int *)c->biglist, c->meta, max_word, c->bitmap_words);
     return GP_OK;
 }
 
@@ -829,8 +882,9 @@ int gp_csr_scratch(gp_csr *c, int slot, size_t bytes, void **out)
 extern "C" int gp_csr_free(gp_csr_t *c)
 {
     if (!c) return GP_OK;
-    gp_drop_graphs(c);
     for (int i = 0; i < 16; ++i) cudaFree(c->scratch[i]);
+    for (int i = 0; i < 12; ++i)
+        if (c->trace_ev[i]) cudaEventDestroy(c->trace_ev[i]);
     cudaFree(c->deg);
     cudaFree(c->row_start);
     cudaFree(c->cursor);
@@ -859,31 +913,63 @@ extern "C" int gp_csr_build(gp_csr_t *c, const int64_t *d_edge_index, int64_t nu
     c->num_input_edges = num_edges;
     c->built = false;
     c->in_built = false;
+    c->trace_n = 0;
+    auto mark = [&]() {  // GP_CSR_TRACE=1: an event after every launch (event nodes when captured)
+        if (!gp_env().csr_trace || c->trace_n >= 12) return;
+        if (c->trace_ev[c->trace_n] == nullptr) cudaEventCreate(&c->trace_ev[c->trace_n]);
+        cudaEventRecordWithFlags(c->trace_ev[c->trace_n++], stream,
+                                 gp_is_capturing() ? cudaEventRecordExternal : cudaEventRecordDefault);
+    };
+    mark();
     GP_CUDA_CHECK(cudaMemsetAsync(c->meta, 0, (GP_META_WORDS + c->scan_status_words) * sizeof(int), stream));
     if (n > 0) {
         const long long *ei = (const long long *)d_edge_index;
-        const int tiles = scan_tiles(n + 1);
+        const int vec = (reinterpret_cast<uintptr_t>(ei) & 15u) == 0 && num_edges % 2 == 0;  // both rows 16-byte aligned
         int *ticket_a = c->scan_status + c->scan_status_words - 8, *ticket_b = ticket_a + 1;
         GP_CUDA_CHECK(cudaMemsetAsync(c->deg, 0, (size_t)(n + 1) * sizeof(int), stream));
+        mark();
         if (num_edges > 0)
-            GP_LAUNCH(count_edges_kernel, launch_blocks(num_edges, 256), 256, 0, stream, ei, num_edges, n, sym, c->deg,
-                      c->meta);
+            GP_LAUNCH(count_edges_kernel, launch_blocks(gp_ceil_div(num_edges, 4), 256), 256, 0, stream, ei, num_edges, n, sym,
+                      vec, c->deg, c->meta);
+        mark();
         PtrScanIo pio{c->deg, c->row_start, c->cursor, n};
         gp_count_launch();
-        chained_scan_kernel<1, PtrScanIo><<<tiles, SCAN_THREADS, 0, stream>>>(pio, n + 1, c->scan_status, ticket_a);
+        // (16 items per thread = 22 tiles = one look-back window at Flickr size measured SLOWER: 10.3 us against 8.8 us;
+        // the per-thread serial work outweighs the saved look-back rounds)
+        GP_CUDA_CHECK(gp_launch_pdl(chained_scan_kernel<1, PtrScanIo, SCAN_IPT>, dim3((unsigned)scan_tiles(n + 1)),
+                                    dim3(SCAN_THREADS), 0, stream, pio, (long long)(n + 1), c->scan_status, ticket_a));
+        mark();
         if (num_edges > 0)
-            GP_LAUNCH(scatter_edges_kernel, launch_blocks(num_edges, 256), 256, 0, stream, ei, num_edges, n, sym,
-                      c->cursor, c->col);
+            GP_LAUNCH_PDL(scatter_edges_kernel, launch_blocks(gp_ceil_div(num_edges, 4), 256), 256, 0, stream, ei,
+                          (long long)num_edges, (long long)n, sym, vec, c->cursor, c->col);
+        mark();
         GP_TRY(sort_rows(c, c->row_start, c->deg, c->col, GP_META_MAX_DEGREE, false, stream));  // deg := distinct degree
+        mark();
         RowScanIo rio{c->deg, c->cursor, c->hubidx, c->meta, n};  // cursor := rank of the row inside its class
         gp_count_launch();
-        chained_scan_kernel<ROW_CH, RowScanIo><<<scan_tiles(n), SCAN_THREADS, 0, stream>>>(
-            rio, n, c->scan_status + c->scan_b_offset, ticket_b);
-        GP_LAUNCH(desc_kernel, launch_blocks(n, 256), 256, 0, stream, c->row_start, c->deg, c->cursor, c->hubidx, c->meta,
-                  n, c->desc);
+        GP_CUDA_CHECK(gp_launch_pdl(chained_scan_kernel<ROW_CH, RowScanIo, SCAN_IPT>, dim3((unsigned)scan_tiles(n)),
+                                    dim3(SCAN_THREADS), 0, stream, rio, (long long)n, c->scan_status + c->scan_b_offset,
+                                    ticket_b));
+        mark();
+        GP_LAUNCH_PDL(desc_kernel, launch_blocks(n, 256), 256, 0, stream, (const int *)c->row_start, (const int *)c->deg,
+                      (const int *)c->cursor, (const int *)c->hubidx, (const int *)c->meta, (long long)n, c->desc);
+        mark();
     }
     GP_CUDA_CHECK(cudaGetLastError());
     c->built = true;
+    return GP_OK;
+}
+
+// Diagnostics (GP_CSR_TRACE=1): milliseconds between the marks of the last build: memsets, count, scan, scatter,
+// row sort (both kernels), row scan, descriptors.  syncs on the last mark.  Returns the number of intervals.
+extern "C" int gp_csr_trace_ms(gp_csr_t *c, float *ms, int32_t cap, int32_t *num)
+{
+    GP_REQUIRE(c != nullptr && ms != nullptr && num != nullptr, GP_ERR_INVALID, "gp_csr_trace_ms: NULL argument");
+    GP_REQUIRE(c->trace_n >= 2, GP_ERR_INVALID, "gp_csr_trace_ms: set GP_CSR_TRACE=1 and build first");
+    GP_CUDA_CHECK(cudaEventSynchronize(c->trace_ev[c->trace_n - 1]));
+    int k = 0;
+    for (; k + 1 < c->trace_n && k < cap; ++k) GP_CUDA_CHECK(cudaEventElapsedTime(ms + k, c->trace_ev[k], c->trace_ev[k + 1]));
+    *num = k;
     return GP_OK;
 }
 

@@ -33,6 +33,7 @@
 #include <new>
 
 struct gp_exchange {
+    uint64_t uid = gp_next_uid();
     gp_msbfs *bfs = nullptr;
     int world = 1, rank = 0;
     size_t cap_words = 0;          // lane words per plane the slots were sized for
@@ -43,6 +44,7 @@ struct gp_exchange {
                                    // [6..7] blocks left; bytes 64..: u64 globaltimer stamps (diagnostics)
     int step = 0;
     int grid_blocks = 0;
+    int grid_cap = 0;
     int smem_bytes = 0;
 };
 
@@ -365,7 +367,6 @@ extern "C" int gp_exchange_set_peer(gp_exchange_t *x, int32_t rank, void *d_ptr)
 extern "C" int gp_exchange_free(gp_exchange_t *x)
 {
     if (!x) return GP_OK;
-    gp_drop_graphs(x);
     cudaFree(x->buf);
     cudaFree(x->local);
     delete x;
@@ -392,6 +393,18 @@ extern "C" int gp_exchange_trace(gp_exchange_t *x, uint64_t *h_stamps8)
     GP_REQUIRE(x != nullptr && h_stamps8 != nullptr, GP_ERR_INVALID, "gp_exchange_trace: NULL argument");
     GP_CUDA_CHECK(cudaDeviceSynchronize());
     GP_CUDA_CHECK(cudaMemcpy(h_stamps8, x->local + 16, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return GP_OK;
+}
+
+uint64_t gp_exchange_uid(const gp_exchange *x) { return x->uid; }
+
+// Tuning / tests: cap the cooperative grid (several ranks sharing one GPU must all be resident at once).  Takes
+// effect at the next launch; 0 restores one full wave.
+extern "C" int gp_exchange_set_grid(gp_exchange_t *x, int32_t max_blocks)
+{
+    GP_REQUIRE(x != nullptr && max_blocks >= 0, GP_ERR_INVALID, "gp_exchange_set_grid: bad argument");
+    x->grid_cap = max_blocks;
+    x->grid_blocks = 0;
     return GP_OK;
 }
 
@@ -449,13 +462,10 @@ int gp_exchange_launch(gp_exchange *x, int parity, const float *d_x, int64_t f, 
         if (occ > 4) occ = 4;
         x->grid_blocks = occ * gp_sm_count();
         x->smem_bytes = smem;
-        const char *e = getenv("GP_XCHG_GRID");  // tests: several ranks sharing one GPU need partial grids
-        if (e && atoi(e) > 0 && atoi(e) < x->grid_blocks) x->grid_blocks = atoi(e);
+        const int cap = x->grid_cap > 0 ? x->grid_cap : gp_env().xchg_grid;
+        if (cap > 0 && cap < x->grid_blocks) x->grid_blocks = cap;
     }
-    {
-        const char *e = getenv("GP_XCHG_DEBUG");
-        p.debug = e ? atoi(e) : 0;
-    }
+    p.debug = gp_env().xchg_debug;
     p.vec_x = d_x != nullptr && (reinterpret_cast<uintptr_t>(d_x) & 15u) == 0 && ldx % 4 == 0;
     if (p.n == 0) return GP_OK;
     void *args[] = {&p};

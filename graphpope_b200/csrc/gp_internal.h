@@ -30,6 +30,7 @@ enum : int {
 };
 
 struct gp_csr {
+    uint64_t uid = gp_next_uid();
     int64_t num_nodes = 0;
     int64_t edge_capacity = 0;  // input columns accepted by gp_csr_build
     int64_t key_capacity = 0;   // edge_capacity * (symmetrize ? 2 : 1)
@@ -61,6 +62,8 @@ struct gp_csr {
     // seconds (betweenness) keep their workspace here instead of paying cudaMalloc / cudaFree on every call
     void *scratch[16] = {};
     size_t scratch_bytes[16] = {};
+    cudaEvent_t trace_ev[12] = {};  // GP_CSR_TRACE: events after every launch of the last build (diagnostics)
+    int trace_n = 0;
     int bitmap_words = 0;       // ceil(N / 32) if the long-row sort may use a node bitmap in shared memory, else 0
     int big_smem_bytes = 0;     // dynamic shared memory of rowsort_big_kernel
 };

@@ -16,7 +16,7 @@
 // count small.  The CSR builder (gp_csr.cu) emits a degree-ordered list of 16-byte row descriptors;
 // a row of degree d is served by G = 1,2,4,...,32 "slots" (threads) of <= 4 edges each (4G >= d), hub
 // rows are cut into 128-edge chunks (G = 32, one warp) whose partial ORs meet in a small accumulator
-// that the last-arriving chunk finalises.  One slot = <= 4 column indices -> <= 4 whole frontier rows
+// that the last-arriving chunk finalises (release / acquire through the arrival counter).  One slot = <= 4 column indices -> <= 4 whole frontier rows
 // (one 256-bit load each at 256 anchors per batch, all issued back to back) -> shuffle-OR over the G
 // slots of the row -> finalise.  Three filters cut the gathers to the ones that can matter:
 //   * a per-hop bitmap of non-zero frontier rows, staged in shared memory every level: a neighbour
@@ -474,17 +474,15 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
                 if (finalize_row<VW>(c, off, lead.x, acc, seenv, live_acc, lv, nzrows) || dflag == nullptr) s_notdone = 1;
                 else dflag[lane] = 1;
             } else {
-                // hub chunk: deposit the partial OR; the last chunk to arrive finalises the row.  All
-                // traffic on hub_acc / hub_cnt is L2 atomics; waiting for the OR's return value orders
-                // it before the arrival count without a fence.
+                // hub chunk: deposit the partial OR (fire-and-forget reductions at L2), then arrive with an
+                // acq_rel add: the deposits are released by it, and the chunk that completes the count acquires
+                // every earlier chunk's deposits through the counter's release sequence before it reads them.
                 const size_t hidx = (size_t)b * p.hub_capacity + (size_t)lead.z;
                 u64 *accp = p.hub_acc + hidx * WB;
-                u64 dep = 0;
 #pragma unroll
                 for (int q = 0; q < VW; ++q)
-                    if (acc[q]) dep |= atomicOr(accp + q, acc[q]);
-                asm volatile("" ::"l"(dep) : "memory");  // the ORs have returned from L2 before we count
-                const u32 old = atomicAdd(p.hub_cnt + hidx, 1u);
+                    if (acc[q]) red_or_u64(accp + q, acc[q]);
+                const u32 old = atom_add_acq_rel_u32(p.hub_cnt + hidx, 1u);
                 if (old == (u32)nch - 1u) {
                     u64 comb[VW];
 #pragma unroll
@@ -575,7 +573,7 @@ int launch_bfs_variant(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int
         GP_REQUIRE(occ >= 1, GP_ERR_CUDA, "msbfs kernel does not fit on an SM");
         if (occ > MINB) occ = MINB;
         h->map_smem_bytes = 0;
-        if (!MAPG && cache_bytes + want_map <= dyn_max && getenv("GP_BFS_NO_MAP") == nullptr) {
+        if (!MAPG && cache_bytes + want_map <= dyn_max && !gp_env().bfs_no_map) {
             GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_map, msbfs_kernel<WB, NT, MINB, MAPG>, NT,
                                                                         bfs_cache_bytes<WB, NT, MINB>() + want_map));
             if (occ_map >= occ) h->map_smem_bytes = want_map;
@@ -605,8 +603,8 @@ int launch_bfs_cfg(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int cfg
 {
     const size_t want_map = (size_t)p.map_stride * sizeof(u32);
     const bool fits = bfs_cache_bytes<WB, NT, MINB>() + want_map <= 200 * 1024 / (size_t)MINB;
-    static const bool force_global = getenv("GP_BFS_MAPG") != nullptr;  // experiment: never stage the maps
-    if ((!fits || force_global) && cfg_id == GP_BFS_DEFAULT_CFG && getenv("GP_BFS_NO_MAP") == nullptr)
+    const bool force_global = gp_env().bfs_mapg != 0;  // experiment: never stage the maps
+    if ((!fits || force_global) && cfg_id == GP_BFS_DEFAULT_CFG && !gp_env().bfs_no_map)
         return launch_bfs_variant<WB, NT, MINB, true>(h, p, stream, cfg_id);
     return launch_bfs_variant<WB, NT, MINB, false>(h, p, stream, cfg_id);
 }
@@ -616,12 +614,8 @@ int launch_bfs_cfg(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int cfg
 template <int WB>
 int launch_bfs(gp_msbfs *h, const BfsParams &p, cudaStream_t stream)
 {
-    static int cfg = -1;
-    if (cfg < 0) {
-        const char *s = getenv("GP_BFS_CFG");
-        cfg = s ? atoi(s) : GP_BFS_DEFAULT_CFG;
-        if (cfg < 0 || cfg > 7) cfg = GP_BFS_DEFAULT_CFG;
-    }
+    int cfg = gp_env().bfs_cfg;
+    if (cfg < 0 || cfg > 7) cfg = GP_BFS_DEFAULT_CFG;
     switch (cfg) {
         case 0: return launch_bfs_cfg<WB, 768, 1>(h, p, stream, 0);   // 85 regs, 24 warps/SM, one tile queue per SM
         case 1: return launch_bfs_cfg<WB, 384, 2>(h, p, stream, 1);   // 85 regs, 24 warps/SM
@@ -706,7 +700,7 @@ extern "C" int gp_msbfs_create(const gp_csr_t *csr, int64_t max_anchors, gp_msbf
         h->status = reinterpret_cast<int *>(h->counters + 4);
         h->nzmap = reinterpret_cast<u32 *>(h->status + 16);
     }
-    if (getenv("GP_BFS_TRACE")) alloc((void **)&h->trace, GP_BFS_TRACE_WORDS * sizeof(u64));
+    if (gp_env().bfs_trace) alloc((void **)&h->trace, GP_BFS_TRACE_WORDS * sizeof(u64));
     if (rc == GP_OK && (cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess ||
                         cudaEventCreate(&h->ev_pipe0) != cudaSuccess || cudaEventCreate(&h->ev_pipe1) != cudaSuccess)) {
         gp_set_error("gp_msbfs_create: cudaEventCreate failed");
@@ -723,7 +717,7 @@ extern "C" int gp_msbfs_create(const gp_csr_t *csr, int64_t max_anchors, gp_msbf
 extern "C" int gp_msbfs_free(gp_msbfs_t *h)
 {
     if (!h) return GP_OK;
-    gp_drop_graphs(h);
+    gp_pipe_cache_free(h->pipe_cache);
     cudaFree(h->lane_buf);
     cudaFree(h->scratch);
     cudaFree(h->hub_acc);

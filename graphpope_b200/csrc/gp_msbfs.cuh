@@ -23,7 +23,12 @@ enum : int {
     GP_BFS_ST_WORDS = 8
 };
 
+struct gp_pipe_cache;  // captured pipelines of this handle (gp_api.cu)
+void gp_pipe_cache_free(gp_pipe_cache *pc);
+
 struct gp_msbfs {
+    uint64_t uid = gp_next_uid();
+    gp_pipe_cache *pipe_cache = nullptr;
     const gp_csr *csr = nullptr;
     int64_t num_nodes = 0;
     int64_t max_anchors = 0;

@@ -93,26 +93,15 @@ int gp_launch_xcopy_tma(const float *d_x, int64_t num_nodes, int64_t num_feature
     if (num_nodes == 0 || num_features == 0) return GP_OK;
     GP_REQUIRE(gp_xcopy_tma_ok(d_x, num_features, ld_x, d_out, ld_out), GP_ERR_INVALID,
                "gp_launch_xcopy_tma: rows must be 16-byte aligned and at most %d bytes long", XC_STAGE_BYTES);
-    static int stages = 0;
-    if (stages == 0) {
-        const char *e = getenv("GP_XCOPY_STAGES");
-        int s = e ? atoi(e) : 4;
-        stages = s < 3 ? 3 : (s > XC_MAX_STAGES ? XC_MAX_STAGES : s);
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-        GP_CUDA_CHECK(cudaFuncSetAttribute(xcopy_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           XC_MAX_STAGES * XC_STAGE_BYTES));
-        attr_set = true;
-    }
+    int stages = gp_env().xcopy_stages;
+    stages = stages < 3 ? 3 : (stages > XC_MAX_STAGES ? XC_MAX_STAGES : stages);
+    GP_CUDA_CHECK(cudaFuncSetAttribute(xcopy_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       XC_MAX_STAGES * XC_STAGE_BYTES));
     const u32 row_bytes = (u32)(num_features * 4);
     const int rows_per_stage = XC_STAGE_BYTES / (int)row_bytes;
     const long long nblk = (num_nodes + rows_per_stage - 1) / rows_per_stage;
-    static int grid_cap = 0;  // experiment: fewer driver CTAs = a slower copy that disturbs its neighbours less
-    if (grid_cap == 0) {
-        const char *e = getenv("GP_XCOPY_GRID");
-        grid_cap = e && atoi(e) > 0 ? atoi(e) : gp_sm_count();
-    }
+    // experiment (GP_XCOPY_GRID): fewer driver blocks = a slower copy that disturbs its neighbours less
+    const int grid_cap = gp_env().xcopy_grid > 0 ? gp_env().xcopy_grid : gp_sm_count();
     const int grid = (int)(nblk < grid_cap ? nblk : grid_cap);
     GP_LAUNCH(xcopy_tma_kernel, grid, 32, (size_t)stages * XC_STAGE_BYTES, stream,
               reinterpret_cast<const unsigned char *>(d_x), (long long)num_nodes, row_bytes, (long long)ld_x * 4,

@@ -279,8 +279,29 @@ def normalize_into(dist_u16: torch.Tensor, out: torch.Tensor, col_offset: int = 
     return out
 
 
+class HostContext:
+    """Explicit state of the one-call host entry (``gp_ctx_t``): its own handles, device staging, stream and pinned
+    ring.  One call at a time per context; separate contexts (e.g. one per host thread) do not serialise."""
+
+    def __init__(self):
+        self._lib = _lib.require_cuda()
+        self._h = c_void_p()
+        check(self._lib.gp_ctx_create(byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._lib.gp_ctx_free(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def geodesic_embed_host(edge_index, num_nodes: int, anchors, x=None, symmetrize: bool = False,
-                        want_hops: bool = False, out: torch.Tensor | None = None):
+                        want_hops: bool = False, out: torch.Tensor | None = None, ctx: HostContext | None = None):
     """One C-ABI call with HOST buffers: returns (features cpu float32 [N, F+K], hops|None, stats).
 
     This is the boundary the reference-side stub binds: host
@@ -305,8 +326,13 @@ def geodesic_embed_host(edge_index, num_nodes: int, anchors, x=None, symmetrize:
         out = torch.empty((n, f + k), dtype=torch.float32)
     hops = torch.empty((n, k), dtype=torch.uint16) if want_hops else None
     st = MsbfsStats()
-    check(lib.gp_geodesic_embed_host(_ptr(ei), ei.size(1), n, _lib.GP_CSR_SYMMETRIZE if symmetrize else 0,
-                                     _ptr(a), k, _ptr(x), f, _ptr(out), f + k, f, _ptr(hops), byref(st)))
+    flags = _lib.GP_CSR_SYMMETRIZE if symmetrize else 0
+    if ctx is None:
+        check(lib.gp_geodesic_embed_host(_ptr(ei), ei.size(1), n, flags, _ptr(a), k, _ptr(x), f, _ptr(out), f + k, f,
+                                         _ptr(hops), byref(st)))
+    else:
+        check(lib.gp_geodesic_embed_host_ctx(ctx._h, _ptr(ei), ei.size(1), n, flags, _ptr(a), k, _ptr(x), f, _ptr(out),
+                                             f + k, f, _ptr(hops), byref(st)))
     return out, hops, st.as_dict()
 
 

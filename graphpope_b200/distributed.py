@@ -300,7 +300,7 @@ class PushExchange:
     Sharing one process (tests: several "ranks" on one GPU) is supported through ``peers=``.
     """
 
-    def __init__(self, engine, group=None, world=None, rank=None):
+    def __init__(self, engine, group=None, world=None, rank=None, grid_blocks=0):
         import ctypes
 
         from . import _lib
@@ -314,6 +314,8 @@ class PushExchange:
             raise ValueError("the push exchange covers the GPUs of one NVSwitch node (<= 8 ranks)")
         self._h = c_void_p()
         check(self.lib.gp_exchange_create(engine.bfs._h, self.world, self.rank, ctypes.byref(self._h)))
+        if grid_blocks:  # ranks sharing one GPU (tests): partial grids, so that all of them are resident at once
+            check(self.lib.gp_exchange_set_grid(self._h, int(grid_blocks)))
         self._opened = []
         self._pad = {}
         if world is None and self.world > 1:  # one process per GPU: CUDA IPC mappings of the other ranks' buffers

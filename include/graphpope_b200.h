@@ -61,7 +61,8 @@ enum gp_cdist_mode {
 
 typedef struct gp_csr gp_csr_t;     /* de-duplicated digraph in CSR form          */
 typedef struct gp_msbfs gp_msbfs_t; /* multi-source BFS workspace + results       */
-typedef struct gp_exchange gp_exchange_t; /* NVLink push-exchange buffers of one rank */
+typedef struct gp_exchange gp_exchange_t; /* exchange buffers of one rank (gp_exchange.cu) */
+typedef struct gp_ctx gp_ctx_t;     /* state of the one-call host entry: handles, staging, stream */
 
 typedef struct gp_csr_info {
     int64_t num_nodes;
@@ -106,6 +107,10 @@ int gp_csr_info(gp_csr_t *csr, gp_csr_info_t *info, gp_stream_t stream);
  * lists v with u->v), 1 in-edges (row v lists u with u->v).  d_rowptr int32[N+1],
  * d_col int32[>= num_edges].  Rows are ascending and unique.                    */
 int gp_csr_export(gp_csr_t *csr, int which, int32_t *d_rowptr, int32_t *d_col, gp_stream_t stream);
+/* Diagnostics (GP_CSR_TRACE=1 in the environment): milliseconds of the stages of the last build (memsets, count, scan,
+ * scatter, row sort, row scan, descriptors) from events recorded after every launch; *num = values written
+ * (<= cap).  syncs.                                                                                          */
+int gp_csr_trace_ms(gp_csr_t *csr, float *ms, int32_t cap, int32_t *num);
 int gp_csr_free(gp_csr_t *csr);
 
 /* ------------------------------------------------------------------ MS-BFS
@@ -225,6 +230,9 @@ int gp_geodesic_run_exchange(gp_csr_t *csr, gp_msbfs_t *bfs, gp_exchange_t *xchg
 int gp_exchange_run(gp_exchange_t *xchg, const float *d_x, int64_t num_features, int64_t ld_x, float *d_out,
                     int64_t ld_out, int64_t col_offset, gp_stream_t stream);
 int gp_exchange_status(gp_exchange_t *xchg, int32_t *deep, gp_stream_t stream);
+/* Tuning / tests: cap the cooperative grid of the fused kernel (ranks sharing one GPU must all be resident at once,
+ * since they wait for each other's flags); 0 = one full wave.                                                 */
+int gp_exchange_set_grid(gp_exchange_t *xchg, int32_t max_blocks);
 /* Diagnostics, syncs the device: globaltimer stamps (ns) of the last step: [0] block 0 starts, [1] block 0 has packed
  * its share, [2] block 0 has seen every peer's flag, [3] the last block leaves. */
 int gp_exchange_trace(gp_exchange_t *xchg, uint64_t *h_stamps8);
@@ -246,6 +254,19 @@ int gp_geodesic_embed_host(const int64_t *h_edge_index, int64_t num_edges, int64
                            const float *h_x, int64_t num_features,
                            float *h_out, int64_t ld_out, int64_t col_offset,
                            uint16_t *h_hops, gp_msbfs_stats_t *stats);
+
+/* The same with an explicit context.  A context owns everything the one-call entry keeps between calls (CSR and
+ * MS-BFS handles, device staging, its stream, the pinned ring for pageable outputs); it serves one call at a time, and
+ * contexts are independent: two host threads with two contexts do not serialise.  gp_geodesic_embed_host uses one
+ * process-wide default context.  The library keeps no other mutable global state: captured CUDA graphs belong to the
+ * MS-BFS handle they were captured for, environment switches are read once per process.                          */
+int gp_ctx_create(gp_ctx_t **out);
+int gp_ctx_free(gp_ctx_t *ctx);
+int gp_geodesic_embed_host_ctx(gp_ctx_t *ctx, const int64_t *h_edge_index, int64_t num_edges, int64_t num_nodes,
+                               uint32_t csr_flags, const int64_t *h_anchors, int64_t num_anchors,
+                               const float *h_x, int64_t num_features,
+                               float *h_out, int64_t ld_out, int64_t col_offset,
+                               uint16_t *h_hops, gp_msbfs_stats_t *stats);
 
 /* Host side of concat_into_features (utils.py:129-135) for results that arrive as a separate
  * [N, block_cols] block: out[:, 0:F] = x, out[:, F:F+block_cols] = block, threaded row copies.      */

@@ -444,7 +444,6 @@ def test_push_exchange_virtual_ranks_on_one_gpu(dev, monkeypatch, world, k, f):
     from ctypes import c_void_p
 
     from graphpope_b200 import _lib, distributed as gpd
-    monkeypatch.setenv("GP_XCHG_GRID", "24")
     lib = _lib.load()
     n = 3000
     ei = synth.chung_lu_symmetric(n, 18000, 2.2, seed=5)
@@ -453,7 +452,7 @@ def test_push_exchange_virtual_ranks_on_one_gpu(dev, monkeypatch, world, k, f):
     ei_d = torch.as_tensor(ei).cuda()
     x = torch.randn(n, f, device="cuda")
     engines = [dev.GeodesicEngine(n, ei.shape[1], per) for _ in range(world)]
-    xch = [gpd.PushExchange(engines[r], world=world, rank=r) for r in range(world)]
+    xch = [gpd.PushExchange(engines[r], world=world, rank=r, grid_blocks=24) for r in range(world)]
     for r in range(world):
         for q in range(world):
             if q != r:
@@ -492,3 +491,54 @@ def test_pageable_output_ring_equals_pinned_output(dev):
     pageable = torch.full((n, f + k), float("nan"))
     dev.geodesic_embed_host(torch.as_tensor(ei), n, anchors, x, out=pageable)
     assert torch.equal(pageable, pinned) and torch.equal(pageable[:, :f], x)
+
+
+def test_two_host_threads_with_their_own_contexts(dev):
+    """gp_ctx_t: two host threads, each with its own context (handles, stream, staging), run the one-call host entry
+    at the same time on different graphs; both results equal the oracle.  No state is shared between contexts."""
+    import threading
+    from oracle import cbfs, geodesic
+    jobs = []
+    for seed, n, k in ((1, 5000, 40), (2, 9000, 96)):
+        ei = np.concatenate([synth.chung_lu_symmetric(n, 6 * n, 2.2, seed=seed), synth.random_digraph(n, n // 4, seed=seed + 7)], axis=1)
+        anchors = np.random.default_rng(seed).integers(0, n, k)
+        x = np.random.default_rng(seed + 1).standard_normal((n, 9)).astype(np.float32)
+        jobs.append((ei, n, anchors, x, geodesic.concat_features(x, cbfs.geodesic_features(ei, n, anchors))))
+    results, errors = [None, None], []
+
+    def work(i):
+        try:
+            ctx = dev.HostContext()
+            ei, n, anchors, x, _ = jobs[i]
+            for _ in range(5):
+                results[i] = dev.geodesic_embed_host(torch.as_tensor(ei), n, anchors, torch.as_tensor(x), ctx=ctx)[0]
+            ctx.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for i in range(2):
+        assert np.array_equal(results[i].numpy().view(np.uint32), jobs[i][4].view(np.uint32)), i
+
+
+def test_two_hundred_runs_are_identical(dev, flickr):
+    """Stress for the hand-rolled grid barrier and the hub-row hand-off: 200 back-to-back runs on the Flickr-shaped
+    graph (graph-replayed pipeline, then eager MS-BFS launches) must give the same hop matrix every time."""
+    shape, ei, anchors = flickr
+    n = shape.num_nodes
+    eng = dev.GeodesicEngine(n, ei.shape[1], 256)
+    ei_d, a_d = torch.as_tensor(ei).cuda(), torch.as_tensor(anchors).cuda()
+    out = torch.empty(n, 256, device="cuda")
+    eng.run(ei_d, a_d, None, out)
+    first = eng.bfs.hops_u16().view(torch.int16).clone()
+    first_out = out.clone()
+    for i in range(100):
+        eng.run(ei_d, a_d, None, out)
+        assert torch.equal(out, first_out), i
+    for i in range(100):
+        eng.bfs.run(a_d)
+        assert torch.equal(eng.bfs.hops_u16().view(torch.int16), first), i
+    assert eng.bfs.stats()["max_level"] >= 5

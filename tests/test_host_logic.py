@@ -149,6 +149,45 @@ def test_host_concat_matches_torch_cat():
         assert torch.isnan(wide[:, 0]).all() and torch.isnan(wide[:, -2:]).all()
 
 
+def _concat_in_child(q):
+    import ctypes
+
+    import numpy as np  # (no torch ops here: torch's own thread pool does not survive fork() either)
+
+    from graphpope_b200 import _lib
+    lib = _lib.load()
+    n, f = 6000, 400  # 2.4 M elements: above the threshold that hands the copy to the worker pool
+    x = np.arange(n * f, dtype=np.float32).reshape(n, f)
+    out = np.zeros((n, f + 4), dtype=np.float32)
+    rc = lib.gp_host_concat(ctypes.c_void_p(x.ctypes.data), f, None, 0, n, ctypes.c_void_p(out.ctypes.data), f + 4)
+    q.put(rc == 0 and bool(np.array_equal(out[:, :f], x)))
+
+
+def test_host_copy_pool_survives_fork():
+    """The worker threads of the host row-copy pool do not exist in a forked child (DataLoader workers,
+    multiprocessing): the child must copy the rows itself instead of waiting for them forever."""
+    import ctypes
+    import multiprocessing as mp
+
+    import torch
+
+    from graphpope_b200 import _lib
+    lib = _lib.load()
+    x = torch.ones(6000, 400)
+    out = torch.zeros(6000, 404)
+    assert lib.gp_host_concat(ctypes.c_void_p(x.data_ptr()), 400, None, 0, 6000, ctypes.c_void_p(out.data_ptr()), 404) == 0
+    ctx = mp.get_context("fork")  # the pool now exists in this process
+    q = ctx.Queue()
+    p = ctx.Process(target=_concat_in_child, args=(q,))
+    p.start()
+    p.join(60)
+    alive = p.is_alive()
+    if alive:
+        p.kill()
+    assert not alive, "gp_host_concat deadlocked in a forked child"
+    assert q.get(timeout=5) is True
+
+
 def test_block_cache_key_and_hit_path(tmp_path, monkeypatch):
     """GRAPHPOPE_CACHE_DIR (SURVEY §8f rank 4): the [N, K] block is stored once and served from disk after;
     the key depends on the graph, the anchors and the options."""
