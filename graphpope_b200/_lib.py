@@ -70,6 +70,7 @@ SIGNATURES = {
     "gp_msbfs_run": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "gp_msbfs_hops_u16": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "gp_msbfs_features": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p]),
+    "gp_msbfs_set_push": (c_int, [c_void_p, c_int32]),
     "gp_msbfs_stats": (c_int, [c_void_p, POINTER(MsbfsStats), c_void_p]),
     "gp_msbfs_free": (c_int, [c_void_p]),
     "gp_geodesic_run": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64,

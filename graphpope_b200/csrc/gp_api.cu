@@ -81,7 +81,7 @@ const GpEnv &gp_env()
         e.bfs_no_map = getenv("GP_BFS_NO_MAP") != nullptr;
         e.bfs_mapg = getenv("GP_BFS_MAPG") != nullptr;
         e.bfs_trace = getenv("GP_BFS_TRACE") != nullptr;
-        e.bfs_push = geti("GP_BFS_PUSH", 1);
+        e.bfs_push = geti("GP_BFS_PUSH", 0);
         e.xchg_grid = geti("GP_XCHG_GRID", 0);
         e.xchg_debug = geti("GP_XCHG_DEBUG", 0);
         e.pdl = geti("GP_PDL", 1);
@@ -455,7 +455,10 @@ int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t 
     }
     if (rc == GP_OK) {
         GpRange r("graphpope:msbfs");
+        bfs->push_edges = d_ei;  // the caller's edge buffer is alive for this call: hop 1 may scan it (push direction)
+        bfs->push_num_edges = e;
         rc = gp_msbfs_run(bfs, d_anchors, k, s);
+        bfs->push_edges = nullptr;
     }
     if (side_copy) GP_CUDA_CHECK(cudaStreamWaitEvent(s, sc.join, 0));  // always re-join: a capture must not end forked
     GP_TRY(rc);

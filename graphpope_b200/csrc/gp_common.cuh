@@ -57,7 +57,7 @@ struct GpEnv {
     int bfs_no_map;      // GP_BFS_NO_MAP: per-hop bitmaps off
     int bfs_mapg;        // GP_BFS_MAPG: per-hop bitmaps read from global memory
     int bfs_trace;       // GP_BFS_TRACE: per-level clocks
-    int bfs_push;        // GP_BFS_PUSH (default 1): hop 1 as an edge scan from the anchors
+    int bfs_push;        // GP_BFS_PUSH (default 0): hop 1 in push direction, as a scan of the raw edge list (measured slower)
     int xchg_grid;       // GP_XCHG_GRID: cap on the exchange kernel's grid (tests: several ranks on one GPU)
     int xchg_debug;      // GP_XCHG_DEBUG
     int pdl;             // GP_PDL (default 1): programmatic dependent launch inside the csr build

@@ -70,6 +70,9 @@ struct BfsParams {
     int *status;
     u64 *counters;
     u64 *trace;                     // optional per-warp phase clocks (diagnostics), else nullptr
+    const long long *push_ei;       // raw edge_index [2][push_e] for the hop-1 push (fused pipeline only), else nullptr
+    long long push_e;
+    int push_sym;                   // the CSR was built with GP_CSR_SYMMETRIZE: every edge also counts reversed
 };
 
 template <int VW>
@@ -242,8 +245,83 @@ __device__ __forceinline__ void load_tile(const BfsParams &p, const int *s_ent_b
     cols = make_int4(c[0], c[1], c[2], c[3]);
 }
 
+// ---- hop 1 in PUSH direction.  The frontier is the K anchors: pulling makes every row look its neighbours up in the
+// anchor bitmap (7-8 K cycles for the 2 K rows that find one).  Instead the raw edge list the CSR was built from is
+// scanned once, coalesced: an edge u -> a whose head is an anchor pushes the anchor's lanes into row u with L2
+// reductions (duplicate edges are idempotent).  Needs the bitmaps and the edge list, i.e. the fused pipeline; one
+// lane-word batch (K <= 256 per GPU).  Kept out of line so its registers do not weigh on the pull loop.  Returns the
+// number of rows pushed to (an upper bound: a row reached over two edges counts twice; it only sizes the next
+// level's filter).
+template <int WB>
+__device__ __noinline__ int push_hop1(const long long *push_ei, long long push_e, int push_sym, int n, const u64 *seeds,
+                                      u64 *counters, long long gtid, long long gthreads, const u32 *map0, u32 *map_w,
+                                      u64 *nxt, u64 *seen, u32 *s_live32, int *s_any)
+{
+    constexpr int VW = WB;
+    const int lane = threadIdx.x & 31;
+    int nzrows = 0;
+    u64 pushes = 0;
+    auto is_anchor = [&](int v) { return ((map0[v >> 5] >> (v & 31)) & 1u) != 0; };
+    // One edge whose head v is an anchor: the tail index and the anchor's lane words are requested together, the row
+    // is updated with reductions nobody waits for.
+    auto push_edge = [&](const long long *tail, int v) {
+        u64 lanes[VW], mine[VW];
+        vload<VW>(seeds + (size_t)v * WB, lanes);
+        const long long uu = __ldg(tail);
+        if ((unsigned long long)uu >= (unsigned long long)n) return;
+        const int u = (int)uu;
+        const size_t ou = (size_t)u * WB;
+#pragma unroll
+        for (int i = 0; i < VW; ++i) mine[i] = 0;
+        if (is_anchor(u)) vload<VW>(seeds + ou, mine);  // u is an anchor itself: its hop-0 lanes
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < VW; ++i) {
+            const u64 nw = lanes[i] & ~mine[i];
+            if (nw) {
+                any = true;
+                red_or_u64(nxt + ou + i, nw);
+                red_or_u64(seen + ou + i, nw);
+                atomicOr(&s_live32[i * 2], (u32)nw);
+                atomicOr(&s_live32[i * 2 + 1], (u32)(nw >> 32));
+            }
+        }
+        if (any) {
+            *s_any = 1;
+            red_or_u32(map_w + (u >> 5), 1u << (u & 31));
+            ++nzrows;
+            pushes += VW;
+        }
+    };
+    const long long *src = push_ei, *dst = push_ei + push_e;
+    constexpr int PE = 8;  // edges per thread and trip: one round trip for the whole Flickr-size scan
+    for (long long i0 = gtid; i0 < push_e; i0 += PE * gthreads) {
+        int d[PE];  // node ids fit 32 bits; -1 = out of range (latched by the csr build) or past the end
+#pragma unroll
+        for (int q = 0; q < PE; ++q) {
+            const long long i = i0 + q * gthreads;
+            const long long v = i < push_e ? __ldg(dst + i) : -1;
+            d[q] = (unsigned long long)v < (unsigned long long)n ? (int)v : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < PE; ++q)
+            if (d[q] >= 0 && is_anchor(d[q])) push_edge(src + i0 + q * gthreads, d[q]);
+        if (push_sym) {  // the reversed copy of every edge (GP_CSR_SYMMETRIZE)
+#pragma unroll 1
+            for (int q = 0; q < PE; ++q) {
+                const long long i = i0 + q * gthreads;
+                const long long v = i < push_e ? __ldg(src + i) : -1;
+                if ((unsigned long long)v < (unsigned long long)n && is_anchor((int)v)) push_edge(dst + i, (int)v);
+            }
+        }
+    }
+    for (int m = 16; m; m >>= 1) pushes += shfl_xor_u64(pushes, m);
+    if (lane == 0 && pushes) atomicAdd(counters + 1, pushes);
+    return nzrows;
+}
+
 // WB lane words per node row = one thread loads a whole row (8, 16 or 32 bytes).
-template <int WB, int NT, int MINB, bool MAPG>
+template <int WB, int NT, int MINB, bool MAPG, bool PUSH>
 __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
 {
     constexpr int VW = WB;
@@ -279,6 +357,12 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
     const bool use_map = MAPG || p.map_smem_words > 0;
     u64 gathers = 0;
 
+#define GP_TRACE_PRO(slot)                                                                    \
+    do {                                                                                      \
+        if (p.trace != nullptr && lane == 0)                                                  \
+            p.trace[(((size_t)31 * total_warps + gwarp) << 2) + (slot)] = (u64)clock64();     \
+    } while (0)
+    GP_TRACE_PRO(0);
     for (int i = tid; i < GP_BFS_MAX_LANE_WORDS * 2; i += NT) s_live32[i] = 0;
     if (tid <= GP_NUM_CLASSES) {
         s_ent_base[tid] = p.meta[GP_META_ENT_BASE + tid];
@@ -307,19 +391,38 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
         if (use_map) atomicOr(p.nzmap + (size_t)b * p.nzwords + (size_t)(a >> 5), 1u << (a & 31));  // map of hop 0
     }
     __syncthreads();
+    GP_TRACE_PRO(1);
     const int total_tiles = s_slot_base[GP_NUM_CLASSES] / 32;
     // tile j of this CTA is global tile blockIdx.x + gridDim.x * j
     const int tiles_cta = total_tiles > (int)blockIdx.x ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int cached_tiles = tiles_cta < JT ? tiles_cta : JT;
-    for (int j = warp; j < cached_tiles; j += WARPS) {
-        int4 lead, cols;
-        load_tile(p, s_ent_base, s_slot_base, ((int)blockIdx.x + (int)gridDim.x * j) * 32, lane, lead, cols);
-        s_lead[j * 32 + lane] = lead;
-        s_cols[j * 32 + lane] = cols;
-        for (int b = 0; b < GP_BFS_DONE_BATCHES; ++b) s_done[(b * JT + j) * 32 + lane] = lead.x < 0 ? 1 : 0;
+    // the cached tiles of a warp are fetched together: their descriptor loads, then their column loads, are all in
+    // flight at once (one tile after the other this was 2 dependent round trips per tile before the first level)
+    {
+        constexpr int TPW = JT / WARPS;  // cached tiles per warp
+        int4 lead[TPW], cols[TPW];
+#pragma unroll
+        for (int q = 0; q < TPW; ++q) {
+            const int j = warp + q * WARPS;
+            lead[q] = make_int4(-1, 0, 0, 0);
+            cols[q] = make_int4(-1, -1, -1, -1);
+            if (j < cached_tiles)
+                load_tile(p, s_ent_base, s_slot_base, ((int)blockIdx.x + (int)gridDim.x * j) * 32, lane, lead[q], cols[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < TPW; ++q) {
+            const int j = warp + q * WARPS;
+            if (j < cached_tiles) {
+                s_lead[j * 32 + lane] = lead[q];
+                s_cols[j * 32 + lane] = cols[q];
+                for (int b = 0; b < GP_BFS_DONE_BATCHES; ++b) s_done[(b * JT + j) * 32 + lane] = lead[q].x < 0 ? 1 : 0;
+            }
+        }
     }
     for (int i = tid; i < GP_BFS_DONE_BATCHES * JT; i += NT) s_tdone[i] = 0;
+    GP_TRACE_PRO(2);
     grid_barrier_flags(p.bar + 0, gridDim.x, false, false, &s_bcast, &s_any, &s_notdone, &s_nzrows, s_queue, p.batches);
+    GP_TRACE_PRO(3);
 
     int level = 1, max_level = 0;
     long long nz_prev = p.num_anchors;  // non-zero rows of the frontier about to be read (hop 0: the anchors)
@@ -373,7 +476,20 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
         GP_TRACE(0);
 
         int nzrows = 0;
-        for (int b = 0; b < p.batches; ++b) {
+        // ---- hop 1 in PUSH direction.  The frontier is the K anchors: pulling makes every row look its neighbours up
+        // in the anchor bitmap (7 K cycles for 2 K rows that find one).  Instead the raw edge list the CSR was built
+        // from is scanned once, coalesced: an edge u -> a whose head is an anchor pushes the anchor's lanes into row
+        // u with L2 reductions (duplicate edges are idempotent).  Needs the bitmaps and the edge list (fused pipeline).
+        // hop 1 in push direction (GP_BFS_PUSH=1, fused pipeline, one lane-word batch): see push_hop1
+        const bool push_level = PUSH && level == 1 && map_level;
+        if constexpr (PUSH) {
+            if (push_level) {
+                nzrows += push_hop1<WB>(p.push_ei, p.push_e, p.push_sym, n, p.seeds, p.counters, gtid, gthreads,
+                                        MAPG ? p.nzmap : s_map, map_w, c.nxt, c.seen, s_live32, &s_any);
+                s_notdone = 1;  // no row has been tested for completeness at this hop
+            }
+        }
+        for (int b = 0; b < (push_level ? 0 : p.batches); ++b) {
             u64 lv[VW], live_acc[VW];
 #pragma unroll
             for (int i = 0; i < VW; ++i) {
@@ -536,8 +652,10 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
     if (lane == 0 && gathers) atomicAdd(p.counters, gathers);
     if (gtid == 0) {
         p.status[GP_BFS_ST_MAX_LEVEL] = max_level;
+        const int pushed = (PUSH && use_map) ? 1 : 0;
         p.status[GP_BFS_ST_LEVELS] = level;
-        p.status[GP_BFS_ST_PULL] = level;
+        p.status[GP_BFS_ST_PULL] = level - pushed;
+        p.status[GP_BFS_ST_PUSH] = pushed;
     }
 }
 
@@ -549,16 +667,16 @@ constexpr size_t bfs_cache_bytes()
     return (size_t)tiles * 32 * (2 * sizeof(int4) + GP_BFS_DONE_BATCHES) + (size_t)tiles * GP_BFS_DONE_BATCHES;
 }
 
-template <int WB, int NT, int MINB, bool MAPG>
+template <int WB, int NT, int MINB, bool MAPG, bool PUSH>
 int launch_bfs_variant(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int cfg_id)
 {
     // Frontier bitmaps are staged in shared memory when they fit without costing a resident CTA.
     const int want_map = (int)((size_t)p.map_stride * sizeof(u32));
-    const int key = (cfg_id * 8 + WB) * 4 + 1 + (MAPG ? 2 : 0);
+    const int key = ((cfg_id * 8 + WB) * 4 + 1 + (MAPG ? 2 : 0)) * 2 + (PUSH ? 1 : 0);
     if (h->grid_blocks == 0 || h->grid_cfg != key || h->map_want_bytes != want_map) {
         int occ = 0, occ_map = 0;
         cudaFuncAttributes fa;
-        GP_CUDA_CHECK(cudaFuncGetAttributes(&fa, msbfs_kernel<WB, NT, MINB, MAPG>));
+        GP_CUDA_CHECK(cudaFuncGetAttributes(&fa, msbfs_kernel<WB, NT, MINB, MAPG, PUSH>));
         int smem_optin = 0, dev = 0;
         GP_CUDA_CHECK(cudaGetDevice(&dev));
         GP_CUDA_CHECK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -567,14 +685,14 @@ int launch_bfs_variant(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int
         int dyn_max = cache_bytes + GP_BFS_MAP_SMEM_MAX;
         if (dyn_max > dyn_room) dyn_max = dyn_room;
         GP_REQUIRE(dyn_max >= cache_bytes, GP_ERR_CUDA, "msbfs work cache does not fit in shared memory");
-        GP_CUDA_CHECK(cudaFuncSetAttribute(msbfs_kernel<WB, NT, MINB, MAPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
-        GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, msbfs_kernel<WB, NT, MINB, MAPG>, NT,
+        GP_CUDA_CHECK(cudaFuncSetAttribute(msbfs_kernel<WB, NT, MINB, MAPG, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+        GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, msbfs_kernel<WB, NT, MINB, MAPG, PUSH>, NT,
                                                                     bfs_cache_bytes<WB, NT, MINB>()));
         GP_REQUIRE(occ >= 1, GP_ERR_CUDA, "msbfs kernel does not fit on an SM");
         if (occ > MINB) occ = MINB;
         h->map_smem_bytes = 0;
         if (!MAPG && cache_bytes + want_map <= dyn_max && !gp_env().bfs_no_map) {
-            GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_map, msbfs_kernel<WB, NT, MINB, MAPG>, NT,
+            GP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_map, msbfs_kernel<WB, NT, MINB, MAPG, PUSH>, NT,
                                                                         bfs_cache_bytes<WB, NT, MINB>() + want_map));
             if (occ_map >= occ) h->map_smem_bytes = want_map;
         }
@@ -590,7 +708,7 @@ int launch_bfs_variant(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int
     // inside a graph capture the timing events become event-record nodes (re-recorded on every replay)
     const unsigned ev_flags = gp_is_capturing() ? cudaEventRecordExternal : cudaEventRecordDefault;
     GP_CUDA_CHECK(cudaEventRecordWithFlags(h->ev_start, stream, ev_flags));
-    GP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)msbfs_kernel<WB, NT, MINB, MAPG>, dim3(h->grid_blocks),
+    GP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)msbfs_kernel<WB, NT, MINB, MAPG, PUSH>, dim3(h->grid_blocks),
                                               dim3(NT), args, bfs_cache_bytes<WB, NT, MINB>() + h->map_smem_bytes, stream));
     GP_CUDA_CHECK(cudaEventRecordWithFlags(h->ev_stop, stream, ev_flags));
     return GP_OK;
@@ -604,9 +722,14 @@ int launch_bfs_cfg(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int cfg
     const size_t want_map = (size_t)p.map_stride * sizeof(u32);
     const bool fits = bfs_cache_bytes<WB, NT, MINB>() + want_map <= 200 * 1024 / (size_t)MINB;
     const bool force_global = gp_env().bfs_mapg != 0;  // experiment: never stage the maps
+    // the push variant exists for the default launch shape only (it is an experiment that lost: profiles/r02_notes.md)
+    const bool push = p.push_ei != nullptr && p.batches <= GP_BFS_PUSH_BATCHES && cfg_id == GP_BFS_DEFAULT_CFG &&
+                      !gp_env().bfs_no_map;
     if ((!fits || force_global) && cfg_id == GP_BFS_DEFAULT_CFG && !gp_env().bfs_no_map)
-        return launch_bfs_variant<WB, NT, MINB, true>(h, p, stream, cfg_id);
-    return launch_bfs_variant<WB, NT, MINB, false>(h, p, stream, cfg_id);
+        return push ? launch_bfs_variant<WB, NT, MINB, true, NT == 384 && MINB == 2>(h, p, stream, cfg_id)
+                    : launch_bfs_variant<WB, NT, MINB, true, false>(h, p, stream, cfg_id);
+    return push ? launch_bfs_variant<WB, NT, MINB, false, NT == 384 && MINB == 2>(h, p, stream, cfg_id)
+                : launch_bfs_variant<WB, NT, MINB, false, false>(h, p, stream, cfg_id);
 }
 
 // Launch shapes (threads per CTA, CTAs per SM) trade resident warps against registers per thread,
@@ -790,9 +913,21 @@ extern "C" int gp_msbfs_run(gp_msbfs_t *h, const int64_t *d_anchors, int64_t num
     p.status = h->status;
     p.counters = h->counters;
     p.trace = h->trace;
+    p.push_ei = (h->push_hop1 < 0 ? gp_env().bfs_push : h->push_hop1) ? (const long long *)h->push_edges : nullptr;
+    p.push_e = h->push_num_edges;
+    p.push_sym = (h->csr->flags & GP_CSR_SYMMETRIZE) ? 1 : 0;
     GP_TRY(wb == 1 ? launch_bfs<1>(h, p, stream) : wb == 2 ? launch_bfs<2>(h, p, stream)
                                                              : launch_bfs<4>(h, p, stream));
     h->ran = true;
+    return GP_OK;
+}
+
+extern "C" int gp_msbfs_set_push(gp_msbfs_t *h, int32_t enable)
+{
+    GP_REQUIRE(h != nullptr, GP_ERR_INVALID, "gp_msbfs_set_push: handle is NULL");
+    h->push_hop1 = enable ? 1 : 0;
+    gp_pipe_cache_free(h->pipe_cache);  // captured pipelines hold the other kernel variant
+    h->pipe_cache = nullptr;
     return GP_OK;
 }
 
@@ -835,7 +970,7 @@ extern "C" int gp_msbfs_trace(gp_msbfs_t *h, uint64_t *h_out, int64_t cap_words,
     GP_CUDA_CHECK(cudaDeviceSynchronize());
     *levels = st.levels_run < 32 ? st.levels_run : 32;
     *warps = h->grid_blocks * (h->block_threads / 32);
-    const int64_t words = (int64_t)(*levels) * (*warps) * 4;
+    const int64_t words = (int64_t)32 * (*warps) * 4;  // all 32 rows: row 31 holds the prologue stamps of shallow runs
     GP_REQUIRE(words <= cap_words && words <= GP_BFS_TRACE_WORDS, GP_ERR_INVALID, "gp_msbfs_trace: buffer too small");
     GP_CUDA_CHECK(cudaMemcpy(h_out, h->trace, sizeof(u64) * (size_t)words, cudaMemcpyDeviceToHost));
     return GP_OK;

@@ -9,6 +9,7 @@ constexpr int GP_BFS_PLANES = 16;           // deep-hop distance bit planes (uin
 constexpr int GP_BFS_LEVEL_ARRAYS = 15;     // hops 1..15 are recorded as write-once frontier arrays
 constexpr int GP_BFS_CACHE_ITERS = 4;      // warp-iterations whose work items are cached in shared memory
 constexpr int GP_BFS_MAP_SMEM_MAX = 64 * 1024;  // largest set of frontier bitmaps staged in shared memory
+constexpr int GP_BFS_PUSH_BATCHES = 1;     // hop 1 runs in push direction for up to this many lane-word batches
 constexpr int GP_BFS_DONE_BATCHES = 8;     // batches that keep per-row "done" flags for cached items
 constexpr int GP_MAX_RANKS = 8;             // GPUs of one NVSwitch node
 constexpr int GP_BFS_RESULT_ARRAYS = 1 + GP_BFS_LEVEL_ARRAYS + GP_BFS_PLANES;  // 32
@@ -57,6 +58,11 @@ struct gp_msbfs {
     int map_want_bytes = -1; // map size the cached launch configuration was computed for
     int64_t hub_capacity = 0;
     bool hub_zeroed = false;
+    // raw edge_index the CSR was just built from, valid for the next gp_msbfs_run only (set by the fused pipeline,
+    // which holds the caller's buffer): lets hop 1 run in push direction
+    int push_hop1 = -1;  // hop 1 in push direction: -1 = GP_BFS_PUSH (default off), 0 / 1 = gp_msbfs_set_push
+    const int64_t *push_edges = nullptr;
+    int64_t push_num_edges = 0;
     u64 *packed = nullptr;   // [2 slots][GP_PACKED_ARRAYS][cap words] exchange buffers (allocated on first pack)
     int *deep_flag = nullptr;  // device int: 1 if the last packed run had hops > 15 (packed format invalid)
     int *status = nullptr;      // [GP_BFS_ST_WORDS]

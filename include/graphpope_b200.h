@@ -131,6 +131,10 @@ int gp_msbfs_hops_u16(gp_msbfs_t *bfs, uint16_t *d_dist, int64_t ld, int64_t col
  * IEEE fp32 division (bit-equal to the reference's float64 -> float32 rounding). */
 int gp_msbfs_features(gp_msbfs_t *bfs, const float *d_x, int64_t num_features, int64_t ld_x,
                       float *d_out, int64_t ld_out, int64_t col_offset, gp_stream_t stream);
+/* Direction of hop 1 inside gp_geodesic_run (the fused call holds the raw edge list): 1 = PUSH, an edge scan from the
+ * anchors with L2 reductions; 0 = pull like every other hop (default: on the named graphs the pull sweep, which finds
+ * its column indices in shared memory, is as fast; profiles/r02_notes.md).  Results are identical either way.     */
+int gp_msbfs_set_push(gp_msbfs_t *bfs, int32_t enable);
 /* syncs.  Reports latched GP_ERR_INDEX_RANGE / GP_ERR_LEVEL_OVERFLOW. */
 int gp_msbfs_stats(gp_msbfs_t *bfs, gp_msbfs_stats_t *stats, gp_stream_t stream);
 /* syncs on the kernel's own events.  Device time of the last MS-BFS kernel launch alone (CUDA

@@ -542,3 +542,29 @@ def test_two_hundred_runs_are_identical(dev, flickr):
         eng.bfs.run(a_d)
         assert torch.equal(eng.bfs.hops_u16().view(torch.int16), first), i
     assert eng.bfs.stats()["max_level"] >= 5
+
+
+@pytest.mark.parametrize("symmetrize", [False, True])
+@pytest.mark.parametrize("k", [1, 64, 100, 256])
+def test_hop1_push_direction_matches_pull_and_oracle(dev, k, symmetrize):
+    """gp_msbfs_set_push: hop 1 of the fused pipeline as a push (edge scan from the anchors, L2 reductions) on an
+    asymmetric multigraph with self loops and repeated edges, duplicate anchors and anchors adjacent to anchors; with
+    and without GP_CSR_SYMMETRIZE.  Bit-equal to the pull result and to the oracle; the stats report one push level."""
+    n = 5000
+    ei = np.concatenate([synth.chung_lu_symmetric(n, 30000, 2.2, seed=13), synth.random_digraph(n, 4000, seed=14)], axis=1)
+    rng = np.random.default_rng(k)
+    anchors = rng.integers(0, n, k)
+    if k > 2:
+        anchors[1] = anchors[0]              # duplicate anchor
+        anchors[2] = ei[1, ei[0] == anchors[0]][0] if (ei[0] == anchors[0]).any() else anchors[2]  # neighbour of an anchor
+    want = _oracle_hops(ei, n, anchors, symmetrize)
+    ei_d, a_d = torch.as_tensor(ei).cuda(), torch.as_tensor(anchors).cuda()
+    eng = dev.GeodesicEngine(n, ei.shape[1], k, symmetrize)
+    for push in (True, False):
+        eng.bfs.set_push(push)
+        for _ in range(3):  # eager, captured, replayed
+            eng.run(ei_d, a_d)
+        hops = eng.bfs.hops_u16().cpu().numpy()
+        st = eng.bfs.stats()
+        assert np.array_equal(hops, want), push
+        assert st["push_levels"] == (1 if push else 0) and st["pull_levels"] + st["push_levels"] == st["levels_run"]
