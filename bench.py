@@ -475,7 +475,24 @@ for _ in range(5):
     t = time.perf_counter(); out2 = utils.Graphpope(d, "flickr", "geodesic", "stochastic", k, None, num_workers=6)
     warm.append(time.perf_counter() - t)
 assert torch.equal(out, out2) and tuple(out.shape) == (n, f + k) and not out.is_cuda
-print(json.dumps({"import_s": t_import, "cold_ms": cold * 1e3, "warm_pageable_ms": float(np.median(warm)) * 1e3}))
+# what a fresh pageable [N, F+K] tensor costs by itself (allocation + first touch of 270 MB: the reference's
+# torch.cat pays the same), and the same call into a tensor that already exists
+touch = []
+for _ in range(3):
+    t = time.perf_counter(); z = torch.empty(n, f + k); z.zero_(); touch.append(time.perf_counter() - t); del z
+from graphpope_b200 import device as dev
+reuse = torch.empty(n, f + k); reuse.zero_()
+np.random.seed(42); anchors = np.random.choice(np.arange(n), k)
+into = []
+for _ in range(5):
+    t = time.perf_counter(); dev.geodesic_embed_host(d.edge_index, n, anchors, d.x, out=reuse); into.append(time.perf_counter() - t)
+assert torch.equal(reuse, out)
+print(json.dumps({"import_s": t_import, "cold_ms": cold * 1e3, "warm_pageable_ms": float(np.median(warm)) * 1e3,
+                  "fresh_output_tensor_first_touch_ms": float(np.median(touch)) * 1e3,
+                  "warm_pageable_into_existing_tensor_ms": float(np.median(into)) * 1e3,
+                  "note": "cold = first utils.Graphpope call of a fresh process on pageable tensors: library load, CUDA "
+                          "context, allocations, lazy module load and the call; warm = later calls, each returning a NEW "
+                          "pageable tensor (allocation + first touch of its pages included, as in the reference's torch.cat)"}))
 """
 
 

@@ -843,7 +843,6 @@ extern "C" int gp_csr_create(int64_t num_nodes, int64_t edge_capacity, uint32_t 
             rc = (e == cudaErrorMemoryAllocation) ? GP_ERR_OOM : GP_ERR_CUDA;
         }
     };
-    alloc((void **)&c->deg, (nn + 1) * sizeof(int));
     alloc((void **)&c->row_start, (nn + 1) * sizeof(int));
     alloc((void **)&c->cursor, (nn + 1) * sizeof(int));
     alloc((void **)&c->col, kc * sizeof(int));
@@ -854,8 +853,10 @@ extern "C" int gp_csr_create(int64_t num_nodes, int64_t edge_capacity, uint32_t 
     // memset per build clears everything), then the ticket counters
     c->scan_b_offset = (size_t)scan_tiles(num_nodes + 1) * ScanStatus<1>::STRIDE;
     c->scan_status_words = c->scan_b_offset + (size_t)scan_tiles(num_nodes + 1) * ScanStatus<ROW_CH>::STRIDE + 8;
-    alloc((void **)&c->meta, (GP_META_WORDS + c->scan_status_words) * sizeof(int));
+    // one allocation, cleared by ONE memset per build: meta | look-back words | raw edge counts (deg)
+    alloc((void **)&c->meta, (GP_META_WORDS + c->scan_status_words + nn + 1) * sizeof(int));
     c->scan_status = c->meta != nullptr ? c->meta + GP_META_WORDS : nullptr;
+    c->deg = c->meta != nullptr ? c->scan_status + c->scan_status_words : nullptr;
     if (rc != GP_OK) {
         gp_csr_free(c);
         return rc;
@@ -885,7 +886,6 @@ extern "C" int gp_csr_free(gp_csr_t *c)
     for (int i = 0; i < 16; ++i) cudaFree(c->scratch[i]);
     for (int i = 0; i < 12; ++i)
         if (c->trace_ev[i]) cudaEventDestroy(c->trace_ev[i]);
-    cudaFree(c->deg);
     cudaFree(c->row_start);
     cudaFree(c->cursor);
     cudaFree(c->col);
@@ -921,12 +921,11 @@ extern "C" int gp_csr_build(gp_csr_t *c, const int64_t *d_edge_index, int64_t nu
                                  gp_is_capturing() ? cudaEventRecordExternal : cudaEventRecordDefault);
     };
     mark();
-    GP_CUDA_CHECK(cudaMemsetAsync(c->meta, 0, (GP_META_WORDS + c->scan_status_words) * sizeof(int), stream));
+    GP_CUDA_CHECK(cudaMemsetAsync(c->meta, 0, (GP_META_WORDS + c->scan_status_words + (size_t)n + 1) * sizeof(int), stream));
     if (n > 0) {
         const long long *ei = (const long long *)d_edge_index;
         const int vec = (reinterpret_cast<uintptr_t>(ei) & 15u) == 0 && num_edges % 2 == 0;  // both rows 16-byte aligned
         int *ticket_a = c->scan_status + c->scan_status_words - 8, *ticket_b = ticket_a + 1;
-        GP_CUDA_CHECK(cudaMemsetAsync(c->deg, 0, (size_t)(n + 1) * sizeof(int), stream));
         mark();
         if (num_edges > 0)
             GP_LAUNCH(count_edges_kernel, launch_blocks(gp_ceil_div(num_edges, 4), 256), 256, 0, stream, ei, num_edges, n, sym,

@@ -806,16 +806,18 @@ extern "C" int gp_msbfs_create(const gp_csr_t *csr, int64_t max_anchors, gp_msbf
     // lane state, one allocation: seed frontier, then the result block R[0..31] (reached mask, 15
     // first-reached-at-hop arrays, 16 deep-hop bit planes), then three rotating frontiers for hops >= 16.  The
     // seed frontier sits right before R[0] and R[1] so one memset clears the three arrays a run starts from.
-    alloc((void **)&h->lane_buf, (size_t)(1 + GP_BFS_RESULT_ARRAYS + 3) * words * sizeof(u64));
-    h->hub_capacity = csr->hub_capacity;
-    alloc((void **)&h->hub_acc, (size_t)h->hub_capacity * (size_t)h->cap_words_per_node * sizeof(u64));
-    alloc((void **)&h->hub_cnt, (size_t)h->hub_capacity * (size_t)h->cap_words_per_node * sizeof(u32));
-    // small per-run state, one allocation cleared by one memset:
-    //   live [3][MAX_LANE_WORDS] u64 | bar [8] u64 | counters [4] u64 | status [ST_WORDS] int | nzmap
+    // The small per-run state sits right in front of them in the same allocation, so ONE memset per run clears it
+    // together with those three arrays:
+    //   live [3][MAX_LANE_WORDS] u64 | bar [8] u64 | counters [4] u64 | status [16] int | nzmap | pad || seeds | R[0] | ...
     h->nzwords = (h->num_nodes + 31) / 32;
     h->scratch_bytes = (size_t)(3 * GP_BFS_MAX_LANE_WORDS + 8 + 4) * sizeof(u64) + 16 * sizeof(int) +
                        3 * ((size_t)batches * (size_t)h->nzwords + 4) * sizeof(u32);
-    alloc((void **)&h->scratch, h->scratch_bytes);
+    h->scratch_bytes = (h->scratch_bytes + 255) / 256 * 256;
+    alloc((void **)&h->scratch, h->scratch_bytes + (size_t)(1 + GP_BFS_RESULT_ARRAYS + 3) * words * sizeof(u64));
+    h->lane_buf = h->scratch != nullptr ? reinterpret_cast<u64 *>((char *)h->scratch + h->scratch_bytes) : nullptr;
+    h->hub_capacity = csr->hub_capacity;
+    alloc((void **)&h->hub_acc, (size_t)h->hub_capacity * (size_t)h->cap_words_per_node * sizeof(u64));
+    alloc((void **)&h->hub_cnt, (size_t)h->hub_capacity * (size_t)h->cap_words_per_node * sizeof(u32));
     if (rc == GP_OK) {
         h->live = reinterpret_cast<u64 *>(h->scratch);
         h->bar = h->live + 3 * GP_BFS_MAX_LANE_WORDS;
@@ -841,8 +843,7 @@ extern "C" int gp_msbfs_free(gp_msbfs_t *h)
 {
     if (!h) return GP_OK;
     gp_pipe_cache_free(h->pipe_cache);
-    cudaFree(h->lane_buf);
-    cudaFree(h->scratch);
+    cudaFree(h->scratch);  // the lane arrays live in the same allocation
     cudaFree(h->hub_acc);
     cudaFree(h->hub_cnt);
     cudaFree(h->packed);
@@ -872,15 +873,14 @@ extern "C" int gp_msbfs_run(gp_msbfs_t *h, const int64_t *d_anchors, int64_t num
     const int64_t n = h->num_nodes;
     const size_t words = (size_t)wb * batches * (size_t)n;
     const int map_stride = (int)(((int64_t)batches * h->nzwords + 3) / 4 * 4);
-    const size_t run_scratch = (size_t)((char *)h->nzmap - (char *)h->scratch) + 3 * (size_t)map_stride * sizeof(u32);
-    GP_CUDA_CHECK(cudaMemsetAsync(h->scratch, 0, run_scratch, stream));  // live, bar, counters, status, maps
     if (n == 0 || num_anchors == 0) {
+        GP_CUDA_CHECK(cudaMemsetAsync(h->scratch, 0, h->scratch_bytes, stream));  // status / counters, read by gp_msbfs_stats
         h->ran = true;
         return GP_OK;
     }
-    // seeds, reached mask and the hop-1 frontier; every later frontier array is cleared by the kernel one level
-    // before it is written
-    GP_CUDA_CHECK(cudaMemsetAsync(h->lane_buf, 0, 3 * words * sizeof(u64), stream));
+    // ONE memset: live, bar, counters, status, maps + seeds, reached mask and the hop-1 frontier; every later frontier
+    // array is cleared by the kernel one level before it is written
+    GP_CUDA_CHECK(cudaMemsetAsync(h->scratch, 0, h->scratch_bytes + 3 * words * sizeof(u64), stream));
     if (!h->hub_zeroed) {
         // the kernel leaves these zeroed again (the finalising chunk resets its row's words)
         GP_CUDA_CHECK(cudaMemsetAsync(h->hub_acc, 0, (size_t)h->hub_capacity * h->cap_words_per_node * sizeof(u64), stream));
