@@ -409,6 +409,7 @@ def secondary_c5(dev, gpd, synth, world, rank, local_rank, dist, barrier, peak_g
     anchors = synth.stochastic_anchors(n, k, 42)
     a_d = torch.as_tensor(anchors).cuda()
     engine = dev.GeodesicEngine(n, ei_d.size(1), k // world)
+    engine.bfs.set_stage_events(True)  # stage clocks (12 us of event nodes in a step of tens of milliseconds)
     peer = gpd.PeerAssembly(engine) if world > 1 else None
     x_d = torch.zeros(n, f, device="cuda")  # x = zeros [N, 100] for C5
     out_d = torch.empty(n, f + k, device="cuda")
@@ -614,7 +615,7 @@ def main():
     e_unique = engine.csr.info()["num_edges"]
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stage_ms = []
+    stage_ms, bfs_dev_ms = [], []
     launches0 = dev.launch_count()
     align_t = torch.zeros(1, device="cuda")
     barrier()
@@ -629,7 +630,7 @@ def main():
         starts[i].record()
         step()
         stops[i].record()
-        stage_ms.append(engine.bfs.pipeline_stage_ms())  # event nodes of the replayed graph (syncs on the last one)
+        bfs_dev_ms.append(engine.bfs.kernel_device_ms())  # the kernel's own %globaltimer stamps (syncs)
     barrier()
     launches = dev.launch_count() - launches0
     if peer is not None and hasattr(peer, "trace"):
@@ -655,6 +656,27 @@ def main():
 
     # ---- parity of what the timed loop produced (untimed)
     parity_ok, parity_info = check_device_result(out_d, x_d, ei, n, f, anchors, world, rank, dist)
+
+    # ---- stage times: a second pass over the same step with CUDA-event nodes inside the replayed graph (csr build |
+    # MS-BFS kernel | epilogue).  An event-record node costs ~4 us of the step, so the timed loop above runs without
+    # them (it reads the MS-BFS kernel's own device-clock stamps instead); this pass is not part of `value`.
+    engine.bfs.set_stage_events(True)
+    for _ in range(3):
+        step()
+    barrier()
+    ev_pass_ms = []
+    for i in range(args.steps):
+        flush_l2(i)
+        if world > 1:
+            dist.all_reduce(align_t)
+        a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_ev.record(); step(); b_ev.record()
+        stage_ms.append(engine.bfs.pipeline_stage_ms())
+        ev_pass_ms.append(a_ev.elapsed_time(b_ev))
+    barrier()
+    engine.bfs.set_stage_events(False)
+    stage_ok, _ = check_device_result(out_d, x_d, ei, n, f, anchors, world, rank, dist)
+    parity_ok = parity_ok and stage_ok
 
     peaks = {}
     try:
@@ -727,10 +749,11 @@ def main():
         b_bfs = bytes_bfs(n, e_unique, K_PER_GPU)
         b_csr = bytes_csr(n, ei.shape[1], e_unique)
         b_epi = bytes_epilogue(n, k_total, f)
-        st = np.asarray(stage_ms)  # [steps, 3] csr, bfs kernel, epilogue
+        st = np.asarray(stage_ms)  # [steps, 3] csr, bfs kernel, epilogue — from the event pass
         csr_ms, bfs_avg_ms, epi_ms = [float(v) for v in st.mean(axis=0)]
+        ev_step_ms = float(np.mean(ev_pass_ms))
         if world > 1 and not hasattr(peer, "trace"):  # pull path: the graph ends at the pack, exchange + decode follow it
-            epi_ms = max(ms_per_step - csr_ms - bfs_avg_ms, 1e-6)
+            epi_ms = max(ev_step_ms - csr_ms - bfs_avg_ms, 1e-6)
         achieved = b_bfs / (bfs_avg_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None
         try:
@@ -766,12 +789,18 @@ def main():
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
                          "algorithmic_bytes": b_bfs, "kernel_ms": bfs_avg_ms,
-                         "kernel_share_of_step": bfs_avg_ms / ms_per_step,
+                         "kernel_ms_device_clock_in_timed_loop": float(np.mean(bfs_dev_ms)),
+                         "kernel_share_of_step": float(np.mean(bfs_dev_ms)) / ms_per_step,
+                         "timing_note": "kernel_ms and `stages` = CUDA events recorded as nodes of the replayed graph in a "
+                                        "second pass of the same step (rank 0); each event node costs ~4 us, so the timed loop "
+                                        "runs without them and reads the kernel's own %globaltimer stamps (entry -> end of the "
+                                        "last level; excludes the cooperative launch and the exit)",
                          "stages": {"csr_build": entry(csr_ms, b_csr), "msbfs_kernel": entry(bfs_avg_ms, b_bfs),
                                     ("exchange_and_epilogue" if world > 1 else "epilogue"): entry(epi_ms, b_epi),
                                     "step": entry(ms_per_step, b_csr + b_bfs + b_epi),
-                                    "note": "stage times are event nodes inside the replayed CUDA graph of the timed step "
-                                            "(rank 0); bytes per DESIGN.md §4"}},
+                                    "step_with_event_nodes_ms": ev_step_ms,
+                                    "note": "stage times: event nodes inside the replayed CUDA graph, second pass (rank 0); "
+                                            "`step` = the timed loop; bytes per DESIGN.md §4"}},
             "bfs": {"levels": stats["levels_run"], "max_level": stats["max_level"],
                     "pull_levels": stats["pull_levels"], "push_levels": stats["push_levels"],
                     "edges_examined_per_WE": stats["edges_examined"] / max(1, w_words * e_unique),

@@ -58,6 +58,8 @@ SIGNATURES = {
     "gp_device_info": (c_int, [POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), c_char_p, c_int64]),
     "gp_launch_count": (c_int64, []),
     "gp_msbfs_kernel_ms": (c_int, [c_void_p, POINTER(ctypes.c_float)]),
+    "gp_msbfs_set_stage_events": (c_int, [c_void_p, c_int32]),
+    "gp_msbfs_kernel_device_ns": (c_int, [c_void_p, POINTER(c_uint64), c_void_p]),
     "gp_pipeline_stage_ms": (c_int, [c_void_p, POINTER(ctypes.c_float)]),
     "gp_msbfs_trace": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_int32), POINTER(c_int32)]),
     "gp_csr_create": (c_int, [c_int64, c_int64, c_uint32, POINTER(c_void_p)]),

@@ -84,6 +84,7 @@ const GpEnv &gp_env()
         e.bfs_push = geti("GP_BFS_PUSH", 0);
         e.xchg_grid = geti("GP_XCHG_GRID", 0);
         e.xchg_debug = geti("GP_XCHG_DEBUG", 0);
+        e.stage_events = geti("GP_STAGE_EVENTS", 0);
         e.pdl = geti("GP_PDL", 1);
         e.csr_trace = geti("GP_CSR_TRACE", 0);
         e.nvtx = geti("GP_NVTX", 1);
@@ -376,6 +377,7 @@ struct PipeEntry {
     cudaGraphExec_t exec = nullptr;
     int seen = 0;
     int kernels = 0;  // kernel nodes in the captured graph
+    bool has_events = false;  // captured with the stage-event nodes
     uint64_t stamp = 0;
 };
 
@@ -447,7 +449,8 @@ int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t 
     }
     // stage clocks of the step (gp_pipeline_stage_ms): inside a capture these become event-record nodes
     const unsigned ev_flags = gp_is_capturing() ? cudaEventRecordExternal : cudaEventRecordDefault;
-    GP_CUDA_CHECK(cudaEventRecordWithFlags(bfs->ev_pipe0, s, ev_flags));
+    const bool stage_events = gp_stage_events_on(bfs);
+    if (stage_events) GP_CUDA_CHECK(cudaEventRecordWithFlags(bfs->ev_pipe0, s, ev_flags));
     int rc;
     {
         GpRange r("graphpope:csr_build");
@@ -466,8 +469,8 @@ int run_pipeline_eager(gp_csr *csr, gp_msbfs *bfs, const int64_t *d_ei, int64_t 
     if (xchg != nullptr) GP_TRY(gp_exchange_launch(xchg, parity, d_x, f, ldx, d_out, ldo, coff, s));
     else if (d_out != nullptr) GP_TRY(gp_msbfs_features(bfs, side_copy ? nullptr : d_x, f, ldx, d_out, ldo, coff, s));
     else GP_TRY(gp_msbfs_pack(bfs, (int32_t)coff, nullptr, nullptr, nullptr, nullptr, nullptr, s));  // coff = slot
-    GP_CUDA_CHECK(cudaEventRecordWithFlags(bfs->ev_pipe1, s, ev_flags));
-    bfs->pipe_timed = true;
+    if (stage_events) GP_CUDA_CHECK(cudaEventRecordWithFlags(bfs->ev_pipe1, s, ev_flags));
+    bfs->pipe_timed = stage_events;
     return GP_OK;
 }
 
@@ -535,6 +538,7 @@ static int geodesic_run_impl(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_ed
                                               parity);
             g_capturing = false;
             ent->kernels = g_capture_count;
+            ent->has_events = bfs->pipe_timed;
             const cudaError_t ce = cudaStreamEndCapture(pc.capture_stream, &graph);
             if (rc == GP_OK && ce == cudaSuccess && graph != nullptr) {
                 if (cudaGraphInstantiate(&ent->exec, graph, 0) != cudaSuccess) ent->exec = nullptr;
@@ -550,7 +554,7 @@ static int geodesic_run_impl(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_ed
         csr->built = true;
         gp_msbfs_layout(bfs, num_anchors);  // the handle may have run another anchor count since the capture
         bfs->ran = true;
-        bfs->pipe_timed = true;
+        bfs->pipe_timed = bfs->kernel_timed = ent->has_events;
         gp_count_launches(ent->kernels);  // kernels inside the graph
         GpRange r("graphpope:pipeline_graph_replay");
         GP_CUDA_CHECK(cudaGraphLaunch(ent->exec, stream));

@@ -60,6 +60,7 @@ struct GpEnv {
     int bfs_push;        // GP_BFS_PUSH (default 0): hop 1 in push direction, as a scan of the raw edge list (measured slower)
     int xchg_grid;       // GP_XCHG_GRID: cap on the exchange kernel's grid (tests: several ranks on one GPU)
     int xchg_debug;      // GP_XCHG_DEBUG
+    int stage_events;    // GP_STAGE_EVENTS (default 0): event NODES around csr / bfs / epilogue inside captured pipelines
     int pdl;             // GP_PDL (default 1): programmatic dependent launch inside the csr build
     int csr_trace;       // GP_CSR_TRACE: events after every launch of the csr build
     int nvtx;            // GP_NVTX (default 1): NVTX ranges around the stages

@@ -363,6 +363,11 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
             p.trace[(((size_t)31 * total_warps + gwarp) << 2) + (slot)] = (u64)clock64();     \
     } while (0)
     GP_TRACE_PRO(0);
+    if (gtid == 0) {  // device-clock stamps of the kernel (gp_msbfs_kernel_device_ns): entry, and after the last level
+        u64 t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.counters[2] = t;
+    }
     for (int i = tid; i < GP_BFS_MAX_LANE_WORDS * 2; i += NT) s_live32[i] = 0;
     if (tid <= GP_NUM_CLASSES) {
         s_ent_base[tid] = p.meta[GP_META_ENT_BASE + tid];
@@ -651,6 +656,9 @@ __global__ void __launch_bounds__(NT, MINB) msbfs_kernel(BfsParams p)
     for (int m = 16; m; m >>= 1) gathers += shfl_xor_u64(gathers, m);
     if (lane == 0 && gathers) atomicAdd(p.counters, gathers);
     if (gtid == 0) {
+        u64 t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.counters[3] = t;
         p.status[GP_BFS_ST_MAX_LEVEL] = max_level;
         const int pushed = (PUSH && use_map) ? 1 : 0;
         p.status[GP_BFS_ST_LEVELS] = level;
@@ -707,10 +715,11 @@ int launch_bfs_variant(gp_msbfs *h, const BfsParams &p, cudaStream_t stream, int
     gp_count_launch();
     // inside a graph capture the timing events become event-record nodes (re-recorded on every replay)
     const unsigned ev_flags = gp_is_capturing() ? cudaEventRecordExternal : cudaEventRecordDefault;
-    GP_CUDA_CHECK(cudaEventRecordWithFlags(h->ev_start, stream, ev_flags));
+    h->kernel_timed = gp_stage_events_on(h);
+    if (h->kernel_timed) GP_CUDA_CHECK(cudaEventRecordWithFlags(h->ev_start, stream, ev_flags));
     GP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)msbfs_kernel<WB, NT, MINB, MAPG, PUSH>, dim3(h->grid_blocks),
                                               dim3(NT), args, bfs_cache_bytes<WB, NT, MINB>() + h->map_smem_bytes, stream));
-    GP_CUDA_CHECK(cudaEventRecordWithFlags(h->ev_stop, stream, ev_flags));
+    if (h->kernel_timed) GP_CUDA_CHECK(cudaEventRecordWithFlags(h->ev_stop, stream, ev_flags));
     return GP_OK;
 }
 
@@ -922,6 +931,36 @@ extern "C" int gp_msbfs_run(gp_msbfs_t *h, const int64_t *d_anchors, int64_t num
     return GP_OK;
 }
 
+bool gp_stage_events_on(const gp_msbfs *h)
+{
+    if (!gp_is_capturing()) return true;
+    return (h->stage_events < 0 ? gp_env().stage_events : h->stage_events) != 0;
+}
+
+extern "C" int gp_msbfs_set_stage_events(gp_msbfs_t *h, int32_t enable)
+{
+    GP_REQUIRE(h != nullptr, GP_ERR_INVALID, "gp_msbfs_set_stage_events: handle is NULL");
+    h->stage_events = enable ? 1 : 0;
+    gp_pipe_cache_free(h->pipe_cache);  // captured pipelines were recorded with the other setting
+    h->pipe_cache = nullptr;
+    return GP_OK;
+}
+
+// Device-clock duration of the last MS-BFS kernel: %globaltimer at the entry of thread 0 and after the last level, in
+// nanoseconds (no event nodes needed: this is what the timed loop of bench.py reads).  syncs the stream.
+extern "C" int gp_msbfs_kernel_device_ns(gp_msbfs_t *h, uint64_t *ns, gp_stream_t stream_)
+{
+    GP_REQUIRE(h != nullptr && ns != nullptr, GP_ERR_INVALID, "gp_msbfs_kernel_device_ns: NULL argument");
+    GP_REQUIRE(h->ran, GP_ERR_INVALID, "gp_msbfs_kernel_device_ns: gp_msbfs_run has not been called");
+    u64 st[2] = {0, 0};
+    *ns = 0;
+    if (h->num_nodes == 0 || h->num_anchors == 0) return GP_OK;
+    GP_CUDA_CHECK(cudaMemcpyAsync(st, h->counters + 2, sizeof(st), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+    GP_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream_));
+    *ns = st[1] > st[0] ? st[1] - st[0] : 0;
+    return GP_OK;
+}
+
 extern "C" int gp_msbfs_set_push(gp_msbfs_t *h, int32_t enable)
 {
     GP_REQUIRE(h != nullptr, GP_ERR_INVALID, "gp_msbfs_set_push: handle is NULL");
@@ -980,6 +1019,8 @@ extern "C" int gp_msbfs_kernel_ms(gp_msbfs_t *h, float *ms)
 {
     GP_REQUIRE(h != nullptr && ms != nullptr, GP_ERR_INVALID, "gp_msbfs_kernel_ms: NULL argument");
     GP_REQUIRE(h->ran, GP_ERR_INVALID, "gp_msbfs_kernel_ms: gp_msbfs_run has not been called");
+    GP_REQUIRE(h->kernel_timed, GP_ERR_INVALID, "gp_msbfs_kernel_ms: the last run replayed a pipeline captured without "
+               "stage events (gp_msbfs_set_stage_events); gp_msbfs_kernel_device_ns needs none");
     *ms = 0.0f;
     if (h->num_nodes == 0 || h->num_anchors == 0) return GP_OK;
     GP_CUDA_CHECK(cudaEventSynchronize(h->ev_stop));
@@ -990,7 +1031,8 @@ extern "C" int gp_msbfs_kernel_ms(gp_msbfs_t *h, float *ms)
 extern "C" int gp_pipeline_stage_ms(gp_msbfs_t *h, float *ms3)
 {
     GP_REQUIRE(h != nullptr && ms3 != nullptr, GP_ERR_INVALID, "gp_pipeline_stage_ms: NULL argument");
-    GP_REQUIRE(h->ran && h->pipe_timed, GP_ERR_INVALID, "gp_pipeline_stage_ms: gp_geodesic_run has not been called");
+    GP_REQUIRE(h->ran && h->pipe_timed && h->kernel_timed, GP_ERR_INVALID,
+               "gp_pipeline_stage_ms: no fused run with stage events on this handle (gp_msbfs_set_stage_events)");
     ms3[0] = ms3[1] = ms3[2] = 0.0f;
     if (h->num_nodes == 0 || h->num_anchors == 0) return GP_OK;
     GP_CUDA_CHECK(cudaEventSynchronize(h->ev_pipe1));

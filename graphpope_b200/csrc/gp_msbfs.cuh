@@ -73,10 +73,15 @@ struct gp_msbfs {
     int block_threads = 512;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;  // bracket the persistent kernel alone
     cudaEvent_t ev_pipe0 = nullptr, ev_pipe1 = nullptr;  // first / last node of the last gp_geodesic_run pipeline
-    bool pipe_timed = false;
+    bool pipe_timed = false;   // the last fused run recorded ev_pipe0 / ev_pipe1
+    bool kernel_timed = false; // the last run recorded ev_start / ev_stop
+    int stage_events = -1;     // event nodes inside CAPTURED pipelines: -1 = GP_STAGE_EVENTS (default off), 0 / 1 = set
 };
 
 void gp_msbfs_layout(gp_msbfs *h, int64_t num_anchors);
+// Whether this launch records the stage events: always for eager launches (an event record costs ~1 us there), inside a
+// stream capture only on request (an event-record NODE costs ~4 us of the replayed step: 246 -> 231 us without the four).
+bool gp_stage_events_on(const gp_msbfs *h);
 
 // Fused decode + concat epilogue over `num_ranks` plane sets (1 = local result).
 struct GpDecodeParams {

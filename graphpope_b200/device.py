@@ -204,6 +204,19 @@ class MsBfs:
         check(self._lib.gp_msbfs_kernel_ms(self._h, byref(ms)))
         return float(ms.value)
 
+    def set_stage_events(self, enable: bool):
+        """Record event nodes around csr build / MS-BFS / epilogue inside the captured pipeline (each node costs ~4 us of
+        the replayed step, so they are off by default); needed by :meth:`pipeline_stage_ms` / :meth:`kernel_ms` after
+        a replayed run."""
+        check(self._lib.gp_msbfs_set_stage_events(self._h, int(bool(enable))))
+
+    def kernel_device_ms(self) -> float:
+        """Duration of the last MS-BFS kernel by the device clock (%globaltimer stamps written by the kernel itself:
+        entry of thread 0 to the end of the last level); needs no event nodes.  Syncs."""
+        ns = ctypes.c_uint64()
+        check(self._lib.gp_msbfs_kernel_device_ns(self._h, byref(ns), _stream()))
+        return ns.value / 1e6
+
     def pipeline_stage_ms(self):
         """(csr build, MS-BFS kernel, epilogue) device milliseconds of the last fused run on this handle,
         from event nodes inside the replayed CUDA graph."""

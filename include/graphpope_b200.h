@@ -151,10 +151,15 @@ int gp_geodesic_run(gp_csr_t *csr, gp_msbfs_t *bfs, const int64_t *d_edge_index,
                     const int64_t *d_anchors, int64_t num_anchors, const float *d_x, int64_t num_features,
                     int64_t ld_x, float *d_out, int64_t ld_out, int64_t col_offset, gp_stream_t stream);
 
-/* syncs on the pipeline's own events.  Device time of the three stages of the last gp_geodesic_run /
- * gp_geodesic_run_packed on this handle, in milliseconds: ms3[0] = csr build (+ the MS-BFS state memsets),
- * ms3[1] = the persistent MS-BFS kernel, ms3[2] = epilogue (decode + concat, or pack).  The events are nodes of
- * the replayed CUDA graph, so these are the times inside the timed step, not of stages launched on their own. */
+/* Stage clocks.  Eager launches always record CUDA events around the csr build, the MS-BFS kernel and the epilogue.
+ * Inside the captured pipeline of gp_geodesic_run an event-record NODE costs ~4 us of the replayed step (246 -> 231 us
+ * for the four at Flickr size), so they are recorded only on request: gp_msbfs_set_stage_events(bfs, 1) (the handle's
+ * captured pipelines are dropped and re-captured).  gp_pipeline_stage_ms (syncs on its own events): ms3[0] = csr build
+ * (+ the MS-BFS state memset), ms3[1] = the persistent MS-BFS kernel, ms3[2] = epilogue (decode + concat, pack, or
+ * the exchange kernel) of the last fused run.  gp_msbfs_kernel_device_ns needs no events: the kernel stamps
+ * %globaltimer at its entry and after its last level.                                                        */
+int gp_msbfs_set_stage_events(gp_msbfs_t *bfs, int32_t enable);
+int gp_msbfs_kernel_device_ns(gp_msbfs_t *bfs, uint64_t *ns, gp_stream_t stream);
 int gp_pipeline_stage_ms(gp_msbfs_t *bfs, float *ms3);
 
 /* async.  The x half of concat_into_features (utils.py:133-134) alone: d_out[:, 0:F] = d_x as ONE strided

@@ -10,7 +10,7 @@ ei = synth.make_graph(sh); anchors = synth.stochastic_anchors(n, k, 42)
 ei_d = torch.as_tensor(ei).cuda(); a_d = torch.as_tensor(anchors).cuda()
 x = torch.randn(n, f, device="cuda"); out = torch.empty(n, f + k, device="cuda")
 flush = torch.empty(64 * 1024 * 1024, device="cuda")
-eng = dev.GeodesicEngine(n, ei.shape[1], k)
+eng = dev.GeodesicEngine(n, ei.shape[1], k); eng.bfs.set_stage_events(True)
 names = ["memsets", "count", "scan1", "scatter", "rowsort", "scan9", "desc"]
 rows = []
 for i in range(14):

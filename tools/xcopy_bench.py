@@ -24,7 +24,7 @@ med, mn = timed(lambda: out[:, :f].copy_(x))
 print(f"torch strided copy_ {med*1e3:.1f} us = {8*n*f/med/1e6:.0f} GB/s", flush=True)
 ei = synth.make_graph(sh); anchors = synth.stochastic_anchors(n, k, 42)
 ei_d = torch.as_tensor(ei).cuda(); a_d = torch.as_tensor(anchors).cuda()
-eng = dev.GeodesicEngine(n, ei.shape[1], k)
+eng = dev.GeodesicEngine(n, ei.shape[1], k); eng.bfs.set_stage_events(True)
 for _ in range(4): eng.run(ei_d, a_d, x, out)
 med, mn = timed(lambda: eng.run(ei_d, a_d, x, out))
 print(f"GP_XCOPY_OVERLAP={os.environ.get('GP_XCOPY_OVERLAP','2')}: step {med*1e3:.1f} us median ({mn*1e3:.1f} min), msbfs kernel {eng.bfs.kernel_ms()*1e3:.1f} us", flush=True)
