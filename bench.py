@@ -325,8 +325,9 @@ def timed_steps(fn, barrier, dist, world, reps, flush=None):
     for i in range(reps):
         if flush is not None:
             flush(i)
-        if world > 1:
-            dist.all_reduce(align)  # device-side alignment of the ranks, not waited for by the host
+        if world > 1:  # device-side alignment of the ranks (see align_ranks in main)
+            dist.all_reduce(align)
+            torch.cuda._sleep(400_000)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize()
         total += a.elapsed_time(b)
@@ -618,15 +619,22 @@ def main():
     stage_ms, bfs_dev_ms = [], []
     launches0 = dev.launch_count()
     align_t = torch.zeros(1, device="cuda")
-    barrier()
-    for i in range(args.steps):
-        flush_l2(i)  # untimed: evict the previous step's lines from the 126 MB L2
-        # untimed alignment ON THE DEVICE: a tiny all-reduce that the host does not wait for.  Its kernel ends at
-        # the same moment on every rank and the step is already queued behind it, so the ranks enter the timed
-        # region together.  (dist.barrier() blocks the host, and the ranks' launch jitter after it — tens of
-        # microseconds — then shows up inside the step as waiting for the last rank's flag.)
+
+    def align_ranks():
+        """Untimed alignment of the ranks on the device: a tiny all-reduce the host does not wait for ends at the same
+        moment on every GPU, and a ~0.2 ms device-side spin after it gives every host time to queue the step behind
+        it.  (dist.barrier() blocks the host, whose launch jitter afterwards — tens of microseconds — shows up inside
+        the step as waiting for the last rank's flag; so does a host that queues its graph launch later than the
+        all-reduce takes.)"""
         if world > 1:
             dist.all_reduce(align_t)
+            torch.cuda._sleep(400_000)
+
+    barrier()
+    for i in range(args.steps):
+        # untimed: flush the L2, then align the ranks ON THE DEVICE (align_ranks above)
+        flush_l2(i)  # untimed: evict the previous step's lines from the 126 MB L2
+        align_ranks()
         starts[i].record()
         step()
         stops[i].record()
@@ -667,8 +675,7 @@ def main():
     ev_pass_ms = []
     for i in range(args.steps):
         flush_l2(i)
-        if world > 1:
-            dist.all_reduce(align_t)
+        align_ranks()
         a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a_ev.record(); step(); b_ev.record()
         stage_ms.append(engine.bfs.pipeline_stage_ms())
