@@ -380,7 +380,11 @@ def kmeans(table: torch.Tensor, num_clusters: int, n_init: int = 10, max_iter: i
     max_iter = 300, tol = 1e-4 scaled by the mean feature variance, unseeded).
 
     Returns ``(centers float32 [K, D] on the device, inertia, iterations of the best run)``.  Parity with
-    scikit-learn is statistical (the reference does not seed it): same objective, same stopping rule.
+    scikit-learn is statistical (the reference does not seed it): same objective, same stopping rule.  One known
+    divergence: a cluster that loses all its rows keeps its previous centre here, where scikit-learn moves it onto
+    the row farthest from its own centre; after a k-means++ start this is rare and only lowers the odds of that run
+    being the best of ``n_init`` (the result is still the run with the lowest inertia).  Tables wider than 128
+    columns are not clustered on the device (``utils.attach_node2vec`` keeps scikit-learn for those).
     """
     lib = _lib.require_cuda()
     x = table.to(device="cuda", dtype=torch.float32).contiguous()
