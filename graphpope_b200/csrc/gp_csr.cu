@@ -317,6 +317,30 @@ struct PtrScanIo {
     __device__ void finish(const int (&)[1]) const {}
 };
 
+// The same for the first scan of gp_csr_build; it also queues the rows of more than 128 raw edges for the CTA-wide
+// row sort, which can then run BESIDE the sort of the short rows instead of after it.
+struct PtrScanBuildIo {
+    const int *cnt;
+    int *ptr;
+    int *cursor;
+    long long n;
+    int *biglist;
+    int *meta;
+    __device__ void load(long long i, int (&v)[1]) const
+    {
+        if (i < n) v[0] = cnt[i];
+    }
+    __device__ void store(long long i, const int (&excl)[1], const int (&v)[1]) const
+    {
+        ptr[i] = excl[0];
+        if (i < n) {
+            cursor[i] = excl[0];
+            if (v[0] > 128) biglist[atomicAdd(&meta[GP_META_NUM_BIG_ROWS], 1)] = (int)i;
+        }
+    }
+    __device__ void finish(const int (&)[1]) const {}
+};
+
 __device__ __forceinline__ int degree_class(int d)
 {
     // 0: hub rows (cut into GP_CHUNK_EDGES chunks), then G = 32, 16, 8, 4, 2, 1 slots of GP_SLOT_EDGES edges
@@ -532,7 +556,7 @@ __device__ __forceinline__ int thread_row_sort_unique16(int *colbuf, int s, int 
 // queued for rowsort_big_kernel.
 __global__ void __launch_bounds__(256)
 rowsort_small_kernel(const int *__restrict__ ptr, const int *len_in, int *__restrict__ colbuf, long long n, int *deg,
-                     int *__restrict__ biglist, int *meta, int max_word)
+                     int *__restrict__ biglist, int *meta, int max_word, int collect_big)
 {
     const int lane = lane_id();
     const long long nblk = (n + 255) / 256;
@@ -560,8 +584,8 @@ rowsort_small_kernel(const int *__restrict__ ptr, const int *len_in, int *__rest
             longer &= longer - 1;
             const int rs = __shfl_sync(FULL_MASK, s, src), rlen = __shfl_sync(FULL_MASK, len, src);
             const long long rr = r - lane + src;
-            if (rlen > 128) {
-                if (lane == 0) biglist[atomicAdd(&meta[GP_META_NUM_BIG_ROWS], 1)] = (int)rr;
+            if (rlen > 128) {  // queued for rowsort_big_kernel (by the first scan of gp_csr_build when !collect_big)
+                if (collect_big && lane == 0) biglist[atomicAdd(&meta[GP_META_NUM_BIG_ROWS], 1)] = (int)rr;
                 continue;
             }
             int d;
@@ -797,9 +821,30 @@ int sort_rows(gp_csr *c, const int *ptr, int *len, int *colbuf, int max_word, bo
     // programmatic launches: inside gp_csr_build they follow kernels of the same chain (after a memset or a
     // one-thread kernel the attribute simply has no effect)
     GP_LAUNCH_PDL(rowsort_small_kernel, launch_blocks(n, 256), 256, 0, stream, ptr, (const int *)len, colbuf, (long long)n, len,
-                  c->biglist, c->meta, max_word);
+                  c->biglist, c->meta, max_word, 1);
     GP_LAUNCH_PDL(rowsort_big_kernel, gp_sm_count() * 4, BIG_THREADS, (size_t)c->big_smem_bytes, stream, ptr,
                   (const int *)len, colbuf, len, (const int *)c->biglist, c->meta, max_word, c->bitmap_words);
+    return GP_OK;
+}
+
+// The same with the long rows already queued (PtrScanBuildIo): the two kernels touch disjoint rows, so the CTA-wide
+// sort of the long rows runs on a side stream (a parallel branch of a captured graph) beside the sort of the short ones.
+int sort_rows_forked(gp_csr *c, const int *ptr, int *len, int *colbuf, int max_word, cudaStream_t stream)
+{
+    const int64_t n = c->num_nodes;
+    if (c->side == nullptr) {
+        GP_CUDA_CHECK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+        GP_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        GP_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
+    GP_CUDA_CHECK(cudaEventRecord(c->ev_fork, stream));
+    GP_CUDA_CHECK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    GP_LAUNCH(rowsort_big_kernel, gp_sm_count() * 4, BIG_THREADS, (size_t)c->big_smem_bytes, c->side, ptr, (const int *)len,
+              colbuf, len, (const int *)c->biglist, c->meta, max_word, c->bitmap_words);
+    GP_CUDA_CHECK(cudaEventRecord(c->ev_join, c->side));
+    GP_LAUNCH_PDL(rowsort_small_kernel, launch_blocks(n, 256), 256, 0, stream, ptr, (const int *)len, colbuf, (long long)n, len,
+                  c->biglist, c->meta, max_word, 0);
+    GP_CUDA_CHECK(cudaStreamWaitEvent(stream, c->ev_join, 0));
     return GP_OK;
 }
 
@@ -886,6 +931,9 @@ extern "C" int gp_csr_free(gp_csr_t *c)
     for (int i = 0; i < 16; ++i) cudaFree(c->scratch[i]);
     for (int i = 0; i < 12; ++i)
         if (c->trace_ev[i]) cudaEventDestroy(c->trace_ev[i]);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->side) cudaStreamDestroy(c->side);
     cudaFree(c->row_start);
     cudaFree(c->cursor);
     cudaFree(c->col);
@@ -931,18 +979,18 @@ extern "C" int gp_csr_build(gp_csr_t *c, const int64_t *d_edge_index, int64_t nu
             GP_LAUNCH(count_edges_kernel, launch_blocks(gp_ceil_div(num_edges, 4), 256), 256, 0, stream, ei, num_edges, n, sym,
                       vec, c->deg, c->meta);
         mark();
-        PtrScanIo pio{c->deg, c->row_start, c->cursor, n};
+        PtrScanBuildIo pio{c->deg, c->row_start, c->cursor, n, c->biglist, c->meta};
         gp_count_launch();
         // (16 items per thread = 22 tiles = one look-back window at Flickr size measured SLOWER: 10.3 us against 8.8 us;
         // the per-thread serial work outweighs the saved look-back rounds)
-        GP_CUDA_CHECK(gp_launch_pdl(chained_scan_kernel<1, PtrScanIo, SCAN_IPT>, dim3((unsigned)scan_tiles(n + 1)),
+        GP_CUDA_CHECK(gp_launch_pdl(chained_scan_kernel<1, PtrScanBuildIo, SCAN_IPT>, dim3((unsigned)scan_tiles(n + 1)),
                                     dim3(SCAN_THREADS), 0, stream, pio, (long long)(n + 1), c->scan_status, ticket_a));
         mark();
         if (num_edges > 0)
             GP_LAUNCH_PDL(scatter_edges_kernel, launch_blocks(gp_ceil_div(num_edges, 4), 256), 256, 0, stream, ei,
                           (long long)num_edges, (long long)n, sym, vec, c->cursor, c->col);
         mark();
-        GP_TRY(sort_rows(c, c->row_start, c->deg, c->col, GP_META_MAX_DEGREE, false, stream));  // deg := distinct degree
+        GP_TRY(sort_rows_forked(c, c->row_start, c->deg, c->col, GP_META_MAX_DEGREE, stream));  // deg := distinct degree
         mark();
         RowScanIo rio{c->deg, c->cursor, c->hubidx, c->meta, n};  // cursor := rank of the row inside its class
         gp_count_launch();

@@ -62,6 +62,8 @@ struct gp_csr {
     // seconds (betweenness) keep their workspace here instead of paying cudaMalloc / cudaFree on every call
     void *scratch[16] = {};
     size_t scratch_bytes[16] = {};
+    cudaStream_t side = nullptr;    // the long rows are sorted beside the short ones (sort_rows_forked)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t trace_ev[12] = {};  // GP_CSR_TRACE: events after every launch of the last build (diagnostics)
     int trace_n = 0;
     int bitmap_words = 0;       // ceil(N / 32) if the long-row sort may use a node bitmap in shared memory, else 0
