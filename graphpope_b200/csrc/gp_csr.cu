@@ -325,6 +325,7 @@ struct PtrScanBuildIo {
     int *cursor;
     long long n;
     int *biglist;
+    int *medlist;
     int *meta;
     __device__ void load(long long i, int (&v)[1]) const
     {
@@ -336,6 +337,7 @@ struct PtrScanBuildIo {
         if (i < n) {
             cursor[i] = excl[0];
             if (v[0] > 128) biglist[atomicAdd(&meta[GP_META_NUM_BIG_ROWS], 1)] = (int)i;
+            else if (v[0] > 16) medlist[atomicAdd(&meta[GP_META_NUM_MED_ROWS], 1)] = (int)i;
         }
     }
     __device__ void finish(const int (&)[1]) const {}
@@ -578,7 +580,7 @@ rowsort_small_kernel(const int *__restrict__ ptr, const int *len_in, int *__rest
             if (d != len) deg[r] = d;
             mx = max(mx, d);
         }
-        u32 longer = __ballot_sync(FULL_MASK, len > 16);
+        u32 longer = collect_big ? __ballot_sync(FULL_MASK, len > 16) : 0u;  // build mode: queued rows, other kernel
         while (longer) {
             const int src = __ffs(longer) - 1;
             longer &= longer - 1;
@@ -637,7 +639,8 @@ __device__ __forceinline__ void network_step(int *a, int len, int pairs, int sh,
 // scan.  Dynamic shared memory: max(BIG_SMEM_ELEMS ints, bitmap_words words).
 __global__ void __launch_bounds__(BIG_THREADS)
 rowsort_big_kernel(const int *__restrict__ ptr, const int *len_in, int *colbuf, int *deg,
-                   const int *__restrict__ biglist, int *meta, int max_word, int bitmap_words)
+                   const int *__restrict__ biglist, int *meta, int max_word, int bitmap_words,
+                   const int *__restrict__ medlist)
 {
     extern __shared__ __align__(16) int s_buf[];
     __shared__ int s_warp[BIG_THREADS / 32];
@@ -744,6 +747,28 @@ rowsort_big_kernel(const int *__restrict__ ptr, const int *len_in, int *colbuf, 
             if (s_carry > *(volatile int *)&meta[max_word]) atomicMax(&meta[max_word], s_carry);
         }
     }
+    // ---- rows of 17..128 raw edges (gp_csr_build only): one warp each, in registers.  The CTAs that had no long row
+    // take them (all CTAs when every CTA had one), so they run beside the long rows and beside rowsort_small_kernel.
+    if (medlist != nullptr) {
+        const int nmed = meta[GP_META_NUM_MED_ROWS];
+        const int busy = nbig < (int)gridDim.x ? nbig : 0;  // CTAs [0, busy) are still sorting a long row
+        const int wpc = BIG_THREADS / 32;
+        const int nw = ((int)gridDim.x - busy) * wpc;
+        int mx = 0;
+        if ((int)blockIdx.x >= busy) {
+            for (int q = ((int)blockIdx.x - busy) * wpc + warp; q < nmed; q += nw) {
+                const int r = medlist[q];
+                const int rs = ptr[r], rlen = len_in[r];
+                int d;
+                if (rlen <= 32) d = warp_row_sort_unique<1>(colbuf, rs, rlen, lane);
+                else if (rlen <= 64) d = warp_row_sort_unique<2>(colbuf, rs, rlen, lane);
+                else d = warp_row_sort_unique<4>(colbuf, rs, rlen, lane);
+                if (lane == 0 && d != rlen) deg[r] = d;
+                mx = max(mx, d);
+            }
+        }
+        if (lane == 0 && mx > 0 && mx > *(volatile int *)&meta[max_word]) atomicMax(&meta[max_word], mx);
+    }
 }
 
 // ---------------------------------------------------------------- work-list descriptors
@@ -823,7 +848,8 @@ int sort_rows(gp_csr *c, const int *ptr, int *len, int *colbuf, int max_word, bo
     GP_LAUNCH_PDL(rowsort_small_kernel, launch_blocks(n, 256), 256, 0, stream, ptr, (const int *)len, colbuf, (long long)n, len,
                   c->biglist, c->meta, max_word, 1);
     GP_LAUNCH_PDL(rowsort_big_kernel, gp_sm_count() * 4, BIG_THREADS, (size_t)c->big_smem_bytes, stream, ptr,
-                  (const int *)len, colbuf, len, (const int *)c->biglist, c->meta, max_word, c->bitmap_words);
+                  (const int *)len, colbuf, len, (const int *)c->biglist, c->meta, max_word, c->bitmap_words,
+                  (const int *)nullptr);
     return GP_OK;
 }
 
@@ -840,7 +866,7 @@ int sort_rows_forked(gp_csr *c, const int *ptr, int *len, int *colbuf, int max_w
     GP_CUDA_CHECK(cudaEventRecord(c->ev_fork, stream));
     GP_CUDA_CHECK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
     GP_LAUNCH(rowsort_big_kernel, gp_sm_count() * 4, BIG_THREADS, (size_t)c->big_smem_bytes, c->side, ptr, (const int *)len,
-              colbuf, len, (const int *)c->biglist, c->meta, max_word, c->bitmap_words);
+              colbuf, len, (const int *)c->biglist, c->meta, max_word, c->bitmap_words, (const int *)c->medlist);
     GP_CUDA_CHECK(cudaEventRecord(c->ev_join, c->side));
     GP_LAUNCH_PDL(rowsort_small_kernel, launch_blocks(n, 256), 256, 0, stream, ptr, (const int *)len, colbuf, (long long)n, len,
                   c->biglist, c->meta, max_word, 0);
@@ -893,6 +919,8 @@ extern "C" int gp_csr_create(int64_t num_nodes, int64_t edge_capacity, uint32_t 
     alloc((void **)&c->col, kc * sizeof(int));
     alloc((void **)&c->hubidx, (nn + 1) * sizeof(int));
     alloc((void **)&c->biglist, (size_t)c->big_capacity * sizeof(int));
+    c->med_capacity = kcap / 17 + 1;
+    alloc((void **)&c->medlist, (size_t)c->med_capacity * sizeof(int));
     alloc((void **)&c->desc, (size_t)c->desc_capacity * sizeof(int4));
     // meta words, then the look-back words of the two scans of a build (separate regions, so one
     // memset per build clears everything), then the ticket counters
@@ -942,6 +970,7 @@ extern "C" int gp_csr_free(gp_csr_t *c)
     cudaFree(c->deg_in);
     cudaFree(c->hubidx);
     cudaFree(c->biglist);
+    cudaFree(c->medlist);
     cudaFree(c->desc);
     cudaFree(c->meta);
     delete c;
@@ -979,7 +1008,7 @@ extern "C" int gp_csr_build(gp_csr_t *c, const int64_t *d_edge_index, int64_t nu
             GP_LAUNCH(count_edges_kernel, launch_blocks(gp_ceil_div(num_edges, 4), 256), 256, 0, stream, ei, num_edges, n, sym,
                       vec, c->deg, c->meta);
         mark();
-        PtrScanBuildIo pio{c->deg, c->row_start, c->cursor, n, c->biglist, c->meta};
+        PtrScanBuildIo pio{c->deg, c->row_start, c->cursor, n, c->biglist, c->medlist, c->meta};
         gp_count_launch();
         // (16 items per thread = 22 tiles = one look-back window at Flickr size measured SLOWER: 10.3 us against 8.8 us;
         // the per-thread serial work outweighs the saved look-back rounds)

@@ -24,6 +24,7 @@ enum : int {
     GP_META_IS_SYMMETRIC = 5,
     GP_META_IN_BUILT = 6,
     GP_META_NUM_HUB_ROWS = 7,   // rows with degree > GP_CHUNK_EDGES
+    GP_META_NUM_MED_ROWS = 8,   // rows of 17..128 raw edges queued for the warp-per-row sort (gp_csr_build)
     GP_META_ENT_BASE = 16,      // [8]: first descriptor of each class, then the total
     GP_META_SLOT_BASE = 24,     // [8]: first slot of each class, then the total
     GP_META_WORDS = 32
@@ -53,6 +54,8 @@ struct gp_csr {
     int *deg_in = nullptr;      // [N + 1]
     int *hubidx = nullptr;      // [N + 1] index among the hub rows (hub rows only)
     int *biglist = nullptr;     // [big_capacity] rows queued for the CTA-wide row sort
+    int *medlist = nullptr;     // [med_capacity] rows of 17..128 raw edges, sorted by one warp each beside the short rows
+    int64_t med_capacity = 0;
     int4 *desc = nullptr;       // [desc_capacity] {row, first edge, count | chunks << 8, hub index or -1}
     int *meta = nullptr;        // [GP_META_WORDS], followed in the same allocation by scan_status
     int *scan_status = nullptr; // look-back words of the chained scans + ticket counters in the last 8 words
