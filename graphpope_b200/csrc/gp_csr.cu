@@ -25,6 +25,7 @@
 // the finished CSR, built on demand.
 #include "gp_internal.h"
 
+#include <algorithm>
 #include <new>
 
 namespace {
@@ -349,11 +350,16 @@ __device__ __forceinline__ int degree_class(int d)
     return d > GP_CHUNK_EDGES ? 0 : d > 64 ? 1 : d > 32 ? 2 : d > 16 ? 3 : d > 8 ? 4 : d > 4 ? 5 : 6;
 }
 
-// Row scan: channel 0 edges, 1..7 work-list entries of class 0..6, 8 hub rows.
+// Row scan: channel 0 edges, 1..7 work-list entries of class 0..6, 8 hub rows.  The scan writes the work-list
+// descriptors itself: the descriptors of a class live in a region whose START is fixed when the handle is created
+// (desc_off), so a row's position is known from its exclusive prefix alone and no second pass over the rows is needed.
+//   desc = {row, first edge, count | chunks << 8 | first << 30, hub index or -1}, one per row, hub rows one per
+//   GP_CHUNK_EDGES-edge chunk.
 struct RowScanIo {
     const int *deg;
-    int *rank;     // [n] position of the row among the entries of its class
-    int *hubidx;   // [n] index among the hub rows (hub rows only)
+    const int *row_start;
+    int4 *desc;
+    int off[GP_NUM_CLASSES];
     int *meta;
     long long n;
     __device__ void load(long long i, int (&v)[ROW_CH]) const
@@ -368,13 +374,25 @@ struct RowScanIo {
     }
     __device__ void store(long long i, const int (&excl)[ROW_CH], const int (&v)[ROW_CH]) const
     {
-        const int c = degree_class(v[0]);
-        int r = 0;
+        const int d = v[0];
+        const int c = degree_class(d);
+        int r = 0, base = 0;
 #pragma unroll
         for (int k = 0; k < GP_NUM_CLASSES; ++k)
-            if (k == c) r = excl[1 + k];
-        rank[i] = r;
-        if (c == 0) hubidx[i] = excl[8];
+            if (k == c) {
+                r = excl[1 + k];
+                base = off[k];
+            }
+        const int s = row_start[i];
+        if (c != 0) {
+            desc[base + r] = make_int4((int)i, s, d, -1);
+        } else {
+            const int nch = (d + GP_CHUNK_EDGES - 1) / GP_CHUNK_EDGES;
+            for (int k = 0; k < nch; ++k) {
+                const int cnt = min(GP_CHUNK_EDGES, d - k * GP_CHUNK_EDGES);
+                desc[base + r + k] = make_int4((int)i, s + k * GP_CHUNK_EDGES, cnt | (nch << 8) | (k == 0 ? 1 << 30 : 0), excl[8]);
+            }
+        }
     }
     __device__ void finish(const int (&total)[ROW_CH]) const
     {
@@ -771,35 +789,6 @@ rowsort_big_kernel(const int *__restrict__ ptr, const int *len_in, int *colbuf, 
     }
 }
 
-// ---------------------------------------------------------------- work-list descriptors
-// desc = {row, first edge, count | chunks << 8 | first << 30, hub index or -1}, one per row, hub rows
-// one per GP_CHUNK_EDGES-edge chunk.
-__global__ void desc_kernel(const int *__restrict__ row_start, const int *__restrict__ deg,
-                            const int *__restrict__ rank, const int *__restrict__ hubidx,
-                            const int *__restrict__ meta, long long n, int4 *__restrict__ desc)
-{
-    __shared__ int s_ent[GP_NUM_CLASSES];
-    gp_pdl_enter();
-    if (threadIdx.x < GP_NUM_CLASSES) s_ent[threadIdx.x] = meta[GP_META_ENT_BASE + threadIdx.x];
-    __syncthreads();
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
-        const int s = row_start[r], d = deg[r];
-        const int c = degree_class(d);
-        const int ent = s_ent[c] + rank[r];
-        if (c != 0) {
-            desc[ent] = make_int4((int)r, s, d, -1);
-        } else {
-            const int nch = (d + GP_CHUNK_EDGES - 1) / GP_CHUNK_EDGES;
-            const int h = hubidx[r];
-            for (int k = 0; k < nch; ++k) {
-                const int cnt = min(GP_CHUNK_EDGES, d - k * GP_CHUNK_EDGES);
-                desc[ent + k] = make_int4((int)r, s + k * GP_CHUNK_EDGES, cnt | (nch << 8) | (k == 0 ? 1 << 30 : 0), h);
-            }
-        }
-    }
-}
-
 // is_symmetric: every row of the out-edge CSR equals the same row of the in-edge CSR (warp per row).
 __global__ void compare_csr_kernel(const int *__restrict__ row_start, const int *__restrict__ deg,
                                    const int *__restrict__ col, const int *__restrict__ rowptr_in,
@@ -892,7 +881,21 @@ extern "C" int gp_csr_create(int64_t num_nodes, int64_t edge_capacity, uint32_t 
     c->key_capacity = kcap;
     c->flags = flags;
     c->hub_capacity = kcap / (GP_CHUNK_EDGES + 1) + 1;
-    c->desc_capacity = num_nodes + kcap / GP_CHUNK_EDGES + 2;
+    {
+        // region of class c: hub chunks (<= E/128 + one partial chunk per hub row), then rows of more than 64, 32, 16, 8,
+        // 4 edges (a class cannot hold more rows than E / its smallest degree, nor more than N), then everything else
+        const int64_t min_deg[GP_NUM_CLASSES] = {0, 65, 33, 17, 9, 5, 0};
+        int64_t off = 0;
+        for (int k = 0; k < GP_NUM_CLASSES; ++k) {
+            int64_t cap = k == 0 ? kcap / GP_CHUNK_EDGES + c->hub_capacity + 1
+                                 : (min_deg[k] ? std::min<int64_t>(num_nodes, kcap / min_deg[k]) : num_nodes) + 1;
+            c->desc_off[k] = (int)off;
+            off += cap;
+        }
+        GP_REQUIRE(off < (1ll << 31), GP_ERR_UNSUPPORTED, "gp_csr_create: work list too large for this build");
+        c->desc_off[GP_NUM_CLASSES] = (int)off;
+        c->desc_capacity = off;
+    }
     c->big_capacity = kcap / 129 + 1;
     // node bitmap for the long-row sort, if it fits next to a few resident CTAs
     const int64_t words = (num_nodes + 31) / 32;
@@ -917,7 +920,6 @@ extern "C" int gp_csr_create(int64_t num_nodes, int64_t edge_capacity, uint32_t 
     alloc((void **)&c->row_start, (nn + 1) * sizeof(int));
     alloc((void **)&c->cursor, (nn + 1) * sizeof(int));
     alloc((void **)&c->col, kc * sizeof(int));
-    alloc((void **)&c->hubidx, (nn + 1) * sizeof(int));
     alloc((void **)&c->biglist, (size_t)c->big_capacity * sizeof(int));
     c->med_capacity = kcap / 17 + 1;
     alloc((void **)&c->medlist, (size_t)c->med_capacity * sizeof(int));
@@ -968,7 +970,6 @@ extern "C" int gp_csr_free(gp_csr_t *c)
     cudaFree(c->rowptr_in);
     cudaFree(c->col_in);
     cudaFree(c->deg_in);
-    cudaFree(c->hubidx);
     cudaFree(c->biglist);
     cudaFree(c->medlist);
     cudaFree(c->desc);
@@ -1021,14 +1022,18 @@ extern "C" int gp_csr_build(gp_csr_t *c, const int64_t *d_edge_index, int64_t nu
         mark();
         GP_TRY(sort_rows_forked(c, c->row_start, c->deg, c->col, GP_META_MAX_DEGREE, stream));  // deg := distinct degree
         mark();
-        RowScanIo rio{c->deg, c->cursor, c->hubidx, c->meta, n};  // cursor := rank of the row inside its class
+        RowScanIo rio;  // writes the work-list descriptors as it goes
+        rio.deg = c->deg;
+        rio.row_start = c->row_start;
+        rio.desc = c->desc;
+        for (int k = 0; k < GP_NUM_CLASSES; ++k) rio.off[k] = c->desc_off[k];
+        rio.meta = c->meta;
+        rio.n = n;
         gp_count_launch();
         GP_CUDA_CHECK(gp_launch_pdl(chained_scan_kernel<ROW_CH, RowScanIo, SCAN_IPT>, dim3((unsigned)scan_tiles(n)),
                                     dim3(SCAN_THREADS), 0, stream, rio, (long long)n, c->scan_status + c->scan_b_offset,
                                     ticket_b));
         mark();
-        GP_LAUNCH_PDL(desc_kernel, launch_blocks(n, 256), 256, 0, stream, (const int *)c->row_start, (const int *)c->deg,
-                      (const int *)c->cursor, (const int *)c->hubidx, (const int *)c->meta, (long long)n, c->desc);
         mark();
     }
     GP_CUDA_CHECK(cudaGetLastError());
@@ -1064,7 +1069,7 @@ int gp_csr_ensure_in(gp_csr *c, cudaStream_t stream)
     GP_LAUNCH(set_meta_kernel, 1, 1, 0, stream, c->meta, GP_META_IS_SYMMETRIC, 1);
     if (n > 0) {
         // cursor / scan_status are free again once the out-edge CSR is finished... except that cursor
-        // holds the class ranks only until desc_kernel has run, which it has
+        // is only the scatter cursor of the build, which has finished
         int *ticket = c->scan_status + c->scan_status_words - 8;
         GP_CUDA_CHECK(cudaMemsetAsync(c->deg_in, 0, (size_t)(n + 1) * sizeof(int), stream));
         GP_CUDA_CHECK(cudaMemsetAsync(c->scan_status, 0, c->scan_status_words * sizeof(int), stream));

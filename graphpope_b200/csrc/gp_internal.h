@@ -38,7 +38,9 @@ struct gp_csr {
     int64_t num_input_edges = 0;
     uint32_t flags = 0;
     int64_t hub_capacity = 0;   // upper bound on rows with degree > GP_CHUNK_EDGES
-    int64_t desc_capacity = 0;  // upper bound on work-list descriptors
+    int64_t desc_capacity = 0;  // work-list descriptors: the sum of the class regions below
+    int desc_off[8] = {};       // first descriptor of each degree class's region (fixed at create: a class cannot
+                                // hold more rows than edge_capacity / its smallest degree), then the total
     int64_t big_capacity = 0;   // upper bound on rows with more than 128 raw edges
     bool built = false;
     bool in_built = false;      // host view of GP_META_IN_BUILT (in-edge CSR materialised)
@@ -47,12 +49,11 @@ struct gp_csr {
     int *deg = nullptr;         // [N + 1] raw edge count per row, then the distinct out-degree
     int *row_start = nullptr;   // [N + 1] first column of each row (exclusive prefix of the RAW counts)
     int *col = nullptr;         // [key_capacity]
-    int *cursor = nullptr;      // [N + 1] scatter cursors, then the row's rank inside its degree class
+    int *cursor = nullptr;      // [N + 1] scatter cursors
     // in-edge CSR (compact), allocated and built on first use
     int *rowptr_in = nullptr;   // [N + 1]
     int *col_in = nullptr;      // [key_capacity]
     int *deg_in = nullptr;      // [N + 1]
-    int *hubidx = nullptr;      // [N + 1] index among the hub rows (hub rows only)
     int *biglist = nullptr;     // [big_capacity] rows queued for the CTA-wide row sort
     int *medlist = nullptr;     // [med_capacity] rows of 17..128 raw edges, sorted by one warp each beside the short rows
     int64_t med_capacity = 0;

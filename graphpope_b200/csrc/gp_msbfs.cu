@@ -51,7 +51,8 @@ struct BfsParams {
     int hub_capacity;
     const int *__restrict__ col;
     const int4 *__restrict__ desc;
-    const int *__restrict__ meta;   // csr meta words (class bases)
+    const int *__restrict__ meta;   // csr meta words (class counts as running totals, slot bases)
+    int desc_off[GP_NUM_CLASSES];   // first descriptor of each class's region in `desc` (fixed per csr handle)
     const long long *__restrict__ anchors;
     u64 *result;                    // R[0..31], see the layout note above
     u64 *seeds;                     // level-0 frontier (the anchors)
@@ -230,10 +231,10 @@ __device__ __forceinline__ void load_tile(const BfsParams &p, const int *s_ent_b
     while (t0 >= s_slot_base[cls + 1]) ++cls;  // regions are GP_SLOT_ALIGN aligned: warp-uniform
     const int gsh = cls <= 1 ? 5 : 6 - cls;    // log2 of slots per row: 32,32,16,8,4,2,1
     const int rel = t0 - s_slot_base[cls] + lane;
-    const int ent = s_ent_base[cls] + (rel >> gsh);
+    const int idx_in_class = rel >> gsh;
     const int sub = rel & ((1 << gsh) - 1);
-    const bool active = ent < s_ent_base[cls + 1];
-    const int4 d = active ? __ldg(p.desc + ent) : make_int4(-1, 0, 0, -1);
+    const bool active = idx_in_class < s_ent_base[cls + 1] - s_ent_base[cls];  // entries of the class
+    const int4 d = active ? __ldg(p.desc + p.desc_off[cls] + idx_in_class) : make_int4(-1, 0, 0, -1);
     lead = make_int4(active ? d.x : -1, d.z, d.w, gsh);
     const int cnt = d.z & 0xFF;
     int c[GP_SLOT_EDGES];
@@ -902,6 +903,7 @@ extern "C" int gp_msbfs_run(gp_msbfs_t *h, const int64_t *d_anchors, int64_t num
     p.num_anchors = (int)num_anchors;
     p.hub_capacity = (int)h->hub_capacity;
     p.desc = h->csr->desc;
+    for (int k = 0; k < GP_NUM_CLASSES; ++k) p.desc_off[k] = h->csr->desc_off[k];
     p.hub_acc = h->hub_acc;
     p.hub_cnt = h->hub_cnt;
     p.bar = h->bar;
