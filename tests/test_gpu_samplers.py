@@ -149,6 +149,20 @@ def _assert_same_ranking(got, want, k, rtol=1e-10):
                 abs(want[u] - cut) <= rtol * abs(cut), (u, v, want[u], want[v])
 
 
+def _assert_anchor_lists(method, ei, n, golden, want_scores, rtol):
+    """utils.sample_anchor_nodes against the lists the unmodified reference returned, for every K frozen in the
+    fixture; positions may differ only where the reference's own scores tie within the sampler's tolerance."""
+    from graphpope_b200 import utils
+    for k in (1, 16, 64, 256):
+        got = utils.sample_anchor_nodes(Data(ei, n), k, method)
+        want = golden[f"anchors/{k}"].tolist()
+        assert len(got) == len(want)
+        for u, v in zip(got, want):
+            if u != v:
+                assert abs(want_scores[u] - want_scores[v]) <= rtol * max(abs(want_scores[u]), abs(want_scores[v]), 1e-300), \
+                    (method, k, u, v)
+
+
 def test_betweenness_scores_and_anchor_lists(dev, golden_betweenness):
     """nx.betweenness_centrality (utils.py:32-36): Brandes with 32 sources per warp-wide batch."""
     from graphpope_b200 import utils
@@ -164,6 +178,7 @@ def test_betweenness_scores_and_anchor_lists(dev, golden_betweenness):
     for k in (1, 16, 64, 256):
         _assert_same_ranking(got, want, k)
     assert utils.sample_anchor_nodes(Data(ei, n), 16, "betweenness_centrality") == g["anchors/16"].tolist()
+    _assert_anchor_lists("betweenness_centrality", ei, n, g, want, 1e-10)
 
 
 @pytest.mark.parametrize("spl", [1, 2, 4])
@@ -218,6 +233,7 @@ def test_eigenvector_scores_and_anchor_lists(dev, golden_eigenvector):
     for k in (1, 16, 64, 256):
         _assert_same_ranking(got, g["scores"], k, rtol=1e-9)
     assert utils.sample_anchor_nodes(Data(ei, n), 16, "eigenvector_centrality") == g["anchors/16"].tolist()
+    _assert_anchor_lists("eigenvector_centrality", ei, n, g, g["scores"], 1e-9)
     # a directed cycle (period 5: every eigenvalue has modulus 1, the shift makes the Perron root dominant)
     cyc = np.array([[0, 1, 2, 3, 4], [1, 2, 3, 4, 0]])
     x, _ = dev.DeviceCsr(5, 5).build(torch.as_tensor(cyc).cuda()).eigenvector()
