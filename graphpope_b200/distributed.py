@@ -204,6 +204,7 @@ class SharedHostMatrix:
         arr = np.frombuffer(self._mm, dtype=np.float32, count=self.rows * self.cols).reshape(self.rows, self.cols)
         self.tensor = torch.from_numpy(arr)
         self._registered = False
+        self.shard = (0, 0)
         if register and torch.cuda.is_available():
             rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), self.nbytes, 0)
             if int(rc) != 0:
@@ -259,6 +260,7 @@ def sharded_embed_host_shared(engine, edge_index: torch.Tensor, anchors, x: torc
         raise ValueError(f"shared matrix is {tuple(out.shape)}, expected {(n, f + k)}")
     rank, world = shared.rank, shared.world
     lo, hi = shard_bounds(k, world, rank)
+    shared.shard = (lo, hi)  # the anchor columns this rank computed
     kr = hi - lo
     key = (n, kr, edge_index.size(1))
     if staging.get("shape") != key:

@@ -30,6 +30,8 @@ What runs where
   * ``eigenvector_centrality`` anchors: device (float64 power iteration on ``A^T + I``; strong connectivity
     checked with two single-anchor MS-BFS sweeps, as networkx >= 3.2 refuses disconnected graphs).
     ``GRAPHPOPE_BETWEENNESS=networkx`` / ``GRAPHPOPE_EIGENVECTOR=networkx`` keep the reference's own calls.
+Inside a ``torch.distributed`` job ``GRAPHPOPE_SHARED=1`` makes the ranks of a node share the geodesic work and
+return ONE node-shared host matrix instead of computing a private copy each (main.py:88-98 runs this in every rank).
 There is no CPU fallback for the device parts: without the CUDA library or a GPU these functions raise.
 """
 from __future__ import annotations
@@ -54,6 +56,25 @@ def _output_device() -> str:
     ``x[n_id]`` gathers, main.py:120,177, then run on the device and the 91 MB device->host copy plus the
     host concat disappear).  Default ``cpu`` = the reference's contract."""
     return os.environ.get("GRAPHPOPE_OUTPUT", "cpu")
+
+
+def _shared_world():
+    """``GRAPHPOPE_SHARED=1`` inside an initialised ``torch.distributed`` job with more than one rank: the ranks of
+    the node share the work AND the result.  The reference runs ``Graphpope`` in every DDP rank
+    (main.py:88-98) and each ends up with its own copy of the same matrix; here rank r runs the MS-BFS for its
+    ``K/G`` anchors only and all ranks return one page-locked ``[N, F+K]`` matrix in POSIX shared memory
+    (``distributed.SharedHostMatrix``).  Needs identical anchors on every rank — true for every sampler under the
+    reference's ``seed_everything`` (main.py:260)."""
+    if os.environ.get("GRAPHPOPE_SHARED", "0") != "1":
+        return None
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return None
+    return dist
+
+
+_shared_keepalive: list = []  # node-shared matrices handed out (their CUDA registration lives as long as the process)
 
 
 def _cache_dir():
@@ -327,8 +348,22 @@ def attach_distance_embedding(data, dataset, num_anchor_nodes, sampling_method, 
         # torch.cat type-promotes; keep that behaviour by taking the generic route (also the cached one:
         # the cache holds the [N, K] block, not the concatenation)
         return concat_into_features(get_geodesic_distance_vector(data, num_workers), data)
+    dist = _shared_world()
     if _output_device() == "cuda":
         out = _device_features(data, x)
+    elif dist is not None:
+        from . import distributed as _gpd
+
+        _lib.require_cuda()
+        n, k = int(data.num_nodes), len(data.anchor_nodes)
+        ei = _edge_index_of(data).to("cpu").contiguous()
+        xc = x.to("cpu").contiguous()
+        eng = _dev.GeodesicEngine(n, ei.size(1), max(1, -(-k // dist.get_world_size())), SYMMETRIZE)
+        shared = _gpd.SharedHostMatrix(n, xc.size(1) + k)
+        out = _gpd.sharded_embed_host_shared(eng, ei, data.anchor_nodes, xc, shared, {})
+        _shared_keepalive.append(shared)
+        if k and shared.shard[1] > shared.shard[0]:
+            last_stats.update(eng.bfs.stats())
     else:
         out, _, stats = _dev.geodesic_embed_host(_edge_index_of(data), int(data.num_nodes), data.anchor_nodes,
                                                  x, SYMMETRIZE)
