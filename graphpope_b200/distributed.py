@@ -95,6 +95,9 @@ def sharded_geodesic_features(engine, edge_index: torch.Tensor, anchors: torch.T
         out = torch.empty((n, f + k), dtype=torch.float32, device="cuda")
     if world == 1:
         return engine.run(edge_index, anchors, x, out)
+    if k % world:
+        raise ValueError(f"the all-gather path needs num_anchor_nodes={k} divisible by the world size {world}; "
+                         "PeerAssembly pads a ragged K itself")
     lo, hi = shard_bounds(k, world, rank)
     engine.csr.build(edge_index)
     engine.bfs.run(anchors[lo:hi].contiguous())

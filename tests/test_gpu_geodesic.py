@@ -568,3 +568,25 @@ def test_hop1_push_direction_matches_pull_and_oracle(dev, k, symmetrize):
         st = eng.bfs.stats()
         assert np.array_equal(hops, want), push
         assert st["push_levels"] == (1 if push else 0) and st["pull_levels"] + st["push_levels"] == st["levels_run"]
+
+
+@pytest.mark.parametrize("k", [50, 3, 64])
+def test_exchange_entry_pads_a_ragged_anchor_count(dev, k):
+    """PushExchange.run (gp_geodesic_run_exchange) with an anchor count that is not a multiple of 8: the shard is
+    padded with repeats of the last anchor, computed into a scratch matrix and the real columns copied out.  One rank
+    here (the padding logic is per rank); three calls = eager, captured, replayed."""
+    from graphpope_b200 import distributed as gpd
+    from oracle import cbfs, geodesic
+    n, f = 4000, 12
+    ei = np.concatenate([synth.chung_lu_symmetric(n, 24000, 2.2, seed=3), synth.random_digraph(n, 900, seed=4)], axis=1)
+    anchors = np.random.default_rng(k).integers(0, n, k)
+    x = np.random.default_rng(1).standard_normal((n, f)).astype(np.float32)
+    want = geodesic.concat_features(x, cbfs.geodesic_features(ei, n, anchors))
+    eng = dev.GeodesicEngine(n, ei.shape[1], -(-k // 8) * 8)
+    xch = gpd.PushExchange(eng, world=1, rank=0)
+    ei_d, a_d, x_d = torch.as_tensor(ei).cuda(), torch.as_tensor(anchors).cuda(), torch.as_tensor(x).cuda()
+    for _ in range(3):
+        out, flag = xch.run(ei_d, a_d, x_d)
+        assert flag.item() == 0
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    xch.close()
