@@ -363,6 +363,7 @@ def secondary_c4(dev, gpd, synth, utils, ei, ei_d, shape, world, rank, dist, bar
         torch.cuda.synchronize()
         sample_s = time.perf_counter() - t0
         a_d = torch.as_tensor(anchors).cuda()
+        barrier()  # the samplers' first call differs by seconds between ranks; the exchange waits only so long for a peer
         for _ in range(3):
             sharded_device_step(dev, gpd, peer, engine, ei_d, a_d, x_d, out_d, world)
         barrier()
@@ -414,6 +415,7 @@ def secondary_c5(dev, gpd, synth, world, rank, local_rank, dist, barrier, peak_g
     peer = gpd.PeerAssembly(engine) if world > 1 else None
     x_d = torch.zeros(n, f, device="cuda")  # x = zeros [N, 100] for C5
     out_d = torch.empty(n, f + k, device="cuda")
+    barrier()
     for _ in range(2):
         sharded_device_step(dev, gpd, peer, engine, ei_d, a_d, x_d, out_d, world)
     barrier()

@@ -55,7 +55,7 @@ constexpr int XCHG_WARPS = XCHG_THREADS / 32;
 constexpr size_t XCHG_FLAG_BYTES = 256;
 constexpr int XCHG_STAGES = 3;
 constexpr int XCHG_STAGE_CAP = 18 * 1024;  // bytes of peer segments per stage
-constexpr long long GP_XCHG_TIMEOUT_CYCLES = 6000000000ll;  // ~3 s at 1.9 GHz
+constexpr long long GP_XCHG_TIMEOUT_CYCLES = 16000000000ll;  // ~8 s at 1.9 GHz
 
 struct XchgParams {
     // local result (gp_msbfs.cu layout)

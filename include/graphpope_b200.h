@@ -226,7 +226,7 @@ int gp_decode_peers(const uint64_t *const *h_rank_ptrs, int32_t num_ranks, int64
  *                           16-byte aligned, ld_out and col_offset multiples of 4.  Replays a CUDA graph.
  *   gp_exchange_status      syncs.  *deep = 1 if some shard had hops > 15 in the last step (the 5-plane format
  *                           cannot hold them: redo the step through gp_msbfs_planes / gp_decode_gathered);
- *                           GP_ERR_CUDA if a peer's flag never arrived (bounded wait, ~3 s).                   */
+ *                           GP_ERR_CUDA if a peer's flag never arrived (bounded wait, ~8 s).                   */
 int gp_exchange_create(gp_msbfs_t *bfs, int32_t world, int32_t rank, gp_exchange_t **out);
 int gp_exchange_ipc_export(gp_exchange_t *xchg, uint8_t *handle64);
 int gp_exchange_local_ptr(gp_exchange_t *xchg, void **d_ptr);
