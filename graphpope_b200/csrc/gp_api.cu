@@ -202,7 +202,10 @@ HostCtx &default_ctx()
 
 int ensure_ctx(HostCtx &c, int64_t n, int64_t e, int64_t k, uint32_t flags)
 {
-    if (c.stream == nullptr) GP_CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    if (c.stream == nullptr) {
+        GP_TRY(gp_device_info(nullptr, nullptr, nullptr, nullptr, 0));  // GP_ERR_NO_DEVICE, not a raw runtime error
+        GP_CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    }
     if (c.n == n && c.flags == flags && e <= c.e_cap && k <= c.k_cap) return GP_OK;
     c.release();
     GP_TRY(gp_csr_create(n, e, flags, &c.csr));

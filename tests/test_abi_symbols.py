@@ -63,3 +63,26 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "/root/reference" not in text, f
+
+
+def test_plain_c_caller_compiles_and_runs(tmp_path):
+    """examples/embed_host.c: the boundary from strict C99, no Python / torch in the process.  With a B200 it checks
+    its own rows (exit 0); without one the library must answer GP_ERR_NO_DEVICE cleanly (exit 2), not crash."""
+    import shutil
+    import subprocess
+
+    from graphpope_b200 import _lib
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / "embed_host")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "embed_host.c"), "-L", libdir, "-lgraphpope_b200",
+                    f"-Wl,-rpath,{libdir}", "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert "graphpope_b200 ABI 1" in r.stdout
+    if r.returncode == 0:
+        assert "6 nodes x (2 features + 4 anchors): ok" in r.stdout
+    else:
+        assert r.returncode == 2 and "no CUDA device" in r.stdout, r.stdout + r.stderr
