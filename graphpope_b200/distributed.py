@@ -187,15 +187,26 @@ class SharedHostMatrix:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         nbytes = max(4 * self.rows * self.cols, mmap.PAGESIZE)
         self.nbytes = -(-nbytes // mmap.PAGESIZE) * mmap.PAGESIZE
-        box = [name or "graphpope_%s" % uuid.uuid4().hex]
-        if self.world > 1:
-            dist.broadcast_object_list(box, src=0, group=group)
-        self.path = os.path.join("/dev/shm", box[0])
+        box = [os.path.basename(name) if name else "graphpope_%s" % uuid.uuid4().hex, None]
         if self.rank == 0:
-            fd = os.open(self.path, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
-            os.ftruncate(fd, self.nbytes)
+            # rank 0 creates the file and RESERVES its pages before anyone maps it: a full /dev/shm is an OSError
+            # here (reported on every rank), not a SIGBUS at the first touch inside cudaHostRegister
+            path = os.path.join("/dev/shm", box[0])
+            try:
+                fd = os.open(path, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
+                try:
+                    os.posix_fallocate(fd, 0, self.nbytes)
+                except OSError:
+                    os.close(fd)
+                    os.unlink(path)
+                    raise
+            except OSError as err:
+                box[1] = f"{path}: {err}"
         if self.world > 1:
-            dist.barrier(group=group)
+            dist.broadcast_object_list(box, src=0, group=group)  # also orders "created" before the other ranks' open
+        if box[1] is not None:
+            raise RuntimeError(f"cannot create the node-shared matrix ({self.nbytes} bytes): {box[1]}")
+        self.path = os.path.join("/dev/shm", box[0])
         if self.rank != 0:
             fd = os.open(self.path, os.O_RDWR)
         self._mm = mmap.mmap(fd, self.nbytes, mmap.MAP_SHARED, mmap.PROT_READ | mmap.PROT_WRITE)

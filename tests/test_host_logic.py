@@ -219,3 +219,22 @@ def test_block_cache_key_and_hit_path(tmp_path, monkeypatch):
     monkeypatch.setattr(utils, "sample_anchor_nodes", lambda **kw: [0, 2])
     out = utils.attach_distance_embedding(d, "toy", 2, "stochastic", None, 4)
     assert len(calls) == 2 and out.shape == (3, 4) and torch.equal(out[:, 2:], a)
+
+
+def test_shared_matrix_that_does_not_fit_is_an_error_not_a_crash():
+    """SharedHostMatrix reserves its pages when it creates the file: asking for more than /dev/shm holds raises."""
+    import os
+    import shutil
+
+    from graphpope_b200 import distributed as gpd
+
+    total = shutil.disk_usage("/dev/shm").total
+    rows = total // (4 * 1024) + (1 << 20)  # 1024 columns: ~4 GiB more than the whole file system (refused up front)
+    before = set(os.listdir("/dev/shm"))
+    with pytest.raises(RuntimeError, match="node-shared matrix"):
+        gpd.SharedHostMatrix(rows, 1024, register=False)
+    assert set(os.listdir("/dev/shm")) == before  # nothing left behind
+    m = gpd.SharedHostMatrix(5, 7, register=False)  # single process, no process group
+    m.tensor.fill_(2.0)
+    assert m.tensor.shape == (5, 7) and float(m.tensor.sum()) == 70.0 and not os.path.exists(m.path)
+    m.close()
