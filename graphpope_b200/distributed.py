@@ -376,13 +376,16 @@ class PushExchange:
         f = 0 if x is None else x.size(1)
         if out is None:
             out = torch.empty((n, f + k), dtype=torch.float32, device="cuda")
-        key = (anchors.data_ptr(), k)
-        if key not in self._pad:  # stable tensors = stable graph keys; a ragged K is padded with repeats of the last anchor
+        # stable tensors = stable graph keys; a ragged K is padded with repeats of the last anchor.  The entry keeps
+        # `anchors` itself: its storage cannot be freed and handed to another tensor while the key is live, and an
+        # in-place update (version counter) re-derives the padded copy
+        key = (anchors.data_ptr(), k, anchors._version)
+        if key not in self._pad:
             padded, per = pad_anchors(anchors, self.world)
             shard = padded[self.rank * per:(self.rank + 1) * per].contiguous()
             tmp = None if padded.numel() == k else torch.empty((n, f + padded.numel()), dtype=torch.float32, device="cuda")
-            self._pad = {key: (shard, per, tmp)}
-        shard, per, tmp = self._pad[key]
+            self._pad = {key: (shard, per, tmp, anchors)}
+        shard, per, tmp, _ = self._pad[key]
         dst = out if tmp is None else tmp
         edge_index = edge_index.contiguous()
         if x is not None and x.stride(1) != 1:
