@@ -238,3 +238,44 @@ def test_shared_matrix_that_does_not_fit_is_an_error_not_a_crash():
     m.tensor.fill_(2.0)
     assert m.tensor.shape == (5, 7) and float(m.tensor.sum()) == 70.0 and not os.path.exists(m.path)
     m.close()
+
+
+@pytest.mark.parametrize("workers", [1, 2, 3])
+def test_pool_helper_shims_host_logic(golden_small, monkeypatch, workers):
+    """The reference-shaped halves of the pool helpers (utils.py:64-114) — node slices in float arithmetic, ordered
+    merge, Python ``float`` / literal ``int 0`` entries — against what the unmodified reference returned
+    (reference_shims.npz).  The hop matrix comes from the oracle here (no GPU); tests/test_gpu_shims.py runs the same
+    checks with the device sweep underneath."""
+    import os
+
+    import networkx as nx
+
+    from conftest import GOLDEN_DIR, micro_names
+    from oracle import geodesic as og
+
+    shims = np.load(os.path.join(GOLDEN_DIR, "reference_shims.npz"))
+
+    def oracle_hops(G, anchor_nodes):
+        ei, n = utils._graph_to_edge_index(G)
+        return og.t2_bfs_csr_hops(ei.numpy(), n, [int(a) for a in anchor_nodes])
+
+    monkeypatch.setattr(utils, "_hops_of_graph", oracle_hops)
+
+    def check(got, keys, rows, is_int):
+        assert list(got.keys()) == keys.tolist()
+        for k, want_row, int_row in zip(keys.tolist(), rows, is_int):
+            assert [type(v) for v in got[k]] == [int if i else float for i in int_row]
+            assert got[k] == want_row.tolist()
+
+    for name in micro_names(golden_small):
+        n = int(golden_small[f"micro/{name}/n"])
+        ei = golden_small[f"micro/{name}/edges"]
+        G = nx.DiGraph()
+        G.add_nodes_from(range(n))
+        G.add_edges_from(zip(ei[0].tolist(), ei[1].tolist()))
+        anchors = [int(a) for a in golden_small[f"micro/{name}/anchors"]]
+        check(utils.all_pairs_shortest_path_length_parallel(G, anchors, workers), shims[f"{name}/all_pairs_keys/{workers}"],
+              shims[f"{name}/all_pairs_rows/{workers}"], shims[f"{name}/all_pairs_is_int/{workers}"])
+        part = shims[f"{name}/partition"]
+        check(utils.shortest_path_length(G, anchors, part.tolist()), part, shims[f"{name}/partition_rows"],
+              shims[f"{name}/partition_is_int"])
