@@ -106,7 +106,7 @@ def run_reference_arm(args, shape, ei, anchors, e_unique):
     the GPU box) on all host threads; every step is a bounded row sample, `value` is the rate it measured."""
     cores = min(os.cpu_count() or 1, 32)
     n = shape.num_nodes
-    total_budget = 150.0
+    total_budget = float(os.environ.get("GP_BENCH_REF_BUDGET_S", "150"))  # tests shrink it; the default fills ~4 minutes
     per_step = max(2.0, total_budget / max(1, args.steps + args.warmup))
     rates, secs, rows = [], [], 0
     for i in range(args.warmup + args.steps):
