@@ -500,6 +500,17 @@ print(json.dumps({"import_s": t_import, "cold_ms": cold * 1e3, "warm_pageable_ms
 """
 
 
+def guarded(fn, *a):
+    """A secondary line that dies (out of memory on a shared box, ...) must not take the headline line with it: the
+    error is reported in its place and the line is marked unchecked."""
+    try:
+        return fn(*a)
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        traceback.print_exc()
+        return {"error": f"{type(e).__name__}: {e}"[:400], "parity_checked": False}, False
+
+
 def cold_call():
     """Fresh process: the first utils.Graphpope call on PAGEABLE tensors (what main.py:94-98 does once per process)."""
     try:
@@ -738,10 +749,10 @@ def main():
     secondary, sec_ok = {}, True
     want = set() if args.no_secondary else {s.strip() for s in args.secondary.split(",") if s.strip()}
     if "c3" in want and world == 1:
-        secondary["C3_node2vec_block"], ok = secondary_c3(dev, synth, peak, peaks)
+        secondary["C3_node2vec_block"], ok = guarded(secondary_c3, dev, synth, peak, peaks)
         sec_ok &= ok
     if "c4" in want:
-        res, ok = secondary_c4(dev, gpd, synth, utils, ei, ei_d, shape, world, rank, dist, barrier, flush_l2, peak)
+        res, ok = guarded(secondary_c4, dev, gpd, synth, utils, ei, ei_d, shape, world, rank, dist, barrier, flush_l2, peak)
         secondary["C4_flickr_k1024_centrality_anchors"] = res
         sec_ok &= ok
     if "cold" in want and world == 1 and rank == 0:
@@ -749,7 +760,7 @@ def main():
     if "c5" in want:
         del flush, flush_r, out_d, x_d
         torch.cuda.empty_cache()
-        res, ok = secondary_c5(dev, gpd, synth, world, rank, local_rank, dist, barrier, peak)
+        res, ok = guarded(secondary_c5, dev, gpd, synth, world, rank, local_rank, dist, barrier, peak)
         secondary["C5_products_k4096"] = res
         sec_ok &= ok
 

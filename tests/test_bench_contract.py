@@ -40,3 +40,14 @@ def test_reference_arm_prints_the_contract_line():
                        capture_output=True, text=True, timeout=600, cwd=ROOT,
                        env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
     assert r.returncode == 0 and not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_a_failing_secondary_line_is_reported_not_fatal(capsys):
+    import bench
+
+    def boom(x):
+        raise RuntimeError("CUDA out of memory (simulated) %d" % x)
+
+    res, ok = bench.guarded(boom, 7)
+    assert ok is False and res["parity_checked"] is False and "simulated) 7" in res["error"]
+    assert bench.guarded(lambda a, b: ({"v": a + b}, True), 1, 2) == ({"v": 3}, True)
