@@ -306,6 +306,20 @@ def secondary_c3(dev, synth, peak_gbs, peaks):
                                "bf16 peak at the fastest mode; ncu summary under profiles/" %
                                (100 * max(m["tflops_bf16x3"] for m in res["modes"].values()) /
                                 float(peaks.get("bf16_tflops", 1664.7)), float(peaks.get("bf16_tflops", 1664.7))))
+    # the reference's scikit-learn path (pairwise + MinMaxScaler, utils.py:174-176) on the host cores
+    try:
+        from oracle import node2vec as onv
+        emb_h, c_h = emb.cpu().numpy(), centres.cpu().numpy()
+        cpu = {}
+        for mode in ("euclidean", "distance"):
+            t0 = time.perf_counter()
+            onv.node2vec_block(emb_h, c_h, mode)
+            cpu[mode + "+minmax_ms"] = (time.perf_counter() - t0) * 1e3
+        res["cpu_sklearn_path"] = dict(cpu, cores=os.cpu_count(), kind="port",
+                                       note="oracle restatement of sklearn pairwise + MinMaxScaler on host arrays, "
+                                            "whatever threads BLAS takes; a reported baseline, not the target")
+    except Exception as e:  # noqa: BLE001
+        res["cpu_sklearn_path"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     res["parity_checked"] = ok_all
     return res, ok_all
 
