@@ -813,6 +813,8 @@ def main():
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": headline_config(shape, world, e_unique),
             "details": {"parallelism": f"anchor-shard x{world}",
+                        "step_ms_rank0": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)),
+                                          "max": float(np.max(step_ms))},
                         "l2": "between steps (untimed): 256 MiB buffer written, then a second 256 MiB buffer read, so the "
                               "L2 holds neither the previous step's lines nor dirty lines to write back",
                         "step": "csr build + ms-bfs + fused normalise/concat epilogue" +
