@@ -19,6 +19,8 @@
  *   - Data-dependent failures detected on the device (edge index out of range,
  *     anchor out of range, hop distance not representable in uint16) are
  *     latched in the handle and reported by the next syncing call.
+ *   - The header is strict C99; examples/embed_host.c is a complete caller of the
+ *     one-call host entry with its expected rows (built and run by the test suite).
  */
 #ifndef GRAPHPOPE_B200_H
 #define GRAPHPOPE_B200_H
@@ -257,7 +259,8 @@ int gp_normalize_into(const uint16_t *d_dist, int64_t num_nodes, int64_t num_anc
  * runs the MS-BFS and the epilogue, and copies the feature block back into
  * h_out[:, col_offset:col_offset+K] (row pitch ld_out floats).  If h_x != NULL
  * its F columns are copied into h_out[:, 0:F] on the host while the GPU works.
- * h_hops (optional, may be NULL) receives the uint16 hop matrix [N, K].  syncs. */
+ * h_hops (optional, may be NULL) receives the uint16 hop matrix [N, K].  syncs.
+ * GP_ERR_NO_DEVICE when the process sees no CUDA device (there is no CPU fallback). */
 int gp_geodesic_embed_host(const int64_t *h_edge_index, int64_t num_edges, int64_t num_nodes,
                            uint32_t csr_flags, const int64_t *h_anchors, int64_t num_anchors,
                            const float *h_x, int64_t num_features,
