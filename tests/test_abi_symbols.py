@@ -86,3 +86,43 @@ def test_plain_c_caller_compiles_and_runs(tmp_path):
         assert "6 nodes x (2 features + 4 anchors): ok" in r.stdout
     else:
         assert r.returncode == 2 and "no CUDA device" in r.stdout, r.stdout + r.stderr
+
+
+def test_sass_is_sm_100a_with_the_blackwell_paths_it_claims():
+    """The in-tree library holds sm_100a code only, and the instructions DESIGN.md names are really in it:
+    tcgen05.mma / commit / ld (cdist), the bulk-copy engine + mbarriers (exchange, x copy), 256-bit loads (MS-BFS)."""
+    import shutil
+    import subprocess
+
+    from graphpope_b200 import _lib
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("no cuobjdump")
+    elfs = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    archs = set(re.findall(r"\.(sm_\w+)\.cubin", elfs))
+    assert archs == {"sm_100a"}, archs
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    per_kernel, cur = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per_kernel[cur] = set()
+            continue
+        for mnem in ("UTCHMMA", "UTCBAR", "LDTM", "UBLKCP", "SYNCS", "LDG.E.ENL2.256", "HMMA.", "WGMMA"):
+            if cur is not None and mnem in line:
+                per_kernel[cur].add(mnem)
+
+    def used_by(fragment):
+        got = set()
+        for name, mn in per_kernel.items():
+            if fragment in name:
+                got |= mn
+        return got
+
+    assert {"UTCHMMA", "UTCBAR", "LDTM", "SYNCS"} <= used_by("cdist_kernel")
+    assert {"UBLKCP", "SYNCS"} <= used_by("exchange_decode_kernel")
+    assert {"UBLKCP", "SYNCS"} <= used_by("xcopy_tma_kernel")
+    assert "LDG.E.ENL2.256" in used_by("msbfs_kernel")
+    assert not any("WGMMA" in mn for mn in per_kernel.values())  # sm_90a-only; must not appear
