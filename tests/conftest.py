@@ -36,5 +36,13 @@ def golden_eigenvector():
     return np.load(os.path.join(GOLDEN_DIR, "reference_eigenvector.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_deep_hub():
+    return np.load(os.path.join(GOLDEN_DIR, "reference_deep_hub.npz"))
+
+
+DEEP_HUB_NAMES = ("deep_chain", "hub_star", "lollipop")
+
+
 def micro_names(golden):
     return sorted({k.split("/")[1] for k in golden.files if k.startswith("micro/")})

@@ -7,6 +7,7 @@ Run in the build container only (needs /root/reference):
     python tests/golden/generate_golden.py --betweenness   # ONLY reference_betweenness.npz (seconds)
     python tests/golden/generate_golden.py --eigenvector   # ONLY reference_eigenvector.npz (seconds)
     python tests/golden/generate_golden.py --shims         # ONLY reference_shims.npz (seconds)
+    python tests/golden/generate_golden.py --deep-hub      # ONLY reference_deep_hub.npz (~1 min)
 
 The reference has no tests or golden vectors of its own, so these
 files ARE the parity pins: every value below is produced by
@@ -134,14 +135,62 @@ def shims_fixture(utils):
     print("wrote reference_shims.npz with", len(out), "arrays")
 
 
+def deep_hub_graphs():
+    """name -> (num_nodes, edge_index [2,E], anchors): the shapes that take the special paths of the device kernels —
+    hop counts far beyond the 15 one-hot result arrays (deep bit planes), rows beyond 128 edges (hub chunks, CTA row
+    sort), and a mix of both with more than 64 anchors (two lane words, repeated anchors)."""
+    out = {}
+    n = 5000  # the graph of tests/test_gpu_geodesic.py::test_deep_path_uses_many_distance_planes
+    out["deep_chain"] = (n, np.stack([np.arange(n - 1), np.arange(1, n)]).astype(np.int64),
+                         np.array([n - 1, 0, 2500], dtype=np.int64))
+    n = 6000  # the graph of test_hub_rows_take_the_cta_and_warp_paths
+    e = [(0, i) for i in range(1, 5001)] + [(i, 0) for i in range(1, 5001)]
+    e += [(5001, i) for i in range(5002, 5302)] + [(i, 5001) for i in range(5002, 5302)]
+    e += [(i, i + 1) for i in range(5302, 5999)] + [(5001, 0), (5500, 5001)]
+    out["hub_star"] = (n, np.asarray(e, dtype=np.int64).T, np.array([0, 17, 5001, 5999, 5302, 5100, 17], dtype=np.int64))
+    # lollipop: a two-way chain of 60 nodes whose last node is a two-way hub of 200 leaves, one-way shortcuts, an
+    # isolated node; 70 anchors with repeats
+    n = 60 + 200 + 1
+    e = [(i, i + 1) for i in range(59)] + [(i + 1, i) for i in range(59)]
+    e += [(59, j) for j in range(60, 260)] + [(j, 59) for j in range(60, 260)]
+    e += [(0, 30), (100, 5), (200, 201), (201, 200), (7, 7), (0, 1)]
+    rng = np.random.default_rng(77)
+    anchors = np.concatenate([[0, 59, 60, 259, 260, 30, 30], rng.integers(0, n, 63)]).astype(np.int64)
+    out["lollipop"] = (n, np.asarray(e, dtype=np.int64).T, anchors)
+    return out
+
+
+def deep_hub_fixture(utils):
+    """reference_deep_hub.npz: utils.get_geodesic_distance_vector (utils.py:116-126, pool of 2 included) of the
+    unmodified reference on the graphs above (about a minute: N*K nx.shortest_path calls on a 5000-hop chain)."""
+    out = {}
+    for name, (n, ei, anchors) in deep_hub_graphs().items():
+        data = RefData(torch.tensor(ei), n)
+        data.anchor_nodes = anchors
+        emb = utils.get_geodesic_distance_vector(data, 2)
+        assert tuple(emb.shape) == (n, anchors.size)
+        out[f"{name}/n"] = np.int64(n)
+        out[f"{name}/edge_index"] = ei
+        out[f"{name}/anchors"] = anchors
+        out[f"{name}/embedding"] = emb.numpy().astype(np.float32)
+        out[f"{name}/dtype"] = np.asarray(str(emb.dtype))
+        print(name, "max hops", int(round(1.0 / float(emb[emb > 0].min()) - 1)), "dtype", emb.dtype)
+    np.savez_compressed(os.path.join(HERE, "reference_deep_hub.npz"), **out)
+    print("wrote reference_deep_hub.npz")
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--deep-hub", action="store_true")
     ap.add_argument("--pubmed", action="store_true")
     ap.add_argument("--betweenness", action="store_true")
     ap.add_argument("--eigenvector", action="store_true")
     ap.add_argument("--shims", action="store_true")
     args = ap.parse_args()
     utils = load_reference_utils()
+    if args.deep_hub:
+        deep_hub_fixture(utils)
+        return
     if args.shims:
         shims_fixture(utils)
         return

@@ -122,6 +122,18 @@ def test_micro_graphs_match_reference(dev, golden_small):
         assert np.array_equal(hops, _oracle_hops(ei, n, anchors)), name
 
 
+@pytest.mark.parametrize("name", ["deep_chain", "hub_star"])
+def test_deep_and_hub_graphs_match_reference(dev, golden_deep_hub, name):
+    """Deep bit planes (4999 hops) and hub chunks / CTA row sort (5000- and 300-edge rows) against what the
+    unmodified reference returned for these graphs (reference_deep_hub.npz), bit for bit.  (The third graph of the
+    fixture, both at once with two lane words, is in tests/test_gpu_shims.py.)"""
+    g = golden_deep_hub
+    n, ei, anchors = int(g[f"{name}/n"]), g[f"{name}/edge_index"], g[f"{name}/anchors"]
+    hops, feats, _ = _gpu_hops_and_features(dev, ei, n, anchors)
+    assert np.array_equal(_bits(feats), _bits(g[f"{name}/embedding"]))
+    assert np.array_equal(hops, _oracle_hops(ei, n, anchors))
+
+
 def test_toy_pipeline_matches_reference(dev, golden_small):
     n = int(golden_small["toy/n"])
     ei, x = golden_small["toy/edge_index"], golden_small["toy/x"]

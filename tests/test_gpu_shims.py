@@ -78,3 +78,19 @@ def test_get_geodesic_distance_vector_matches_dict_path(golden_small):
     data.anchor_nodes = anchors
     direct = utils.get_geodesic_distance_vector(data, 2)
     assert direct.dtype == torch.float32 and torch.equal(direct, via_dict.to(torch.float32))
+
+
+def test_lollipop_deep_hub_two_lane_words_matches_reference():
+    """reference_deep_hub.npz/lollipop: 45 hops (deep bit planes), a 201-edge row (hub chunks) and 70 anchors with
+    repeats (two lane words, ragged decode) in one graph, against the unmodified reference's
+    get_geodesic_distance_vector, bit for bit, through the host entry and through the device engine."""
+    import torch
+    from graphpope_b200 import device as dev
+    g = np.load(os.path.join(GOLDEN_DIR, "reference_deep_hub.npz"))
+    n, ei, anchors, want = int(g["lollipop/n"]), g["lollipop/edge_index"], g["lollipop/anchors"], g["lollipop/embedding"]
+    out, _, stats = dev.geodesic_embed_host(torch.as_tensor(ei), n, anchors, None, False)
+    assert stats["max_level"] == 45
+    assert np.array_equal(out.numpy().view(np.uint32), want.view(np.uint32))
+    eng = dev.GeodesicEngine(n, ei.shape[1], len(anchors))
+    feats = eng.run(torch.as_tensor(ei).cuda(), torch.as_tensor(anchors).cuda(), None)
+    assert np.array_equal(feats.cpu().numpy().view(np.uint32), want.view(np.uint32))

@@ -117,3 +117,19 @@ def test_node_slices_cover_range():
             sl = g.node_slices(n, w)
             assert sl[0][0] == 0 and sl[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+
+
+@pytest.mark.parametrize("name", ["deep_chain", "hub_star", "lollipop"])
+def test_deep_and_hub_graphs_match_the_reference(golden_deep_hub, name):
+    """4999-hop chain, 5000-leaf star + 300-leaf hub, lollipop with 70 anchors: what the unmodified reference's
+    get_geodesic_distance_vector returned (tests/golden/generate_golden.py --deep-hub), bit for bit."""
+    gd = golden_deep_hub
+    n, ei, anchors = int(gd[f"{name}/n"]), gd[f"{name}/edge_index"], gd[f"{name}/anchors"]
+    want = gd[f"{name}/embedding"]
+    assert str(gd[f"{name}/dtype"]) == "torch.float32"
+    hops = cbfs.bfs_hops(cbfs.InCsr(ei, n), anchors)
+    got = cbfs.normalise(hops)
+    assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(g.t2_bfs_csr_hops(ei, n, anchors), hops)
+    deepest = {"deep_chain": 4999, "hub_star": 697, "lollipop": 45}[name]
+    assert int(hops[hops != g.UNREACHABLE_U16].max()) == deepest
